@@ -1,6 +1,6 @@
 // jf_gemm.cuh — the weight-streaming "skinny" GEMM at the heart of one Jacobi iteration.
 //
-//   Y[m, n] = sum_k X[m, k] * W[n, k]          m = draft rows (16..256 per MMA), n = output features
+//   Y[m, n] = sum_k X[m, k] * W[n, k]          m = in-flight draft rows (16..256 per MMA), n = output features
 //
 // computed swap-AB on the 5th-gen tensor cores: the WEIGHT tile is the UMMA A operand (M=128 weight rows), the
 // draft rows are the B operand (N = rows padded to 16), so D^T[128 features x rows] lives in TMEM with one
@@ -8,42 +8,51 @@
 // (inference_engine/layers/linear.py:72-73, 149-153; HF Qwen2 q/k/v/o/gate/up/down/lm_head Linear modules
 // called from modeling/cllm2_..._multiblock_lookahead_unified.py:452-463).
 //
-// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
-// Three pipelines: smem ring (full/empty mbarriers), TMEM accumulator double buffer (acc_full/acc_empty), and the
-// persistent unit loop (unit = (n_tile, k_split)), identical in all roles.
+// Warp roles inside the persistent kernel (224 threads):
+//   warp 0  W producer   streams 16 KiB pre-swizzled weight tiles with one bulk copy each; depends on NOTHING but
+//                        free ring slots, so it runs ahead of the grid barriers and keeps HBM busy while the other
+//                        warps are still finishing the previous stage
+//   warp 1  MMA issuer   owns TMEM, one elected lane issues tcgen05.mma
+//   warps 2-5  workers   GEMM epilogues (TMEM -> registers -> global) and every SIMT stage of the forward
+//   warp 6  X producer   loads the activation k-chunks; waits for the grid barrier that publishes them
+// Three pipelines: smem ring (full/empty mbarriers, two arrivals per slot: W and X), TMEM accumulator double buffer
+// (acc_full/acc_empty) and the static unit loop (unit = (n_tile, k_split)), walked identically by all roles.
 #pragma once
 #include "jf_ptx.cuh"
 
 namespace jf {
 
-constexpr int kTileN      = 128;          // weight rows per tile (UMMA M)
-constexpr int kTileK      = 64;           // bf16 per 128-byte swizzle row
-constexpr int kWTileBytes = kTileN * kTileK * 2;   // 16 KiB, contiguous in HBM
-constexpr int kMaxStages  = 16;
-constexpr int kMaxRowsMMA = 256;          // UMMA N limit
-constexpr int kGemmThreads = 192;
+constexpr int kTileN       = 128;          // weight rows per tile (UMMA M)
+constexpr int kTileK       = 64;           // bf16 per 128-byte swizzle row
+constexpr int kWTileBytes  = kTileN * kTileK * 2;   // 16 KiB, contiguous in HBM
+constexpr int kMaxStages   = 12;
+constexpr int kMaxRowsMMA  = 256;          // UMMA N limit
+constexpr int kArgmaxRows  = 256;          // rows one EPI_ARGMAX task may carry (running best lives in smem)
+
+constexpr int kWarpW = 0, kWarpMMA = 1, kWarpWorker0 = 2, kWarpX = 6;
+constexpr int kNumThreads    = 224;
+constexpr int kWorkerThreads = 128;
 
 enum GemmEpilogue : int {
-  EPI_PARTIAL_F32 = 0,   // out[slot][m][n] fp32 partial sums (split-K slot = k_split), deterministic consumer-side reduce
+  EPI_PARTIAL_F32 = 0,   // out[slot][m][n] fp32 partial sums (slot = k_split); the consumer stage reduces in slot order
   EPI_SWIGLU_BF16 = 1,   // two accumulators (gate tile, up tile) -> silu(g)*u -> bf16 in packed-X layout
-  EPI_ARGMAX      = 2,   // LM head: bf16-rounded logits, running (max, lowest index) per row
+  EPI_ARGMAX      = 2,   // LM head: bf16-rounded logits, running (max, lowest index) per row -> atomicMax of packed keys
 };
 
 struct GemmTask {
-  const __nv_bfloat16* W;    // packed weight tiles [n_tiles][k_chunks][128x64 swizzled]
-  const __nv_bfloat16* X;    // packed activations  [k_chunks][xrows_cap x 64 swizzled]
-  void* out;                 // epilogue-specific
-  void* out2;                // epilogue-specific (argmax: indices)
-  const float* bias;         // optional per-feature bias (EPI_PARTIAL: added by slot 0 only)
-  int n_tiles;               // N / 128   (for SWIGLU: number of gate tiles; up tiles follow at +n_tiles)
+  const __nv_bfloat16* W;    // packed weight tiles [n_tiles (x2 for SWIGLU: gate tiles then up tiles)][k_chunks][128x64 sw128]
+  const __nv_bfloat16* X;    // packed activations  [k_chunks][xrows_cap x 64 sw128]
+  void* out;                 // PARTIAL: float*; SWIGLU: packed bf16 X buffer of the next GEMM; ARGMAX: u64 keys [rows]
+  int n_tiles;               // N / 128 (SWIGLU: gate tiles; up tiles follow at +n_tiles)
   int k_chunks;              // K / 64
   int splits;                // split-K factor (1 for SWIGLU / ARGMAX)
-  int M;                     // live rows
+  int M;                     // live rows of this task
+  int x_row0;                // first row inside X / first output row (multiple of 8)
   int xrows_cap;             // row capacity of the packed X buffer
-  int N;                     // out row stride in elements (EPI_PARTIAL) / vocab size (ARGMAX)
-  int M_cap;                 // row capacity of out (slot stride = M_cap * N)
+  int N;                     // PARTIAL: out row stride = real feature count; ARGMAX: vocab size; SWIGLU: intermediate size
+  int M_cap;                 // PARTIAL: row capacity of out (slot stride = M_cap * N)
   int epilogue;
-  int out_kchunks_rows;      // SWIGLU: xrows_cap of the destination packed buffer
+  int out_rows_cap;          // SWIGLU: xrows_cap of the destination packed buffer
 };
 
 struct GemmSmem {
@@ -53,13 +62,10 @@ struct GemmSmem {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad_;
-  float* best_val;           // [4 epilogue warps][argmax_cap] running best bf16-rounded logit (EPI_ARGMAX)
-  int*   best_idx;           // [4][argmax_cap] its vocab index (lowest index wins ties)
-  int    argmax_cap;
-  int    pad2_;
+  unsigned long long best[4][kArgmaxRows];   // EPI_ARGMAX running best key per epilogue warp and row
 };
 
-struct PipeState {      // smem ring position; persists across tasks inside a persistent kernel
+struct PipeState {      // smem ring position; persists across tasks
   uint32_t stage = 0, phase = 0;
   __device__ __forceinline__ void advance(uint32_t nstages) {
     if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -72,17 +78,32 @@ struct AccState {       // TMEM accumulator ring position
   }
 };
 
-__device__ __forceinline__ int round_up16(int x) { return (x + 15) & ~15; }
+__host__ __device__ __forceinline__ int round_up16(int x) { return (x + 15) & ~15; }
 
-// One-time setup by the whole CTA.  smem_tiles must be 1024-byte aligned.
+// Packed argmax key: larger value wins; on equal values the LOWER index wins (torch.argmax on CPU returns the first
+// maximum; reference: modeling/..._unified.py:476).  Values are bf16-rounded logits, never NaN for finite weights.
+__host__ __device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(v);
+#else
+  uint32_t u; memcpy(&u, &v, 4);
+#endif
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
+}
+__host__ __device__ __forceinline__ int argmax_key_index(unsigned long long key) {
+  return (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+}
+
+// One-time setup by the whole CTA.
 __device__ __forceinline__ void gemm_setup(GemmSmem* gs, int nstages) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nstages; ++i) { mbar_init(&gs->full[i], 1); mbar_init(&gs->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&gs->acc_full[i], 1); mbar_init(&gs->acc_empty[i], 128); }
+    for (int i = 0; i < nstages; ++i) { mbar_init(&gs->full[i], 2); mbar_init(&gs->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&gs->acc_full[i], 1); mbar_init(&gs->acc_empty[i], kWorkerThreads); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&gs->tmem_base, 512);
+  if (warp == kWarpMMA) tmem_alloc(&gs->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -90,197 +111,225 @@ __device__ __forceinline__ void gemm_setup(GemmSmem* gs, int nstages) {
 __device__ __forceinline__ void gemm_teardown(GemmSmem* gs) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == 1) tmem_dealloc(gs->tmem_base, 512);
+  if ((threadIdx.x >> 5) == kWarpMMA) tmem_dealloc(gs->tmem_base, 512);
 }
 
-// Bytes of one ring slot for a given padded row count.
-__host__ __device__ __forceinline__ int gemm_slot_bytes(int mpad, bool dual) {
-  int x = (mpad * 128 + 1023) & ~1023;
-  return (dual ? 2 : 1) * kWTileBytes + x;
+// Bytes of one ring slot: one weight tile + the X k-chunk for up to mpad_max rows.
+__host__ __device__ __forceinline__ int gemm_slot_bytes(int mpad_max) {
+  return kWTileBytes + ((mpad_max * 128 + 1023) & ~1023);
 }
 
-// Runs one GEMM task cooperatively over `nctas` CTAs (this CTA has index `cta`).  All threads of the CTA call it.
-// smem_tiles: ring storage (nstages * slot_bytes, 1024-aligned).
-__device__ void gemm_run(const GemmTask& t, GemmSmem* gs, uint8_t* smem_tiles, int nstages, int slot_bytes,
-                         int cta, int nctas, PipeState& pipe, AccState& acc) {
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
+struct UnitRange { int n_tile, split, k0, k1; };
+__device__ __forceinline__ UnitRange unit_range(const GemmTask& t, int u) {
+  UnitRange r;
+  r.n_tile = u / t.splits;
+  r.split = u - r.n_tile * t.splits;
+  r.k0 = (int)(((long long)r.split * t.k_chunks) / t.splits);
+  r.k1 = (int)(((long long)(r.split + 1) * t.k_chunks) / t.splits);
+  return r;
+}
+__device__ __forceinline__ int task_rows_mma(const GemmTask& t) { return t.epilogue == EPI_SWIGLU_BF16 ? 128 : kMaxRowsMMA; }
+
+// ---- warp 0, lane 0 ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gemm_produce_w(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
+                                               int slot_bytes, int cta, int nctas, PipeState& pipe) {
   const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
   const int units = t.n_tiles * t.splits;
-  const int rows_mma = dual ? 128 : kMaxRowsMMA;   // dual mode splits a 256-column accumulator buffer in two
+  const int rows_mma = task_rows_mma(t);
   const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
-  const uint32_t wbytes = (dual ? 2u : 1u) * kWTileBytes;
+  for (int u = cta; u < units; u += nctas) {
+    const UnitRange r = unit_range(t, u);
+    for (int mt = 0; mt < m_tiles; ++mt) {
+      for (int k = r.k0; k < r.k1; ++k) {
+        mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
+        mbar_expect_tx(&gs->full[pipe.stage], kWTileBytes);
+        bulk_g2s(tiles + (size_t)pipe.stage * slot_bytes,
+                 t.W + ((size_t)r.n_tile * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes, &gs->full[pipe.stage]);
+        pipe.advance(nstages);
+        if (dual) {
+          mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
+          mbar_expect_tx(&gs->full[pipe.stage], kWTileBytes);
+          bulk_g2s(tiles + (size_t)pipe.stage * slot_bytes,
+                   t.W + ((size_t)(r.n_tile + t.n_tiles) * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes,
+                   &gs->full[pipe.stage]);
+          pipe.advance(nstages);
+        }
+      }
+    }
+  }
+}
 
-  if (warp == 0) {
-    // ===================== producer: one elected lane streams W tiles (+ the matching X k-chunk) =============
-    if (lane == 0) {
-      for (int u = cta; u < units; u += nctas) {
-        const int n_tile = u / t.splits, split = u % t.splits;
-        const int k0 = (int)(((long long)split * t.k_chunks) / t.splits);
-        const int k1 = (int)(((long long)(split + 1) * t.k_chunks) / t.splits);
-        for (int mt = 0; mt < m_tiles; ++mt) {
-          const int m0 = mt * rows_mma;
-          const int mpad = round_up16(min(t.M - m0, rows_mma));
-          const uint32_t xbytes = (uint32_t)mpad * 128u;
-          for (int k = k0; k < k1; ++k) {
-            mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
-            uint8_t* slot = smem_tiles + (size_t)pipe.stage * slot_bytes;
-            mbar_expect_tx(&gs->full[pipe.stage], wbytes + xbytes);
-            bulk_g2s(slot, t.W + ((size_t)n_tile * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes,
-                     &gs->full[pipe.stage]);
-            if (dual)
-              bulk_g2s(slot + kWTileBytes,
-                       t.W + ((size_t)(n_tile + t.n_tiles) * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes,
-                       &gs->full[pipe.stage]);
-            bulk_g2s(slot + wbytes, t.X + ((size_t)k * t.xrows_cap + m0) * kTileK, xbytes, &gs->full[pipe.stage]);
-            pipe.advance(nstages);
-          }
+// ---- warp 6, lane 0 (after it has seen the grid barrier that publishes X) ----------------------------------------
+__device__ __forceinline__ void gemm_produce_x(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
+                                               int slot_bytes, int cta, int nctas, PipeState& pipe) {
+  const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
+  const int units = t.n_tiles * t.splits;
+  const int rows_mma = task_rows_mma(t);
+  const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
+  for (int u = cta; u < units; u += nctas) {
+    const UnitRange r = unit_range(t, u);
+    for (int mt = 0; mt < m_tiles; ++mt) {
+      const int m0 = mt * rows_mma;
+      const uint32_t xbytes = (uint32_t)round_up16(min(t.M - m0, rows_mma)) * 128u;
+      for (int k = r.k0; k < r.k1; ++k) {
+        mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
+        mbar_expect_tx(&gs->full[pipe.stage], xbytes);
+        bulk_g2s(tiles + (size_t)pipe.stage * slot_bytes + kWTileBytes,
+                 t.X + ((size_t)k * t.xrows_cap + t.x_row0 + m0) * kTileK, xbytes, &gs->full[pipe.stage]);
+        pipe.advance(nstages);
+        if (dual) {   // the "up" slot reuses the gate slot's X chunk: plain arrival keeps the count at two
+          mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
+          mbar_arrive(&gs->full[pipe.stage]);
+          pipe.advance(nstages);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: one elected lane =========================================================
-    if (lane == 0) {
-      const uint32_t tmem = gs->tmem_base;
-      for (int u = cta; u < units; u += nctas) {
-        const int split = u % t.splits;
-        const int k0 = (int)(((long long)split * t.k_chunks) / t.splits);
-        const int k1 = (int)(((long long)(split + 1) * t.k_chunks) / t.splits);
-        for (int mt = 0; mt < m_tiles; ++mt) {
-          const int m0 = mt * rows_mma;
-          const int mpad = round_up16(min(t.M - m0, rows_mma));
-          const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)mpad);
-          mbar_wait(&gs->acc_empty[acc.buf], acc.phase ^ 1);
-          tc_fence_after();
-          // accumulator buffer b occupies columns [b*256, b*256+256); dual mode splits it 128 + 128
-          const uint32_t d0 = tmem + acc.buf * 256u;
-          for (int k = k0; k < k1; ++k) {
-            mbar_wait(&gs->full[pipe.stage], pipe.phase);
-            tc_fence_after();
-            const uint32_t sbase = smem_u32(smem_tiles + (size_t)pipe.stage * slot_bytes);
-            const uint32_t xbase = sbase + wbytes;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {   // 4 x UMMA_K(16) = one 64-wide k-chunk; +32 B inside the swizzle atom
-              const uint64_t db = umma_desc_sw128(xbase + kk * 32);
-              umma_bf16(d0, umma_desc_sw128(sbase + kk * 32), db, idesc, (k > k0 || kk > 0) ? 1u : 0u);
-              if (dual)
-                umma_bf16(d0 + 128u, umma_desc_sw128(sbase + kWTileBytes + kk * 32), db, idesc,
-                          (k > k0 || kk > 0) ? 1u : 0u);
-            }
-            umma_commit(&gs->empty[pipe.stage]);   // frees the smem slot when these MMAs retire
-            pipe.advance(nstages);
-          }
-          umma_commit(&gs->acc_full[acc.buf]);
-          acc.advance();
+  }
+}
+
+// ---- warp 1, lane 0 -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gemm_issue_mma(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
+                                               int slot_bytes, int cta, int nctas, PipeState& pipe, AccState& acc) {
+  const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
+  const int units = t.n_tiles * t.splits;
+  const int rows_mma = task_rows_mma(t);
+  const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
+  const uint32_t tmem = gs->tmem_base;
+  for (int u = cta; u < units; u += nctas) {
+    const UnitRange r = unit_range(t, u);
+    for (int mt = 0; mt < m_tiles; ++mt) {
+      const int m0 = mt * rows_mma;
+      const int mpad = round_up16(min(t.M - m0, rows_mma));
+      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)mpad);
+      mbar_wait(&gs->acc_empty[acc.buf], acc.phase ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem + acc.buf * 256u;     // buffer b = columns [b*256, b*256+256); dual: gate | up halves
+      for (int k = r.k0; k < r.k1; ++k) {
+        mbar_wait(&gs->full[pipe.stage], pipe.phase);
+        const uint32_t sa = smem_u32(tiles + (size_t)pipe.stage * slot_bytes);
+        uint64_t* empty_a = &gs->empty[pipe.stage];
+        pipe.advance(nstages);
+        uint32_t sb = 0;
+        uint64_t* empty_b = nullptr;
+        if (dual) {
+          mbar_wait(&gs->full[pipe.stage], pipe.phase);
+          sb = smem_u32(tiles + (size_t)pipe.stage * slot_bytes);
+          empty_b = &gs->empty[pipe.stage];
+          pipe.advance(nstages);
         }
-      }
-    }
-  } else {
-    // ===================== epilogue warps: TMEM -> registers -> global ==========================================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int feat_in_tile = q * 32 + lane;
-    if (t.epilogue == EPI_ARGMAX) {
-      for (int m = lane; m < t.M; m += 32) {
-        gs->best_val[q * gs->argmax_cap + m] = -INFINITY;
-        gs->best_idx[q * gs->argmax_cap + m] = 0x7fffffff;
-      }
-      __syncwarp();
-    }
-    for (int u = cta; u < units; u += nctas) {
-      const int n_tile = u / t.splits, split = u % t.splits;
-      const int n = n_tile * kTileN + feat_in_tile;
-      for (int mt = 0; mt < m_tiles; ++mt) {
-        const int m0 = mt * rows_mma;
-        const int mlive = min(t.M - m0, rows_mma);
-        const int mpad = round_up16(mlive);
-        mbar_wait(&gs->acc_full[acc.buf], acc.phase);
         tc_fence_after();
-        const uint32_t taddr = gs->tmem_base + acc.buf * 256u + ((uint32_t)(q * 32) << 16);
-        if (t.epilogue == EPI_PARTIAL_F32) {
-          float* out = reinterpret_cast<float*>(t.out) + (size_t)split * t.M_cap * t.N;
-          const float b = (t.bias != nullptr && split == 0) ? t.bias[n] : 0.f;
-          for (int c0 = 0; c0 < mpad; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + c0, v);
-            tmem_ld_wait();
+        const uint32_t xbase = sa + kWTileBytes;
+        const uint32_t accum0 = (k > r.k0) ? 1u : 0u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int m = m0 + c0 + j;
-              if (c0 + j < mlive) out[(size_t)m * t.N + n] = __uint_as_float(v[j]) + b;
-            }
+        for (int kk = 0; kk < 4; ++kk) {   // 4 x UMMA_K(16) = one 64-wide k-chunk; +32 B inside the swizzle atom
+          const uint64_t db = umma_desc_sw128(xbase + kk * 32);
+          umma_bf16(d0, umma_desc_sw128(sa + kk * 32), db, idesc, (accum0 | (kk > 0)) ? 1u : 0u);
+          if (dual) umma_bf16(d0 + 128u, umma_desc_sw128(sb + kk * 32), db, idesc, (accum0 | (kk > 0)) ? 1u : 0u);
+        }
+        umma_commit(empty_a);               // frees the slot(s) when these MMAs retire
+        if (dual) umma_commit(empty_b);
+      }
+      umma_commit(&gs->acc_full[acc.buf]);
+      acc.advance();
+    }
+  }
+}
+
+// ---- warps 2..5: TMEM -> registers -> global ----------------------------------------------------------------------
+__device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, int cta, int nctas, AccState& acc) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q = warp & 3;                       // TMEM lane quarter this warp may access (warp id % 4)
+  const int feat_in_tile = q * 32 + lane;
+  const int units = t.n_tiles * t.splits;
+  const int rows_mma = task_rows_mma(t);
+  const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
+  if (t.epilogue == EPI_ARGMAX) {
+    for (int m = lane; m < t.M; m += 32) gs->best[q][m] = 0ull;
+    __syncwarp();
+  }
+  for (int u = cta; u < units; u += nctas) {
+    const UnitRange r = unit_range(t, u);
+    const int n = r.n_tile * kTileN + feat_in_tile;
+    for (int mt = 0; mt < m_tiles; ++mt) {
+      const int m0 = mt * rows_mma;
+      const int mlive = min(t.M - m0, rows_mma);
+      const int mpad = round_up16(mlive);
+      mbar_wait(&gs->acc_full[acc.buf], acc.phase);
+      tc_fence_after();
+      const uint32_t taddr = gs->tmem_base + acc.buf * 256u + ((uint32_t)(q * 32) << 16);
+      if (t.epilogue == EPI_PARTIAL_F32) {
+        float* out = reinterpret_cast<float*>(t.out) + (size_t)r.split * t.M_cap * t.N;
+        const bool nvalid = n < t.N;
+        for (int c0 = 0; c0 < mpad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = t.x_row0 + m0 + c0 + j;
+            if (nvalid && c0 + j < mlive) out[(size_t)m * t.N + n] = __uint_as_float(v[j]);
           }
-        } else if (t.epilogue == EPI_SWIGLU_BF16) {
-          // gate in columns [0,mpad), up in columns [128,128+mpad).  HF Qwen2MLP rounding points
-          // (transformers Qwen2MLP.forward: down(act(gate(x)) * up(x)), every op in bf16): g,u -> bf16; silu(g) -> bf16;
-          // product -> bf16.  Destination: packed-X layout of the down projection, feature n is its k index.
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(t.out);
-          const int kc = n >> 6, c = n & 63;
-          for (int c0 = 0; c0 < mpad; c0 += 16) {
-            uint32_t g[16], up[16];
-            tmem_ld16(taddr + c0, g);
-            tmem_ld16(taddr + 128u + c0, up);
-            tmem_ld_wait();
+        }
+      } else if (t.epilogue == EPI_SWIGLU_BF16) {
+        // gate in columns [0,mpad), up in columns [128,128+mpad).  HF Qwen2MLP rounding points
+        // (transformers Qwen2MLP.forward: down(act(gate(x)) * up(x)), every op in bf16): g,u -> bf16; silu(g) -> bf16;
+        // product -> bf16.  Destination: packed-X layout of the down projection, feature n is its k index.
+        uint8_t* dst = reinterpret_cast<uint8_t*>(t.out);
+        const int kc = n >> 6, c = n & 63;
+        const bool nvalid = n < t.N;
+        for (int c0 = 0; c0 < mpad; c0 += 16) {
+          uint32_t g[16], up[16];
+          tmem_ld16(taddr + c0, g);
+          tmem_ld16(taddr + 128u + c0, up);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int m = m0 + c0 + j;
-              if (c0 + j < mlive) {
-                const float gf = bf16_round(__uint_as_float(g[j]));
-                const float uf = bf16_round(__uint_as_float(up[j]));
-                const float s = bf16_round(gf / (1.f + __expf(-gf)));
-                const __nv_bfloat16 r = __float2bfloat16_rn(s * uf);
-                *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(dst) +
-                                                  ((size_t)kc * t.out_kchunks_rows) * 128 + sw128_offset(m, c)) = r;
-              }
-            }
-          }
-        } else {  // EPI_ARGMAX
-          // bf16-rounded logits (reference: lm_head output is bf16, then .float(); modeling/..._unified.py:463),
-          // argmax with FIRST index winning ties (torch.argmax on CPU, :476).  Each warp reduces its 32 vocab rows
-          // with shuffles and folds the result into its private running best in shared memory.
-          float* bv = gs->best_val + q * gs->argmax_cap;
-          int* bi = gs->best_idx + q * gs->argmax_cap;
-          const bool valid = n < t.N;
-          for (int c0 = 0; c0 < mpad; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + c0, v);
-            tmem_ld_wait();
-            float rx = -INFINITY;
-            int ridx = 0x7fffffff;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = valid ? bf16_round(__uint_as_float(v[j])) : -INFINITY;
-              int idx = valid ? n : 0x7fffffff;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                const float ox = __shfl_xor_sync(0xffffffffu, x, o);
-                const int oidx = __shfl_xor_sync(0xffffffffu, idx, o);
-                if (ox > x || (ox == x && oidx < idx)) { x = ox; idx = oidx; }
-              }
-              if (lane == j) { rx = x; ridx = idx; }
-            }
-            const int m = m0 + c0 + lane;
-            if (lane < 16 && c0 + lane < mlive) {
-              const float cur = bv[m];
-              const int curi = bi[m];
-              if (rx > cur || (rx == cur && ridx < curi)) { bv[m] = rx; bi[m] = ridx; }
+          for (int j = 0; j < 16; ++j) {
+            const int m = t.x_row0 + m0 + c0 + j;
+            if (nvalid && c0 + j < mlive) {
+              const float gf = bf16_round(__uint_as_float(g[j]));
+              const float uf = bf16_round(__uint_as_float(up[j]));
+              const float s = bf16_round(gf / (1.f + __expf(-gf)));
+              *reinterpret_cast<__nv_bfloat16*>(dst + ((size_t)kc * t.out_rows_cap) * 128 + sw128_offset(m, c)) =
+                  __float2bfloat16_rn(s * uf);
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(&gs->acc_empty[acc.buf]);
-        acc.advance();
+      } else {  // EPI_ARGMAX
+        // bf16-rounded logits (reference: lm_head output is bf16, then .float(); modeling/..._unified.py:463).
+        // Each warp reduces its 32 vocab rows with shuffles and folds the winner into its running best in smem.
+        const bool valid = n < t.N;
+        for (int c0 = 0; c0 < mpad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          unsigned long long mine = 0ull;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            unsigned long long key = valid ? argmax_key(bf16_round(__uint_as_float(v[j])), n) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+              key = other > key ? other : key;
+            }
+            if (lane == j) mine = key;
+          }
+          const int m = m0 + c0 + lane;
+          if (lane < 16 && c0 + lane < mlive && mine > gs->best[q][m]) gs->best[q][m] = mine;
+          __syncwarp();
+        }
       }
+      tc_fence_before();
+      mbar_arrive(&gs->acc_empty[acc.buf]);
+      acc.advance();
     }
-    if (t.epilogue == EPI_ARGMAX) {
-      // per-CTA, per-warp candidates: out [nctas][4][M_cap] (value), out2 same shape (index); the policy step
-      // finishes the reduction over nctas*4 candidates per row with the same tie rule.
-      __syncwarp();
-      float* ov = reinterpret_cast<float*>(t.out) + ((size_t)cta * 4 + q) * t.M_cap;
-      int* oi = reinterpret_cast<int*>(t.out2) + ((size_t)cta * 4 + q) * t.M_cap;
-      for (int m = lane; m < t.M; m += 32) {
-        ov[m] = gs->best_val[q * gs->argmax_cap + m];
-        oi[m] = gs->best_idx[q * gs->argmax_cap + m];
-      }
+  }
+  if (t.epilogue == EPI_ARGMAX) {
+    __syncwarp();
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(t.out);
+    for (int m = lane; m < t.M; m += 32) {
+      const unsigned long long k = gs->best[q][m];
+      if (k != 0ull) atomicMax(&keys[t.x_row0 + m], k);
     }
   }
 }

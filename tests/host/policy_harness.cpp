@@ -1,0 +1,58 @@
+// policy_harness.cpp — host build of the PRODUCT policy code (jacobiforcing_b200/csrc/jf_policy.h, the same header
+// the persistent CUDA kernel compiles) behind a tiny C entry point, so tests can replay the reference's golden
+// forwards (tests/golden/*.json) through it on a CPU-only box.  Test infrastructure; not part of the shipped library.
+// Build: g++ -O2 -shared -fPIC -I jacobiforcing_b200/csrc tests/host/policy_harness.cpp -o build/libjf_policy_host.so
+#include <cstring>
+#include <cstdlib>
+#include "jf_policy.h"
+
+using namespace jf;
+
+extern "C" {
+
+// Forward table: forward f has B[f] rows of L[f] tokens starting at rows_off[f] in rows_flat / greedy_flat.
+// Returns 0 on success, otherwise 100 + index of the first forward whose (kv, rows) differ from the table,
+// or 1 when the policy asks for more forwards than recorded.
+int jf_policy_replay(const int* knobs_i /*12 ints in PolicyKnobs order*/, const int* prompt, int prompt_len, int ctx0,
+                     int first_correct, const int* first_call_tokens, const int* choice_idx, int choice_rows,
+                     const int* pad_stream, int pad_stream_len, int nfw, const int* kv_before, const int* fB,
+                     const int* fL, const long long* rows_off, const int* rows_flat, const int* greedy_flat,
+                     int* gen_out, int gen_cap, int* iters_log, int iters_cap, int* result /*[8]*/) {
+  PolicyKnobs kn;
+  std::memcpy(&kn, knobs_i, sizeof(PolicyKnobs));
+  SeqState* s = (SeqState*)std::calloc(1, sizeof(SeqState));
+  seq_state_init(*s, prompt_len, ctx0, first_correct);
+  for (int i = 0; i < prompt_len && i < gen_cap; ++i) gen_out[i] = prompt[i];
+  DraftSource src{first_call_tokens, choice_idx, choice_rows, pad_stream, pad_stream_len};
+  int f = 0, rc = 0;
+  const int* greedy = nullptr;
+  int gstride = 0;
+  int* gbuf = (int*)std::malloc(sizeof(int) * kRowsMax * kOutColsMax);
+  while (true) {
+    bool more;
+    if (kn.mode == MODE_ENGINE) more = eng_advance(*s, kn, src, greedy, gen_out, gen_cap);
+    else more = hf_advance(*s, kn, src, greedy, gstride, gen_out, gen_cap, iters_log, iters_cap);
+    if (!more) break;
+    if (f >= nfw) { rc = 1; break; }
+    bool same = (kv_before[f] == s->ctx) && (fB[f] == s->B_out) && (fL[f] == s->L_out);
+    if (same)
+      for (int i = 0; i < s->B_out && same; ++i)
+        for (int j = 0; j < s->L_out; ++j)
+          if (rows_flat[rows_off[f] + (long long)i * fL[f] + j] != s->out_rows[i][j]) { same = false; break; }
+    if (!same) { rc = 100 + f; break; }
+    gstride = fL[f];
+    std::memcpy(gbuf, greedy_flat + rows_off[f], sizeof(int) * (size_t)fB[f] * fL[f]);
+    greedy = gbuf;
+    ++f;
+  }
+  result[0] = s->gen_len; result[1] = s->calls; result[2] = s->stop_reason; result[3] = s->total_new;
+  result[4] = s->error; result[5] = f; result[6] = s->total_iters; result[7] = s->ctx;
+  std::free(gbuf);
+  std::free(s);
+  return rc;
+}
+
+int jf_policy_state_bytes() { return (int)sizeof(SeqState); }
+int jf_policy_knob_ints() { return (int)(sizeof(PolicyKnobs) / sizeof(int)); }
+
+}  // extern "C"
