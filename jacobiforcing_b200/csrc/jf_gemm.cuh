@@ -65,10 +65,13 @@ struct GemmSmem {
   unsigned long long best[4][kArgmaxRows];   // EPI_ARGMAX running best key per epilogue warp and row
 };
 
-struct PipeState {      // smem ring position; persists across tasks
-  uint32_t stage = 0, phase = 0;
+struct PipeState {      // smem ring position.  Phase parity is tracked PER SLOT (bit i = parity of slot i) so the ring
+  uint32_t stage = 0;   // geometry (slot size / slot count) can change between forwards once the ring has drained.
+  uint32_t phase_bits = 0;
+  __device__ __forceinline__ uint32_t phase() const { return (phase_bits >> stage) & 1u; }
   __device__ __forceinline__ void advance(uint32_t nstages) {
-    if (++stage == nstages) { stage = 0; phase ^= 1; }
+    phase_bits ^= (1u << stage);
+    if (++stage == nstages) stage = 0;
   }
 };
 struct AccState {       // TMEM accumulator ring position
@@ -96,7 +99,8 @@ __host__ __device__ __forceinline__ int argmax_key_index(unsigned long long key)
 }
 
 // One-time setup by the whole CTA.
-__device__ __forceinline__ void gemm_setup(GemmSmem* gs, int nstages) {
+__device__ __forceinline__ void gemm_setup(GemmSmem* gs) {
+  const int nstages = kMaxStages;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < nstages; ++i) { mbar_init(&gs->full[i], 2); mbar_init(&gs->empty[i], 1); }
@@ -141,13 +145,13 @@ __device__ __forceinline__ void gemm_produce_w(const GemmTask& t, GemmSmem* gs, 
     const UnitRange r = unit_range(t, u);
     for (int mt = 0; mt < m_tiles; ++mt) {
       for (int k = r.k0; k < r.k1; ++k) {
-        mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
+        mbar_wait(&gs->empty[pipe.stage], pipe.phase() ^ 1);
         mbar_expect_tx(&gs->full[pipe.stage], kWTileBytes);
         bulk_g2s(tiles + (size_t)pipe.stage * slot_bytes,
                  t.W + ((size_t)r.n_tile * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes, &gs->full[pipe.stage]);
         pipe.advance(nstages);
         if (dual) {
-          mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
+          mbar_wait(&gs->empty[pipe.stage], pipe.phase() ^ 1);
           mbar_expect_tx(&gs->full[pipe.stage], kWTileBytes);
           bulk_g2s(tiles + (size_t)pipe.stage * slot_bytes,
                    t.W + ((size_t)(r.n_tile + t.n_tiles) * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes,
@@ -172,13 +176,13 @@ __device__ __forceinline__ void gemm_produce_x(const GemmTask& t, GemmSmem* gs, 
       const int m0 = mt * rows_mma;
       const uint32_t xbytes = (uint32_t)round_up16(min(t.M - m0, rows_mma)) * 128u;
       for (int k = r.k0; k < r.k1; ++k) {
-        mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
+        mbar_wait(&gs->empty[pipe.stage], pipe.phase() ^ 1);
         mbar_expect_tx(&gs->full[pipe.stage], xbytes);
         bulk_g2s(tiles + (size_t)pipe.stage * slot_bytes + kWTileBytes,
                  t.X + ((size_t)k * t.xrows_cap + t.x_row0 + m0) * kTileK, xbytes, &gs->full[pipe.stage]);
         pipe.advance(nstages);
         if (dual) {   // the "up" slot reuses the gate slot's X chunk: plain arrival keeps the count at two
-          mbar_wait(&gs->empty[pipe.stage], pipe.phase ^ 1);
+          mbar_wait(&gs->empty[pipe.stage], pipe.phase() ^ 1);
           mbar_arrive(&gs->full[pipe.stage]);
           pipe.advance(nstages);
         }
@@ -205,14 +209,14 @@ __device__ __forceinline__ void gemm_issue_mma(const GemmTask& t, GemmSmem* gs, 
       tc_fence_after();
       const uint32_t d0 = tmem + acc.buf * 256u;     // buffer b = columns [b*256, b*256+256); dual: gate | up halves
       for (int k = r.k0; k < r.k1; ++k) {
-        mbar_wait(&gs->full[pipe.stage], pipe.phase);
+        mbar_wait(&gs->full[pipe.stage], pipe.phase());
         const uint32_t sa = smem_u32(tiles + (size_t)pipe.stage * slot_bytes);
         uint64_t* empty_a = &gs->empty[pipe.stage];
         pipe.advance(nstages);
         uint32_t sb = 0;
         uint64_t* empty_b = nullptr;
         if (dual) {
-          mbar_wait(&gs->full[pipe.stage], pipe.phase);
+          mbar_wait(&gs->full[pipe.stage], pipe.phase());
           sb = smem_u32(tiles + (size_t)pipe.stage * slot_bytes);
           empty_b = &gs->empty[pipe.stage];
           pipe.advance(nstages);

@@ -1,0 +1,317 @@
+// jf_kernel.cuh — the persistent cooperative kernel: one launch runs Jacobi iterations (Qwen2 forward over the
+// in-flight draft rows -> fused LM-head argmax -> accept / shift / re-draft policy -> KV commit) until every sequence
+// reached its fixed point / EOS / token budget.  No host round trip between iterations.
+//
+// One CTA per SM, 224 threads, roles per warp (see jf_gemm.cuh).  Stages are separated by a grid barrier built on a
+// monotonic global counter: barrier k is complete when counter >= k * gridDim.x.  Only the worker warps arrive; the
+// weight producer never waits on it inside a forward (weights do not depend on activations), the X producer waits
+// for the barrier that publishes its operand, the MMA issuer is driven by the shared-memory ring alone.
+#pragma once
+#include "jf_stages.cuh"
+
+namespace jf {
+
+__device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned int target) {
+  if (ld_acquire_gpu_u32(counter) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu_u32(counter) < target) {
+    __nanosleep(40);
+    if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+  }
+}
+
+__device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w, unsigned int& epoch) {
+  __threadfence();
+  fence_proxy_async_all();
+  workers_sync();
+  epoch += 1;
+  if (w.wtid == 0) {
+    red_release_gpu_add_u32(c.bar_counter, 1u);
+    wait_epoch(c.bar_counter, epoch * (unsigned int)w.nctas);
+    __threadfence();
+  }
+  workers_sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// policy stages (CTA 0, worker warps)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void policy_stage_plan(const DevCtx& c, const WorkerCtx& w) {
+  PlanHdr* hdr = c.hdr;
+  const int n_lm = __ldcg(&hdr->n_lm_tasks);
+  for (int i = 0; i < n_lm; ++i) {
+    const int r0 = __ldcg(&hdr->lm_row0[i]), rn = __ldcg(&hdr->lm_rows[i]);
+    for (int t = r0 + w.wtid; t < r0 + rn; t += kWorkerThreads) {
+      const unsigned long long key = __ldcg(&c.argmax_keys[t]);
+      c.greedy[t] = argmax_key_index(key);
+      c.argmax_keys[t] = 0ull;
+    }
+  }
+  if (w.wtid == 0) {
+    hdr->n_commit = __ldcg(&hdr->n_commit_after);
+    hdr->iter = __ldcg(&hdr->iter) + 1;
+    hdr->rows_total = __ldcg(&hdr->rows_total) + __ldcg(&hdr->T);
+    hdr->done = 1;
+  }
+}
+
+__device__ void policy_stage_jacobi(const DevCtx& c, const WorkerCtx& w, bool first, int max_forwards) {
+  PlanHdr* hdr = c.hdr;
+  const int Tprev = first ? 0 : __ldcg(&hdr->T);
+  for (int t = w.wtid; t < Tprev; t += kWorkerThreads) {
+    const unsigned long long key = __ldcg(&c.argmax_keys[t]);
+    c.greedy[t] = argmax_key_index(key);
+    c.argmax_keys[t] = 0ull;
+  }
+  __threadfence_block();
+  workers_sync();
+  if (w.lane == 0) {
+    for (int s = w.wwarp; s < c.n_seqs; s += 4) {
+      SeqState& st = c.seq_state[s];
+      SeqSlot& sl = c.seq_slot[s];
+      sl.had_forward = (sl.active && !first) ? 1 : 0;
+      sl.commit_n = 0;
+      if (st.finished) { sl.active = 0; continue; }
+      const PolicyKnobs& kn = c.knobs[s];
+      const DraftSource& src = c.draft_src[s];
+      const int* greedy = sl.had_forward ? (c.greedy + sl.row0) : nullptr;
+      bool more;
+      if (kn.mode == MODE_ENGINE)
+        more = eng_advance(st, kn, src, greedy, c.gen + (size_t)s * c.gen_cap, c.gen_cap);
+      else
+        more = hf_advance(st, kn, src, greedy, sl.L, c.gen + (size_t)s * c.gen_cap, c.gen_cap,
+                          c.iters_log + (size_t)s * c.iters_cap, c.iters_cap);
+      if (sl.had_forward) {
+        sl.commit_src_row = sl.row0 + st.commit_row * sl.L;
+        sl.commit_n = st.commit_n;
+        sl.commit_pos = sl.ctx_at_forward;
+      }
+      sl.active = more ? 1 : 0;
+    }
+  }
+  __threadfence_block();
+  workers_sync();
+  if (w.wtid == 0) {
+    const int iter_done = first ? 0 : __ldcg(&hdr->iter) + 1;
+    int T = 0, G = 0, nc = 0, units = 0, slots = 0, err = 0;
+    const int CH = c.attn_chunk;
+    for (int s = 0; s < c.n_seqs; ++s) {
+      SeqState& st = c.seq_state[s];
+      SeqSlot& sl = c.seq_slot[s];
+      for (int j = 0; j < sl.commit_n && nc < c.T_cap; ++j) {
+        c.commits[nc].src_row = sl.commit_src_row + j;
+        c.commits[nc].seq = s;
+        c.commits[nc].pos = sl.commit_pos + j;
+        ++nc;
+      }
+      if (!sl.active) continue;
+      if (iter_done >= max_forwards) {
+        st.finished = 1; st.stop_reason = STOP_MAX_ITERS; sl.active = 0;
+        continue;
+      }
+      const int B = st.B_out, L = st.L_out;
+      const int nchunks = (st.ctx + L + CH - 1) / CH;
+      const int qsplit = (L + kQTokPerUnit - 1) / kQTokPerUnit;
+      if (T + B * L > c.T_cap || G + B > c.G_cap || slots + B * L * nchunks > c.attn_slots_cap ||
+          st.ctx + L > c.max_pages_per_seq * kPage || st.ctx + L > c.md.max_pos) {
+        err = 1; st.finished = 1; st.stop_reason = STOP_ERROR; st.error = PERR_CAPACITY; sl.active = 0;
+        continue;
+      }
+      sl.row0 = T; sl.B = B; sl.L = L; sl.g0 = G; sl.ctx_at_forward = st.ctx;
+      for (int i = 0; i < B; ++i) {
+        Group& g = c.groups[G];
+        g.row0 = T + i * L; g.len = L; g.seq = s; g.ctx = st.ctx;
+        g.nchunks = nchunks; g.qsplit = qsplit; g.unit0 = units; g.slot0 = slots;
+        units += c.md.n_kv * nchunks * qsplit;
+        slots += L * nchunks;
+        ++G;
+      }
+      if (c.trace != nullptr) {
+        int tl = *c.trace_len;
+        if (tl + 5 + B * L <= c.trace_cap) {
+          c.trace[tl] = iter_done; c.trace[tl + 1] = s; c.trace[tl + 2] = st.ctx; c.trace[tl + 3] = B; c.trace[tl + 4] = L;
+          for (int i = 0; i < B; ++i)
+            for (int j = 0; j < L; ++j) c.trace[tl + 5 + i * L + j] = st.out_rows[i][j];
+          *c.trace_len = tl + 5 + B * L;
+        }
+      }
+      T += B * L;
+    }
+    hdr->rows_total = (first ? 0 : __ldcg(&hdr->rows_total)) + T;
+    hdr->T = T; hdr->G = G; hdr->n_commit = nc; hdr->attn_units = units; hdr->attn_slots = slots;
+    hdr->iter = iter_done;
+    hdr->want_logits = 0;
+    if (err) hdr->error = err;
+    int nl = 0;
+    for (int r = 0; r < T && nl < kMaxLmTasks; r += kArgmaxRows) {
+      hdr->lm_row0[nl] = r;
+      hdr->lm_rows[nl] = min(kArgmaxRows, T - r);
+      ++nl;
+    }
+    hdr->n_lm_tasks = nl;
+    hdr->done = (T == 0) ? 1 : 0;
+  }
+  __threadfence_block();
+  workers_sync();
+  for (int s = 0; s < c.n_seqs; ++s) {
+    const SeqSlot& sl = c.seq_slot[s];
+    if (!sl.active) continue;
+    const SeqState& st = c.seq_state[s];
+    const int n = sl.B * sl.L;
+    for (int idx = w.wtid; idx < n; idx += kWorkerThreads) {
+      const int i = idx / sl.L, j = idx - i * sl.L;
+      c.tok[sl.row0 + idx] = st.out_rows[i][j];
+      c.row_group[sl.row0 + idx] = sl.g0 + i;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------
+enum Role : int { ROLE_W = 0, ROLE_MMA = 1, ROLE_WORKER = 2, ROLE_X = 3 };
+
+struct IterPlan {
+  int T, G, done, n_commit, attn_units, n_lm, want_logits;
+};
+
+template <int ROLE>
+__device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring_bytes, const WorkerCtx& w,
+                         int run_mode, int max_forwards) {
+  const int cta = blockIdx.x, nctas = gridDim.x;
+  unsigned int epoch = 0;
+  PipeState pipe;
+  AccState acc;
+  const ModelDims& md = c.md;
+  const int kc_h = md.h >> 6, kc_q = md.q_dim >> 6, kc_i = md.inter >> 6;
+  const int nt_qkv = (md.qkv_dim + 127) >> 7, nt_h = (md.h + 127) >> 7, nt_i = (md.inter + 127) >> 7;
+  const int nt_v = (md.vocab + 127) >> 7;
+  int nstages = 1, slot_bytes = 0;
+
+  auto gemm_stage = [&](const GemmTask& t, bool barrier_after) {
+    if (ROLE == ROLE_W) {
+      gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
+    } else if (ROLE == ROLE_X) {
+      wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);
+      fence_proxy_async_all();
+      gemm_produce_x(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
+    } else if (ROLE == ROLE_MMA) {
+      gemm_issue_mma(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, acc);
+    } else {
+      gemm_epilogue(t, gs, cta, nctas, acc);
+    }
+    if (barrier_after) {
+      if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch); else epoch += 1;
+    }
+  };
+#define JF_SIMT_STAGE(body)                                   \
+  do {                                                        \
+    if (ROLE == ROLE_WORKER) { body; grid_barrier(c, w, epoch); } else { epoch += 1; } \
+  } while (0)
+
+  if (run_mode == RUN_JACOBI) {
+    JF_SIMT_STAGE(if (cta == 0) policy_stage_jacobi(c, w, true, max_forwards));
+  }
+
+  for (;;) {
+    if (ROLE != ROLE_WORKER) wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);
+    const PlanHdr* hdr = c.hdr;
+    IterPlan ip;
+    ip.T = __ldcg(&hdr->T); ip.G = __ldcg(&hdr->G); ip.done = __ldcg(&hdr->done);
+    ip.n_commit = __ldcg(&hdr->n_commit); ip.attn_units = __ldcg(&hdr->attn_units);
+    ip.n_lm = __ldcg(&hdr->n_lm_tasks); ip.want_logits = __ldcg(&hdr->want_logits);
+    if (ip.done) {
+      if (ROLE == ROLE_WORKER) stage_commit(c, w, ip.n_commit);
+      break;
+    }
+    const int T = ip.T;
+    slot_bytes = gemm_slot_bytes(min(kMaxRowsMMA, round_up16(T)));
+    nstages = min(kMaxStages, ring_bytes / slot_bytes);
+    pipe.stage = 0;
+
+    JF_SIMT_STAGE(stage_commit(c, w, ip.n_commit); stage_rows_norm(c, w, T, true, 0, c.layer[0].ln1));
+
+    for (int l = 0; l < md.layers; ++l) {
+      const LayerW& lw = c.layer[l];
+      GemmTask t;
+      t.M = T; t.x_row0 = 0; t.xrows_cap = c.xrows_cap; t.M_cap = c.T_cap; t.out_rows_cap = c.xrows_cap;
+      // QKV projection (split-K partial sums)
+      t.W = lw.wqkv; t.X = c.xn; t.out = c.part; t.n_tiles = nt_qkv; t.k_chunks = kc_h; t.splits = c.splits_qkv;
+      t.N = md.qkv_dim; t.epilogue = EPI_PARTIAL_F32;
+      gemm_stage(t, true);
+      JF_SIMT_STAGE(stage_qkv_rope(c, w, T, l));
+      JF_SIMT_STAGE(stage_attention(c, w, l, ip.G, ip.attn_units));
+      JF_SIMT_STAGE(stage_attn_combine(c, w, T));
+      // O projection
+      t.W = lw.wo; t.X = c.xa; t.out = c.part; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
+      t.N = md.h; t.epilogue = EPI_PARTIAL_F32;
+      gemm_stage(t, true);
+      JF_SIMT_STAGE(stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2));
+      // gate/up projection with the SwiGLU epilogue
+      t.W = lw.wgu; t.X = c.xn; t.out = c.xact; t.n_tiles = nt_i; t.k_chunks = kc_h; t.splits = 1;
+      t.N = md.inter; t.epilogue = EPI_SWIGLU_BF16;
+      gemm_stage(t, true);
+      // down projection
+      t.W = lw.wd; t.X = c.xact; t.out = c.part; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
+      t.N = md.h; t.epilogue = EPI_PARTIAL_F32;
+      gemm_stage(t, true);
+      JF_SIMT_STAGE(stage_rows_norm(c, w, T, false, c.splits_down,
+                                    (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm));
+    }
+
+    // LM head: fused bf16-rounded argmax (no logits in HBM); optional fp32 logits for the tolerance checks
+    for (int i = 0; i < ip.n_lm; ++i) {
+      GemmTask t;
+      t.W = c.lm_head; t.X = c.xn; t.out = c.argmax_keys; t.n_tiles = nt_v; t.k_chunks = kc_h; t.splits = 1;
+      t.M = __ldcg(&hdr->lm_rows[i]); t.x_row0 = __ldcg(&hdr->lm_row0[i]); t.xrows_cap = c.xrows_cap;
+      t.N = md.vocab; t.M_cap = c.T_cap; t.epilogue = EPI_ARGMAX; t.out_rows_cap = c.xrows_cap;
+      gemm_stage(t, false);
+      if (i == 0 && ip.want_logits) {
+        t.out = c.logits - (size_t)t.x_row0 * md.vocab;
+        t.epilogue = EPI_PARTIAL_F32;
+        gemm_stage(t, false);
+      }
+    }
+    if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch); else epoch += 1;
+
+    JF_SIMT_STAGE(if (cta == 0) {
+      if (run_mode == RUN_JACOBI) policy_stage_jacobi(c, w, false, max_forwards); else policy_stage_plan(c, w);
+    });
+  }
+#undef JF_SIMT_STAGE
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mode, int max_forwards) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const DevCtx& c = *ctxp;
+  GemmSmem* gs = reinterpret_cast<GemmSmem*>(smem);
+  float* red = reinterpret_cast<float*>(smem + ((sizeof(GemmSmem) + 15) & ~(size_t)15));
+  uint8_t* attn = reinterpret_cast<uint8_t*>(red + 16);
+  const int attn_bytes = 2 * kAttnSub * (c.md.d + 8) * 2;
+  const uint32_t base_addr = smem_u32(smem);     // the ring must be 1024-byte aligned in the shared window (sw128)
+  const size_t tiles_off = (((size_t)base_addr + (size_t)(attn - smem) + attn_bytes + 1023) & ~(size_t)1023) - base_addr;
+  uint8_t* tiles = smem + tiles_off;
+  const int ring_bytes = smem_total - (int)tiles_off;
+
+  gemm_setup(gs);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WorkerCtx w;
+  w.cta = blockIdx.x; w.nctas = gridDim.x; w.lane = lane; w.red = red; w.attn_smem = attn;
+  w.wwarp = warp - kWarpWorker0; w.wtid = (int)threadIdx.x - kWarpWorker0 * 32;
+
+  if (warp == kWarpW) {
+    if (lane == 0) run_role<ROLE_W>(c, gs, tiles, ring_bytes, w, run_mode, max_forwards);
+  } else if (warp == kWarpMMA) {
+    if (lane == 0) run_role<ROLE_MMA>(c, gs, tiles, ring_bytes, w, run_mode, max_forwards);
+  } else if (warp == kWarpX) {
+    if (lane == 0) run_role<ROLE_X>(c, gs, tiles, ring_bytes, w, run_mode, max_forwards);
+  } else {
+    run_role<ROLE_WORKER>(c, gs, tiles, ring_bytes, w, run_mode, max_forwards);
+  }
+  __syncwarp();
+  gemm_teardown(gs);
+}
+
+}  // namespace jf

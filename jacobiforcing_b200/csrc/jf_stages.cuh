@@ -1,0 +1,436 @@
+// jf_stages.cuh — the SIMT / mma.sync stages of one Qwen2 forward over the in-flight draft rows, executed by the four
+// worker warps (128 threads) of every CTA of the persistent kernel, between the tcgen05 weight GEMMs.
+//
+// What each stage re-expresses (reference call sites; the arithmetic itself is transformers' Qwen2):
+//   stage_rows_norm   embed_tokens / residual add + Qwen2RMSNorm            unified.py:429, :452-462; layers/layernorm.py:16-40
+//   stage_qkv_rope    q/k/v bias add, apply_rotary_pos_emb, KV append       layers/rotary_embedding.py:6-48, attention.py:10-40
+//   stage_attention   causal GQA attention over [committed pages | in-flight rows]   layers/attention.py:133-136
+//   stage_attn_combine  split-KV merge, output in the O-projection's operand layout
+//   stage_commit      accepted in-flight K/V -> paged cache (replaces DynamicCache trim / trim_kv_only_fast)
+// Rounding points follow the HF bf16 modules: linear outputs, RMSNorm (fp32 statistics, bf16
+// normalised value times bf16 weight), rotary products and sums, residual adds are each rounded to bf16.
+#pragma once
+#include "jf_types.h"
+#include "jf_gemm.cuh"
+
+namespace jf {
+
+struct WorkerCtx {
+  int cta, nctas;
+  int wtid;        // 0..127 among the worker warps
+  int wwarp;       // 0..3
+  int lane;
+  float* red;      // [8] block-reduction scratch
+  uint8_t* attn_smem;
+};
+
+constexpr uint32_t kBarWorkers = 1;   // named barrier ids (0 is __syncthreads)
+constexpr uint32_t kBarReduce  = 2;
+
+__device__ __forceinline__ void workers_sync() { named_bar_sync(kBarWorkers, kWorkerThreads); }
+
+__device__ __forceinline__ float block_sum_128(float v, const WorkerCtx& w) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (w.lane == 0) w.red[w.wwarp] = v;
+  named_bar_sync(kBarReduce, kWorkerThreads);
+  const float r = (w.red[0] + w.red[1]) + (w.red[2] + w.red[3]);
+  named_bar_sync(kBarReduce, kWorkerThreads);
+  return r;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rows: (embedding | split-K reduce + residual add) -> hidden, then RMSNorm -> packed X operand of the next GEMM
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w, int T, bool embed, int splits,
+                                const __nv_bfloat16* normw) {
+  const int h = c.md.h;
+  const int nvec = h >> 3;
+  for (int t = w.cta; t < T; t += w.nctas) {
+    float x[8][8];
+    float ss = 0.f;
+    const __nv_bfloat16* erow = nullptr;
+    if (embed) {
+      int tk = __ldcg(&c.tok[t]);
+      tk = tk < 0 ? 0 : (tk >= c.md.vocab ? c.md.vocab - 1 : tk);
+      erow = c.embed + (size_t)tk * h;
+    }
+    __nv_bfloat16* hrow = c.hidden + (size_t)t * h;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int v = w.wtid + i * kWorkerThreads;
+      if (v < nvec) {
+        if (embed) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(erow) + v), x[i]);
+        } else {
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int s = 0; s < splits; ++s) {
+            const float4* p = reinterpret_cast<const float4*>(c.part + ((size_t)s * c.T_cap + t) * h) + v * 2;
+            const float4 a = __ldcg(p), b = __ldcg(p + 1);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+          }
+          float r[8];
+          unpack8(__ldcg(reinterpret_cast<const uint4*>(hrow) + v), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[i][j] = bf16_round(r[j] + bf16_round(acc[j]));
+        }
+        reinterpret_cast<uint4*>(hrow)[v] = pack8(x[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += x[i][j] * x[i][j];
+      }
+    }
+    ss = block_sum_128(ss, w);
+    const float rstd = 1.0f / sqrtf(ss / (float)h + c.md.eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int v = w.wtid + i * kWorkerThreads;
+      if (v < nvec) {
+        float wt[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(normw) + v), wt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = wt[j] * bf16_round(x[i][j] * rstd);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(v >> 3) * c.xrows_cap + t) * 128 +
+                       (((v & 7) ^ (t & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = pack8(o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// q/k/v: split-K reduce + bias -> bf16, rotary embedding in bf16 arithmetic, scatter to qbuf / in-flight KV scratch
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w, int T, int layer) {
+  const ModelDims& md = c.md;
+  const int d = md.d, half = d >> 1, ppl = d >> 6;     // pairs per lane: 1 (d=64) or 2 (d=128)
+  const int nslots = md.n_q + 2 * md.n_kv;
+  const int N = md.qkv_dim;
+  const int splits = c.splits_qkv;
+  const float* bias = c.layer[layer].bqkv;
+  const int items = T * nslots;
+  for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
+    const int t = item / nslots, slot = item - t * nslots;
+    const int col0 = slot * d;
+    const int g = __ldcg(&c.row_group[t]);
+    int pos = __ldcg(&c.groups[g].ctx) + (t - __ldcg(&c.groups[g].row0));
+    pos = pos < 0 ? 0 : (pos >= md.max_pos ? md.max_pos - 1 : pos);
+    float lo[2], hi[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (j < ppl) {
+        const int e = w.lane * ppl + j;
+        float sl = 0.f, sh = 0.f;
+        for (int s = 0; s < splits; ++s) {
+          const float* p = c.part + ((size_t)s * c.T_cap + t) * N + col0;
+          sl += __ldcg(p + e);
+          sh += __ldcg(p + half + e);
+        }
+        lo[j] = bf16_round(sl + __ldg(bias + col0 + e));
+        hi[j] = bf16_round(sh + __ldg(bias + col0 + half + e));
+      }
+    }
+    if (slot < md.n_q + md.n_kv) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j < ppl) {
+          const int e = w.lane * ppl + j;
+          const float cs = __bfloat162float(__ldg(c.rope_cos + (size_t)pos * half + e));
+          const float sn = __bfloat162float(__ldg(c.rope_sin + (size_t)pos * half + e));
+          const float nlo = bf16_round(bf16_round(lo[j] * cs) - bf16_round(hi[j] * sn));
+          const float nhi = bf16_round(bf16_round(hi[j] * cs) + bf16_round(lo[j] * sn));
+          lo[j] = nlo; hi[j] = nhi;
+        }
+      }
+    }
+    __nv_bfloat16* dst;
+    if (slot < md.n_q) dst = c.qbuf + (size_t)t * md.q_dim + col0;
+    else if (slot < md.n_q + md.n_kv) dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, t, slot - md.n_q);
+    else dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, t, slot - md.n_q - md.n_kv);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (j < ppl) {
+        const int e = w.lane * ppl + j;
+        dst[e] = __float2bfloat16_rn(lo[j]);
+        dst[half + e] = __float2bfloat16_rn(hi[j]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// attention: unit = (group, kv head, key chunk, query split); mma.sync m16n8k16, online softmax over 64-key sub-tiles
+// Chunks are aligned to ABSOLUTE key positions, so a query's result does not depend on how its keys are split between
+// committed pages and in-flight scratch rows (AR decoding and Jacobi decoding of the same prefix agree bit for bit).
+// ---------------------------------------------------------------------------------------------------------------
+template <int D>
+__device__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, const Group& grp, int g_kvh, int chunk,
+                               int qs) {
+  constexpr int LDS = D + 8;                  // padded smem row (bf16 elements) -> conflict-free fragment loads
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem);
+  __nv_bfloat16* Vs = Ks + kAttnSub * LDS;
+  const ModelDims& md = c.md;
+  const int ctx = grp.ctx, len = grp.len, row0 = grp.row0;
+  const int nkeys = ctx + len;
+  const int key_lo = chunk * c.attn_chunk;
+  const int key_hi = min(key_lo + c.attn_chunk, nkeys);
+  const int q0 = qs * kQTokPerUnit;
+  const int qn = min(kQTokPerUnit, len - q0);
+  const int ntt = (qn + 15) >> 4;
+  const int tiles = md.n_rep * ntt;
+  const int nsub = (key_hi - key_lo + kAttnSub - 1) / kAttnSub;
+  const int* bt = c.block_tables + (size_t)grp.seq * c.max_pages_per_seq;
+  const float scale = rsqrtf((float)D);
+  const int r0 = w.lane >> 2, c2 = (w.lane & 3) * 2;
+
+  for (int tb = 0; tb * 4 < tiles; ++tb) {
+    const int tile = tb * 4 + w.wwarp;
+    const bool tvalid = tile < tiles;
+    const int j = tvalid ? tile / ntt : 0;
+    const int tt = tvalid ? tile - j * ntt : 0;
+    const int i0 = q0 + tt * 16;
+    const int head = g_kvh * md.n_rep + j;
+    const int ia = i0 + r0, ib = i0 + r0 + 8;          // token indices of this thread's two fragment rows
+    // the tile takes part only if some key of the chunk is visible to its last token
+    const bool tactive = tvalid && (key_lo <= ctx + min(i0 + 15, len - 1));
+
+    uint32_t qf[D / 16][4];
+    if (tactive) {
+      const __nv_bfloat16* qa = c.qbuf + (size_t)(row0 + min(ia, len - 1)) * md.q_dim + head * D;
+      const __nv_bfloat16* qb = c.qbuf + (size_t)(row0 + min(ib, len - 1)) * md.q_dim + head * D;
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) {
+        qf[ks][0] = __ldcg(reinterpret_cast<const unsigned int*>(qa + ks * 16 + c2));
+        qf[ks][1] = __ldcg(reinterpret_cast<const unsigned int*>(qb + ks * 16 + c2));
+        qf[ks][2] = __ldcg(reinterpret_cast<const unsigned int*>(qa + ks * 16 + 8 + c2));
+        qf[ks][3] = __ldcg(reinterpret_cast<const unsigned int*>(qb + ks * 16 + 8 + c2));
+      }
+    }
+    float o[D / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f; }
+    float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+
+    for (int sub = 0; sub < nsub; ++sub) {
+      const int k0 = key_lo + sub * kAttnSub;
+      if (!(nsub == 1 && tb > 0)) {
+        workers_sync();                                   // previous readers of Ks / Vs are done
+        constexpr int VPR = D / 8;                        // uint4 per row
+        for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
+          const int kv = idx / (kAttnSub * VPR);
+          const int rem = idx - kv * (kAttnSub * VPR);
+          const int jr = rem / VPR, v = rem - jr * VPR;
+          const int pos = k0 + jr;
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if (pos < ctx) {
+            const int page = __ldcg(bt + (pos / kPage));
+            val = __ldcg(reinterpret_cast<const uint4*>(
+                             c.kv_cache + kv_cache_offset(md, c.num_pages, layer, kv, page, g_kvh, pos % kPage)) + v);
+          } else if (pos < nkeys) {
+            val = __ldcg(reinterpret_cast<const uint4*>(
+                             c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, kv, row0 + pos - ctx, g_kvh)) + v);
+          }
+          *reinterpret_cast<uint4*>((kv ? Vs : Ks) + jr * LDS + v * 8) = val;
+        }
+        workers_sync();
+      }
+      if (!tactive || k0 > ctx + min(i0 + 15, len - 1)) continue;
+
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const __nv_bfloat16* kr = Ks + (nt * 8 + r0) * LDS + c2;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
+          mma_bf16_16816(s[nt], qf[ks], b0, b1);
+        }
+      }
+      // scale, causal mask, running max
+      const int qpa = ctx + ia, qpb = ctx + ib;
+      float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int kp = k0 + nt * 8 + c2;
+        s[nt][0] = (kp <= qpa) ? s[nt][0] * scale : -INFINITY;
+        s[nt][1] = (kp + 1 <= qpa) ? s[nt][1] * scale : -INFINITY;
+        s[nt][2] = (kp <= qpb) ? s[nt][2] * scale : -INFINITY;
+        s[nt][3] = (kp + 1 <= qpb) ? s[nt][3] * scale : -INFINITY;
+        mxa = fmaxf(mxa, fmaxf(s[nt][0], s[nt][1]));
+        mxb = fmaxf(mxb, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 1));
+      mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 2));
+      mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 1));
+      mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 2));
+      const float mna = fmaxf(m_a, mxa), mnb = fmaxf(m_b, mxb);
+      const float sca = (mna == -INFINITY) ? 1.f : __expf(m_a - mna);
+      const float scb = (mnb == -INFINITY) ? 1.f : __expf(m_b - mnb);
+      const float mua = (mna == -INFINITY) ? 0.f : mna;
+      const float mub = (mnb == -INFINITY) ? 0.f : mnb;
+      m_a = mna; m_b = mnb;
+      float suma = 0.f, sumb = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = __expf(s[nt][0] - mua); s[nt][1] = __expf(s[nt][1] - mua);
+        s[nt][2] = __expf(s[nt][2] - mub); s[nt][3] = __expf(s[nt][3] - mub);
+        suma += s[nt][0] + s[nt][1];
+        sumb += s[nt][2] + s[nt][3];
+      }
+      l_a = l_a * sca + suma;
+      l_b = l_b * scb + sumb;
+#pragma unroll
+      for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] *= sca; o[nd][1] *= sca; o[nd][2] *= scb; o[nd][3] *= scb; }
+      // O += P V
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const uint16_t* v0 = reinterpret_cast<const uint16_t*>(Vs + (kk * 16 + c2) * LDS + r0);
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd) {
+          const uint32_t b0 = (uint32_t)v0[nd * 8] | ((uint32_t)v0[LDS + nd * 8] << 16);
+          const uint32_t b1 = (uint32_t)v0[8 * LDS + nd * 8] | ((uint32_t)v0[9 * LDS + nd * 8] << 16);
+          mma_bf16_16816(o[nd], pa, b0, b1);
+        }
+      }
+    }
+
+    if (tactive) {
+      l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+      l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+      l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+      l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+      if (ia < len) {
+        const size_t sh = ((size_t)(grp.slot0 + ia * grp.nchunks + chunk) * md.n_q + head);
+        float* op = c.attn_o + sh * D + c2;
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd) *reinterpret_cast<float2*>(op + nd * 8) = make_float2(o[nd][0], o[nd][1]);
+        if ((w.lane & 3) == 0) *reinterpret_cast<float2*>(c.attn_ml + sh * 2) = make_float2(m_a, l_a);
+      }
+      if (ib < len) {
+        const size_t sh = ((size_t)(grp.slot0 + ib * grp.nchunks + chunk) * md.n_q + head);
+        float* op = c.attn_o + sh * D + c2;
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd) *reinterpret_cast<float2*>(op + nd * 8) = make_float2(o[nd][2], o[nd][3]);
+        if ((w.lane & 3) == 0) *reinterpret_cast<float2*>(c.attn_ml + sh * 2) = make_float2(m_b, l_b);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ Group load_group(const DevCtx& c, int g) {
+  Group grp;
+  const int4* p = reinterpret_cast<const int4*>(c.groups + g);
+  const int4 a = __ldcg(p), b = __ldcg(p + 1);
+  grp.row0 = a.x; grp.len = a.y; grp.seq = a.z; grp.ctx = a.w;
+  grp.nchunks = b.x; grp.qsplit = b.y; grp.unit0 = b.z; grp.slot0 = b.w;
+  return grp;
+}
+
+__device__ void stage_attention(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
+  for (int u = w.cta; u < units; u += w.nctas) {
+    int g = 0;
+    Group grp = load_group(c, 0);
+    while (g + 1 < G) {                                   // groups are few; linear scan over unit ranges
+      const int per = c.md.n_kv * grp.nchunks * grp.qsplit;
+      if (u < grp.unit0 + per) break;
+      ++g;
+      grp = load_group(c, g);
+    }
+    const int local = u - grp.unit0;
+    const int kvh = local % c.md.n_kv;
+    const int rest = local / c.md.n_kv;
+    const int chunk = rest % grp.nchunks;
+    const int qs = rest / grp.nchunks;
+    if (c.md.d == 128) attention_unit<128>(c, w, layer, grp, kvh, chunk, qs);
+    else attention_unit<64>(c, w, layer, grp, kvh, chunk, qs);
+  }
+}
+
+// merge the per-chunk partials of every (token, head) in chunk order; write bf16 into the O-projection operand
+__device__ void stage_attn_combine(const DevCtx& c, const WorkerCtx& w, int T) {
+  const ModelDims& md = c.md;
+  const int D = md.d;
+  const int vpl = D >> 5;                                  // floats per lane: 4 (d=128) or 2 (d=64)
+  const int items = T * md.n_q;
+  for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
+    const int t = item / md.n_q, head = item - t * md.n_q;
+    const Group grp = load_group(c, __ldcg(&c.row_group[t]));
+    const int i = t - grp.row0;
+    const int cmax = (grp.ctx + i) / c.attn_chunk;         // last chunk holding a visible key
+    const size_t base = ((size_t)(grp.slot0 + i * grp.nchunks) * md.n_q + head);
+    const size_t cstride = md.n_q;                          // slots of consecutive chunks are adjacent
+    float m = -INFINITY;
+    for (int ch = 0; ch <= cmax; ++ch) m = fmaxf(m, __ldcg(c.attn_ml + (base + ch * cstride) * 2));
+    float l = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ch = 0; ch <= cmax; ++ch) {
+      const float2 ml = __ldcg(reinterpret_cast<const float2*>(c.attn_ml + (base + ch * cstride) * 2));
+      const float wgt = (ml.x == -INFINITY) ? 0.f : __expf(ml.x - m);
+      l += wgt * ml.y;
+      const float* op = c.attn_o + (base + ch * cstride) * D + w.lane * vpl;
+      if (vpl == 4) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(op));
+        acc[0] += wgt * v.x; acc[1] += wgt * v.y; acc[2] += wgt * v.z; acc[3] += wgt * v.w;
+      } else {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(op));
+        acc[0] += wgt * v.x; acc[1] += wgt * v.y;
+      }
+    }
+    const float inv = 1.0f / l;
+    const int f = head * D + w.lane * vpl;                  // feature index = k index of the O projection
+    uint8_t* dst = reinterpret_cast<uint8_t*>(c.xa) + ((size_t)(f >> 6) * c.xrows_cap) * 128 + sw128_offset(t, f & 63);
+    if (vpl == 4) {
+      uint2 pk;
+      pk.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+      pk.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+      *reinterpret_cast<uint2*>(dst) = pk;
+    } else {
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+    }
+  }
+}
+
+// accepted in-flight K/V rows -> their pages (all layers)
+__device__ void stage_commit(const DevCtx& c, const WorkerCtx& w, int n_commit) {
+  const ModelDims& md = c.md;
+  const int per = md.layers * 2;
+  const int items = n_commit * per;
+  const int vpr = md.d >> 3;
+  for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
+    const int e = item / per, lk = item - e * per;
+    const int layer = lk >> 1, kv = lk & 1;
+    const int src_row = __ldcg(&c.commits[e].src_row);
+    const int seq = __ldcg(&c.commits[e].seq);
+    const int pos = __ldcg(&c.commits[e].pos);
+    const int page = __ldcg(c.block_tables + (size_t)seq * c.max_pages_per_seq + pos / kPage);
+    for (int kvh = 0; kvh < md.n_kv; ++kvh) {
+      const uint4* src = reinterpret_cast<const uint4*>(c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, kv, src_row, kvh));
+      uint4* dst = reinterpret_cast<uint4*>(c.kv_cache + kv_cache_offset(md, c.num_pages, layer, kv, page, kvh, pos % kPage));
+      for (int v = w.lane; v < vpr; v += 32) dst[v] = __ldcg(src + v);
+    }
+  }
+}
+
+}  // namespace jf

@@ -1,0 +1,139 @@
+// jf_types.h — device-visible structures shared by the host runtime (jf_engine.cu) and the persistent kernel.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "jf_policy.h"
+
+namespace jf {
+
+constexpr int kPage        = 256;    // KV page size in tokens (reference: kvcache_block_size % 256 == 0, config.py:46)
+constexpr int kMaxLayers   = 64;
+constexpr int kAttnSub     = 64;     // keys per mma.sync sub-tile
+constexpr int kMaxLmTasks  = 16;     // LM-head row tiles of kArgmaxRows per forward
+constexpr int kQTokPerUnit = 64;     // query tokens one attention unit covers
+
+struct ModelDims {
+  int h, layers, n_q, n_kv, d, inter, vocab;
+  int q_dim, kv_dim, qkv_dim;
+  int n_rep;                 // n_q / n_kv
+  int tie;                   // lm_head shares the embedding matrix
+  float eps;
+  float rope_theta;
+  int max_pos;               // rows of the rope tables
+};
+
+struct LayerW {
+  const __nv_bfloat16* wqkv;   // packed tiles, rows = [q | k | v] (HF q_proj / k_proj / v_proj stacked)
+  const float* bqkv;           // [qkv_dim] fp32 (bf16 values)
+  const __nv_bfloat16* wo;     // packed [h x q_dim]
+  const __nv_bfloat16* wgu;    // packed gate tiles [inter x h] then up tiles
+  const __nv_bfloat16* wd;     // packed [h x inter]
+  const __nv_bfloat16* ln1;    // input_layernorm.weight [h]
+  const __nv_bfloat16* ln2;    // post_attention_layernorm.weight [h]
+};
+
+// One attention group = one candidate row of one sequence: `len` in-flight tokens at positions ctx .. ctx+len-1,
+// causal among themselves, all seeing the sequence's committed KV [0, ctx).
+struct Group {
+  int row0, len, seq, ctx;
+  int nchunks;               // ceil((ctx + len) / attn_chunk)
+  int qsplit;                // ceil(len / kQTokPerUnit)
+  int unit0;                 // first attention unit of this group (units = n_kv * nchunks * qsplit)
+  int slot0;                 // first partial slot (slots = len * nchunks)
+};
+
+struct CommitEntry { int src_row, seq, pos; };
+
+struct PlanHdr {
+  int T;                     // in-flight token rows of this forward
+  int G;                     // groups
+  int done;                  // 1: no forward; apply the commit list and exit
+  int n_commit;
+  int attn_units;
+  int attn_slots;
+  int n_lm_tasks;
+  int lm_row0[kMaxLmTasks];
+  int lm_rows[kMaxLmTasks];
+  int iter;                  // forwards executed so far in this launch
+  int error;
+  int want_logits;           // plan mode: also write fp32 logits of LM task 0
+  int n_commit_after;        // plan mode: commit entries to apply once the forward is done
+  int rows_total;            // sum of T over the forwards of this launch
+};
+
+struct SeqSlot {             // per-sequence bookkeeping owned by the policy stage
+  int row0;                  // first plan row of the sequence's rows in the forward in flight
+  int B, L;                  // rows x columns in flight
+  int g0;                    // first group
+  int ctx_at_forward;        // committed KV length when the forward in flight was planned
+  int active;                // has rows in the forward in flight
+  int had_forward;
+  int commit_src_row, commit_n, commit_pos;
+};
+
+struct DevCtx {
+  ModelDims md;
+  // ---- weights
+  const __nv_bfloat16* embed;        // [vocab][h] row-major
+  const __nv_bfloat16* lm_head;      // packed tiles [ceil(vocab/128)][h/64]
+  const __nv_bfloat16* final_norm;   // [h]
+  const __nv_bfloat16* rope_cos;     // [max_pos][d/2]
+  const __nv_bfloat16* rope_sin;
+  LayerW layer[kMaxLayers];
+  // ---- paged KV cache [layer][2][num_pages][n_kv][kPage][d] and the in-flight scratch [layer][2][T_cap][n_kv][d]
+  __nv_bfloat16* kv_cache;
+  __nv_bfloat16* kv_scratch;
+  int num_pages;
+  int max_pages_per_seq;
+  int* block_tables;                 // [S_cap][max_pages_per_seq]
+  // ---- activations
+  int T_cap, xrows_cap, S_cap, G_cap;
+  __nv_bfloat16* hidden;             // [T_cap][h] residual stream
+  __nv_bfloat16* xn;                 // packed [h/64][xrows_cap x 64]   normed hidden (GEMM X operand)
+  __nv_bfloat16* xa;                 // packed [q_dim/64][...]          attention output
+  __nv_bfloat16* xact;               // packed [inter/64][...]          silu(gate)*up
+  float* part;                       // [max_splits][T_cap][max(qkv_dim, h)] split-K partial sums
+  __nv_bfloat16* qbuf;               // [T_cap][q_dim] rotated queries
+  float* attn_o;                     // [attn_slots_cap][n_q][d] unnormalised partial outputs
+  float* attn_ml;                    // [attn_slots_cap][n_q][2] (running max, running sum)
+  int attn_slots_cap;
+  int attn_chunk;                    // keys per attention unit (multiple of kAttnSub)
+  unsigned long long* argmax_keys;   // [T_cap]
+  int splits_qkv, splits_o, splits_down;
+  // ---- plan (written by the host in plan mode, by the policy stage in Jacobi mode)
+  PlanHdr* hdr;
+  int* tok;                          // [T_cap]
+  int* row_group;                    // [T_cap]
+  Group* groups;                     // [G_cap]
+  CommitEntry* commits;              // [T_cap]
+  // ---- outputs / policy
+  int* greedy;                       // [T_cap] argmax token per in-flight row of the last forward
+  float* logits;                     // plan mode debug: [kArgmaxRows][vocab] fp32 (may be null)
+  SeqState* seq_state;               // [S_cap]
+  SeqSlot* seq_slot;                 // [S_cap]
+  PolicyKnobs* knobs;                // [S_cap]
+  DraftSource* draft_src;            // [S_cap]
+  int* gen;                          // [S_cap][gen_cap] prompt + generated tokens
+  int gen_cap;
+  int* iters_log;                    // [S_cap][iters_cap]
+  int iters_cap;
+  int n_seqs;
+  int* trace;                        // optional forward trace: {iter, seq, ctx, B, L, tokens...}*
+  int trace_cap;
+  int* trace_len;
+  // ---- sync
+  unsigned int* bar_counter;
+};
+
+enum RunMode : int { RUN_PLAN = 0, RUN_JACOBI = 1 };
+
+__host__ __device__ inline size_t kv_cache_offset(const ModelDims& md, int num_pages, int layer, int kv, int page,
+                                                  int kvh, int slot) {
+  return ((((size_t)(layer * 2 + kv) * num_pages + page) * md.n_kv + kvh) * kPage + slot) * (size_t)md.d;
+}
+__host__ __device__ inline size_t kv_scratch_offset(const ModelDims& md, int T_cap, int layer, int kv, int row,
+                                                    int kvh) {
+  return (((size_t)(layer * 2 + kv) * T_cap + row) * md.n_kv + kvh) * (size_t)md.d;
+}
+
+}  // namespace jf

@@ -1,0 +1,326 @@
+"""JacobiRuntime — Python host of the C-ABI library: the per-rank pieces the reference's ModelRunner owns
+(inference_engine/engine/model_runner.py): weights (HF tensor names, loader.py:27-47), the paged KV cache with its
+block manager (engine/block_manager.py, pages of 256 tokens), prefill-with-drafting (:777-963; HF: unified.py:175-225)
+and the Jacobi decode operator, here ONE device-resident loop per call instead of a Python loop of forwards.
+
+numpy carries host buffers across the ABI; torch tensors are accepted for weights (host or device pointers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from .policy import MODES, POLICY_ERRORS, STOP_REASONS, PolicyKnobs, draw_choice_indices, draw_prefill_draft
+
+PAGE = 256
+
+
+def _i32(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class SeqHandle:
+    """Host bookkeeping of one sequence: its pages and how many tokens are committed (Sequence.block_table /
+    num_cached_tokens in the reference, engine/sequence.py:44-56)."""
+    seq_id: int
+    pages: List[int] = field(default_factory=list)
+    ctx: int = 0
+    tokens: List[int] = field(default_factory=list)
+
+
+@dataclass
+class JacobiResult:
+    tokens: List[int]
+    calls: int
+    stop_reason: str
+    total_new_tokens: int
+    total_iterations: int
+    iters: List[int]
+    ctx: int
+
+
+class JacobiRuntime:
+    def __init__(self, hf_config, *, device: int = 0, max_rows: int = 1024, max_seqs: int = 8,
+                 num_kv_pages: int = 64, max_pages_per_seq: int = 8, attn_chunk: int = 64, attn_slots: int = 0,
+                 gen_capacity: int = 4096, max_calls: int = 256, trace_capacity: int = 0):
+        self.lib = _cabi.load()
+        g = (lambda k, d=None: hf_config[k] if isinstance(hf_config, dict) else getattr(hf_config, k, d))
+        heads = int(g("num_attention_heads"))
+        hidden = int(g("hidden_size"))
+        head_dim = g("head_dim", None) or hidden // heads
+        theta = g("rope_theta", None)
+        if theta is None:
+            rp = g("rope_parameters", None) or {}
+            theta = rp.get("rope_theta", 1e6)
+        self.model_cfg = _cabi.ModelCfg(
+            hidden, int(g("num_hidden_layers")), heads, int(g("num_key_value_heads")), int(head_dim),
+            int(g("intermediate_size")), int(g("vocab_size")), int(bool(g("tie_word_embeddings", False))),
+            int(g("max_position_embeddings")), float(g("rms_norm_eps", 1e-6)), float(theta))
+        self.runtime_cfg = _cabi.RuntimeCfg(device, max_rows, max_seqs, num_kv_pages, max_pages_per_seq, attn_chunk,
+                                            attn_slots, gen_capacity, max_calls, trace_capacity)
+        self.vocab = int(g("vocab_size"))
+        self.hidden = hidden
+        self.max_rows = (max(max_rows, 16) + 15) & ~15
+        self.max_seqs = max_seqs
+        self.max_pages_per_seq = max_pages_per_seq
+        self.max_calls = max(max_calls, 4)
+        self.trace_capacity = trace_capacity
+        h = C.c_void_p()
+        _cabi.check(self.lib.jf_create(C.byref(self.model_cfg), C.byref(self.runtime_cfg), C.byref(h)), None)
+        self.h = h
+        self.free_pages = list(range(num_kv_pages - 1, -1, -1))
+        self._next_seq = 0
+        self.stats = {"forwards": 0, "device_ms": 0.0, "rows": 0}
+
+    # ---- lifecycle -----------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.jf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.jf_launch_count(self.h))
+
+    def device_info(self) -> dict:
+        sm = C.c_int32()
+        bw, bkv, bact = C.c_int64(), C.c_int64(), C.c_int64()
+        _cabi.check(self.lib.jf_device_info(self.h, C.byref(sm), C.byref(bw), C.byref(bkv), C.byref(bact)), self.h)
+        return {"sm_count": sm.value, "bytes_weights": bw.value, "bytes_kv": bkv.value, "bytes_act": bact.value}
+
+    # ---- weights (loader.py:27-47 loop stays with the caller; this is the per-tensor weight_loader) ---------------
+    def load_tensor(self, name: str, t) -> None:
+        import torch
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t)
+        t = t.detach().contiguous()
+        if t.dtype == torch.bfloat16:
+            dt = _cabi.DTYPE_BF16
+        elif t.dtype == torch.float16:
+            dt = _cabi.DTYPE_F16
+        else:
+            t = t.float().contiguous()
+            dt = _cabi.DTYPE_F32
+        shape = (C.c_int64 * t.dim())(*t.shape)
+        _cabi.check(self.lib.jf_load_tensor(self.h, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim(), dt), self.h)
+
+    def load_state_dict(self, sd: Dict[str, "object"]) -> None:
+        for name, t in sd.items():
+            if name.endswith("rotary_emb.inv_freq"):
+                continue
+            self.load_tensor(name, t)
+        _cabi.check(self.lib.jf_finalize_weights(self.h), self.h)
+
+    def finalize(self) -> None:
+        _cabi.check(self.lib.jf_finalize_weights(self.h), self.h)
+
+    def set_rope_tables(self, cos, sin) -> None:
+        cos = np.ascontiguousarray(np.asarray(cos, dtype=np.float32))
+        sin = np.ascontiguousarray(np.asarray(sin, dtype=np.float32))
+        _cabi.check(self.lib.jf_set_rope_tables(self.h, _ptr(cos), _ptr(sin), cos.shape[0]), self.h)
+
+    # ---- block manager (engine/block_manager.py: allocate / may_append / deallocate; no prefix cache on this path) --
+    def new_sequence(self) -> SeqHandle:
+        s = SeqHandle(self._next_seq)
+        self._next_seq += 1
+        return s
+
+    def ensure_capacity(self, seq: SeqHandle, n_tokens: int) -> None:
+        need = (n_tokens + PAGE - 1) // PAGE
+        if need > self.max_pages_per_seq:
+            raise RuntimeError(f"sequence needs {need} KV pages, max_pages_per_seq={self.max_pages_per_seq}")
+        while len(seq.pages) < need:
+            if not self.free_pages:
+                raise RuntimeError("out of KV pages")
+            seq.pages.append(self.free_pages.pop())
+
+    def release(self, seq: SeqHandle) -> None:
+        self.free_pages.extend(reversed(seq.pages))
+        seq.pages = []
+        seq.ctx = 0
+
+    def _block_tables(self, seqs: Sequence[SeqHandle]) -> np.ndarray:
+        bt = np.zeros((len(seqs), self.max_pages_per_seq), np.int32)
+        for i, s in enumerate(seqs):
+            bt[i, :len(s.pages)] = s.pages
+        return bt
+
+    # ---- one planned forward (the forward_step_batch operator) ------------------------------------------------------
+    def forward(self, tokens, groups, seqs: Sequence[SeqHandle], lm_row0: int, lm_rows: int, commits=(),
+                want_logits: bool = False, want_hidden: bool = False) -> dict:
+        tokens = _i32(tokens)
+        T = int(tokens.shape[0])
+        groups = _i32(groups).reshape(-1, 4)
+        commits = _i32(commits).reshape(-1, 3)
+        bt = self._block_tables(seqs)
+        greedy = np.zeros(T, np.int32)
+        logits = np.zeros((lm_rows, self.vocab), np.float32) if want_logits else None
+        hidden = np.zeros((T, self.hidden), np.uint16) if want_hidden else None
+        ms = C.c_float()
+        _cabi.check(self.lib.jf_forward(self.h, T, _ptr(tokens), groups.shape[0], _ptr(groups), len(seqs), _ptr(bt),
+                                        lm_row0, lm_rows, commits.shape[0], _ptr(commits), _ptr(greedy), _ptr(logits),
+                                        _ptr(hidden), C.byref(ms)), self.h)
+        self.stats["forwards"] += 1
+        self.stats["device_ms"] += ms.value
+        self.stats["rows"] += T
+        return {"greedy": greedy, "logits": logits, "hidden": hidden, "ms": ms.value}
+
+    def commit_rows(self, seqs: Sequence[SeqHandle], commits) -> None:
+        """Append in-flight K/V rows of the last forward to the cache: commits = [(src_row, seq_index, pos)]."""
+        commits = _i32(commits).reshape(-1, 3)
+        if commits.shape[0] == 0:
+            return
+        bt = self._block_tables(seqs)
+        _cabi.check(self.lib.jf_commit_rows(self.h, len(seqs), _ptr(bt), commits.shape[0], _ptr(commits)), self.h)
+
+    # ---- prefill-with-drafting (unified.py:175-225 / model_runner.py:777-963) ---------------------------------------
+    def prefill(self, seq: SeqHandle, prompt: Sequence[int], draft: Sequence[int]):
+        """Forward prompt ++ draft, commit the prompt's KV, return (first_correct_token, prefill_drafted_n_gram) =
+        argmax(logits[-n-1:-1]).  Long prompts are processed in chunks of max_rows rows; logits are computed for the
+        last n+1 rows only."""
+        prompt = [int(t) for t in prompt]
+        draft = [int(t) for t in draft]
+        P, n = len(prompt), len(draft)
+        if seq.ctx != 0:
+            raise ValueError("prefill needs a fresh sequence")
+        if P < 1:
+            raise ValueError("empty prompt")
+        row = prompt + draft
+        total = len(row)
+        self.ensure_capacity(seq, total)
+        want_from = P - 1                      # first row whose argmax is needed
+        out: List[int] = []
+        start = 0
+        ms = 0.0
+        while start < total:
+            end = min(total, start + self.max_rows)
+            if end < total and total - end < n + 1:   # keep the n+1 logit rows inside one chunk
+                end = max(start + 1, total - (n + 1))
+            toks = row[start:end]
+            T = end - start
+            commits = [(i, 0, start + i) for i in range(T) if start + i < P]
+            lm0 = max(0, want_from - start)
+            lm_row0, lm_rows = 0, 0
+            if end > want_from:
+                lm_row0 = (lm0 // 8) * 8
+                lm_rows = T - lm_row0
+            res = self.forward(toks, [(0, T, 0, start)], [seq], lm_row0, lm_rows, commits)
+            ms += res["ms"]
+            if end > want_from:
+                out.extend(int(t) for t in res["greedy"][lm0:T])
+            start = end
+        seq.ctx = P
+        seq.tokens = list(prompt)
+        drafted = out[:n] if n > 0 else out[:1]
+        return drafted[0], drafted, ms
+
+    # ---- the device-resident Jacobi loop -----------------------------------------------------------------------------
+    def jacobi_run(self, seqs: Sequence[SeqHandle], knobs: PolicyKnobs, first_correct: Sequence[int],
+                   first_call_tokens: Optional[Sequence[Sequence[int]]], choice_idx=None, pad_stream=None,
+                   max_forwards: int = 0, want_trace: bool = False):
+        knobs.validate()
+        B = len(seqs)
+        n = knobs.n
+        kc = _cabi.PolicyKnobsC(*knobs.as_ints())
+        prompts = _i32(np.concatenate([_i32(s.tokens) for s in seqs]))
+        plens = _i32([len(s.tokens) for s in seqs])
+        ctxs = _i32([s.ctx for s in seqs])
+        reserve = knobs.max_new_tokens + 3 * n + 1
+        for s in seqs:
+            self.ensure_capacity(s, len(s.tokens) + reserve)
+        bt = self._block_tables(seqs)
+        fc = _i32(first_correct) if first_correct is not None else None
+        fct = _i32(first_call_tokens).reshape(B, n) if first_call_tokens is not None else None
+        ch, ch_rows = None, 0
+        if choice_idx is not None:
+            ch = _i32(choice_idx)
+            ch = ch.reshape(B, -1, max(n - 1, 1)) if n > 1 else ch
+            ch_rows = ch.shape[1] if n > 1 else 0
+        pad, pad_len = None, 0
+        if pad_stream is not None:
+            pad = _i32(pad_stream).reshape(B, -1)
+            pad_len = pad.shape[1]
+        out_cap = knobs.max_new_tokens + 3 * n + 1
+        out = np.zeros((B, out_cap), np.int32)
+        summ = np.zeros((B, 8), np.int32)
+        iters = np.zeros((B, self.max_calls), np.int32)
+        stats = np.zeros(4, np.float32)
+        trace = np.zeros(max(self.trace_capacity, 1), np.int32) if want_trace else None
+        tl = C.c_int32(0)
+        rc = self.lib.jf_jacobi_run(self.h, B, C.byref(kc), _ptr(prompts), _ptr(plens), _ptr(ctxs), _ptr(fc), _ptr(fct),
+                                    _ptr(ch), ch_rows, _ptr(pad), pad_len, _ptr(bt), max_forwards, _ptr(out), out_cap,
+                                    _ptr(summ), _ptr(iters), _ptr(stats), _ptr(trace), C.byref(tl))
+        if rc == _cabi.JF_ERR_POLICY:
+            code = int(summ[:, 4].max())
+            msg = POLICY_ERRORS.get(code, f"policy error {code}")
+            raise (ValueError if code == 2 else RuntimeError)(msg)
+        _cabi.check(rc, self.h)
+        results = []
+        for i, s in enumerate(seqs):
+            ngen, calls, stop, total_new, _err, total_iters, ctx, _ = [int(x) for x in summ[i]]
+            toks = out[i, :ngen].tolist()
+            s.tokens = s.tokens + toks
+            s.ctx = ctx
+            results.append(JacobiResult(toks, calls, STOP_REASONS.get(stop, str(stop)), total_new, total_iters,
+                                        iters[i, :calls].tolist(), ctx))
+        self.stats["forwards"] += int(stats[0])
+        self.stats["device_ms"] += float(stats[1])
+        self.stats["rows"] += int(stats[2])
+        run = {"forwards": int(stats[0]), "device_ms": float(stats[1]), "rows": int(stats[2])}
+        if want_trace:
+            run["trace"] = parse_trace(trace[:tl.value])
+        return results, run
+
+
+def parse_trace(words: np.ndarray) -> List[dict]:
+    out, i = [], 0
+    w = words.tolist()
+    while i + 5 <= len(w):
+        it, s, ctx, B, L = w[i:i + 5]
+        rows = [w[i + 5 + r * L: i + 5 + (r + 1) * L] for r in range(B)]
+        out.append({"iter": it, "seq": s, "kv_before": ctx, "rows": rows})
+        i += 5 + B * L
+    return out
+
+
+def hf_generate(rt: JacobiRuntime, prompts: Sequence[Sequence[int]], *, n: int, max_new_tokens: int, mode: str = "multiblock",
+                K: int = 2, r: float = 0.85, lookahead_start_ratio: float = 0.0, n_gram_pool_size: int = 4,
+                eos: Optional[int] = None, pad: Optional[int] = None, max_iteration_count: int = 128,
+                max_calls: int = 1024, rngs=None, want_trace: bool = False):
+    """The reference driver protocol (JacobiForcing/jacobi_forcing_inference_MR_humaneval.py:152-240) for a batch of
+    independent sequences: prefill with a random draft, then ONE device-resident run that chains the per-block calls.
+    `rngs[i]` is the random.Random the i-th sequence draws its draft tokens from."""
+    import random
+    B = len(prompts)
+    rngs = rngs or [random.Random(2 + i) for i in range(B)]
+    seqs, fcs, fcts, chs = [], [], [], []
+    n_calls = min(max_calls, (max_new_tokens + n - 1) // n + 2)
+    prefill_ms = 0.0
+    for p, rng in zip(prompts, rngs):
+        s = rt.new_sequence()
+        draft = draw_prefill_draft(rng, p, n)
+        fc, drafted, ms = rt.prefill(s, p, draft)
+        prefill_ms += ms
+        seqs.append(s); fcs.append(fc); fcts.append(drafted)
+        chs.append(draw_choice_indices(rng, len(p), n, n_calls + 1))
+    knobs = PolicyKnobs(mode=MODES[mode], n=n, K=K, r=r, lookahead_start_ratio=lookahead_start_ratio,
+                        n_gram_pool_size=n_gram_pool_size, eos=eos, pad=pad, max_iteration_count=max_iteration_count,
+                        max_new_tokens=max_new_tokens, max_calls=min(max_calls, rt.max_calls), vocab=rt.vocab)
+    results, run = rt.jacobi_run(seqs, knobs, fcs, fcts, choice_idx=chs, want_trace=want_trace)
+    run["prefill_ms"] = prefill_ms
+    return seqs, results, run
