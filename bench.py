@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — greedy Jacobi decoding throughput (tokens/sec + Jacobi iterations to fixed point), Qwen2.5-7B shape,
+block size n=32, synthetic 512-token prompt / 512 new tokens, random-init weights (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's B200 path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle port) on the host cores
+
+A "step" = one generation: the device-resident Jacobi loop produces `--gen` new tokens for every sequence of the batch
+from an already prefilled prompt (the reference's metric excludes prefill: toks_per_sec = new_tokens / gen_only_time,
+JacobiForcing/jacobi_forcing_inference_MR_humaneval.py:217-230, 250).
+  value  = new tokens / device time of the persistent kernel (inputs resident in HBM), max over ranks
+  e2e    = new tokens / wall time of the C-ABI call jf_jacobi_run with HOST buffers (H2D of prompts, drafts, block
+           tables and D2H of the generated ids inside the timed region)
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "tokens/sec (greedy Jacobi decode, Qwen2.5-7B random-init, n=32, 512 prompt / 512 gen, prefill excluded)"
+UNIT = "tokens/s"
+
+SHAPES = {
+    "qwen2.5-coder-7b": dict(hidden_size=3584, num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4,
+                             head_dim=128, intermediate_size=18944, vocab_size=152064, tie_word_embeddings=False,
+                             rope_theta=1e6, max_position_embeddings=32768, rms_norm_eps=1e-6),
+    "qwen2-0.5b": dict(hidden_size=896, num_hidden_layers=24, num_attention_heads=14, num_key_value_heads=2,
+                       head_dim=64, intermediate_size=4864, vocab_size=151936, tie_word_embeddings=True,
+                       rope_theta=1e6, max_position_embeddings=32768, rms_norm_eps=1e-6),
+    "tiny": dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=64,
+                 intermediate_size=512, vocab_size=1000, tie_word_embeddings=False, rope_theta=1e6,
+                 max_position_embeddings=4096, rms_norm_eps=1e-6),
+}
+
+
+def algorithmic_bytes_per_forward(cfg: dict, rows: float, ctx: float, batch_groups: float) -> float:
+    """every layer weight + LM head once, committed KV once per group, in-flight KV written
+    and read, embedding rows gathered.  Logits are never materialised (fused argmax)."""
+    h, L, I, V = cfg["hidden_size"], cfg["num_hidden_layers"], cfg["intermediate_size"], cfg["vocab_size"]
+    q = cfg["num_attention_heads"] * cfg["head_dim"]
+    kv = cfg["num_key_value_heads"] * cfg["head_dim"]
+    w_layer = 2 * (h * (q + 2 * kv) + (q + 2 * kv) + q * h + 3 * h * I + 2 * h)
+    w_head = 2 * V * h
+    kvb = L * 2 * kv * 2
+    return L * w_layer + w_head + batch_groups * ctx * kvb + rows * kvb + rows * h * 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1])); mx.append(float(s[2]))
+                for nm, v in zip(names, s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": (max(mx) if mx else None),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_random_weights(rt, cfg: dict, seed: int, device: str):
+    """HF `_init_weights` shape of randomness (N(0, 0.02) linears / embeddings, unit norms, zero biases), drawn on the
+    GPU tensor by tensor and handed to jf_load_tensor by device pointer under the HF parameter names."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    h, I, V = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"]
+    q = cfg["num_attention_heads"] * cfg["head_dim"]
+    kv = cfg["num_key_value_heads"] * cfg["head_dim"]
+
+    def rnd(*shape):
+        return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+
+    rt.load_tensor("model.embed_tokens.weight", rnd(V, h))
+    if not cfg["tie_word_embeddings"]:
+        rt.load_tensor("lm_head.weight", rnd(V, h))
+    rt.load_tensor("model.norm.weight", torch.ones(h, device=device, dtype=torch.bfloat16))
+    for l in range(cfg["num_hidden_layers"]):
+        p = f"model.layers.{l}."
+        rt.load_tensor(p + "self_attn.q_proj.weight", rnd(q, h))
+        rt.load_tensor(p + "self_attn.k_proj.weight", rnd(kv, h))
+        rt.load_tensor(p + "self_attn.v_proj.weight", rnd(kv, h))
+        rt.load_tensor(p + "self_attn.q_proj.bias", torch.zeros(q, device=device, dtype=torch.bfloat16))
+        rt.load_tensor(p + "self_attn.k_proj.bias", torch.zeros(kv, device=device, dtype=torch.bfloat16))
+        rt.load_tensor(p + "self_attn.v_proj.bias", torch.zeros(kv, device=device, dtype=torch.bfloat16))
+        rt.load_tensor(p + "self_attn.o_proj.weight", rnd(h, q))
+        rt.load_tensor(p + "mlp.gate_proj.weight", rnd(I, h))
+        rt.load_tensor(p + "mlp.up_proj.weight", rnd(I, h))
+        rt.load_tensor(p + "mlp.down_proj.weight", rnd(h, I))
+        rt.load_tensor(p + "input_layernorm.weight", torch.ones(h, device=device, dtype=torch.bfloat16))
+        rt.load_tensor(p + "post_attention_layernorm.weight", torch.ones(h, device=device, dtype=torch.bfloat16))
+    rt.finalize()
+    torch.cuda.synchronize()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU HF path (oracle port) on the host cores
+# --------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    import torch
+    from oracle.cpu_baseline import build_timing_model, host_cores, time_reference_jacobi
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    cfg = SHAPES[args.model]
+    model = build_timing_model(args.model, dtype=torch.bfloat16, seed=0)
+    g = torch.Generator().manual_seed(1)
+    prompt = torch.randint(0, cfg["vocab_size"], (args.prompt,), generator=g).tolist()
+    budget = args.ref_budget_s
+    per_step = []
+    for i in range(args.warmup + args.steps):
+        res = time_reference_jacobi(model, prompt, args.n, mode=args.mode, max_new_tokens=args.n, budget_s=budget,
+                                    K=args.K, r=args.r, pool=args.pool, pad=0, draft_seed=2 + i)
+        if i >= args.warmup:
+            per_step.append(res)
+    toks = sum(r["tokens"] for r in per_step)
+    secs = sum(r["seconds"] for r in per_step)
+    iters = sum(r["iters"] for r in per_step)
+    value = toks / secs if secs > 0 else 0.0
+    sample = (f"per step: prefill {args.prompt}+{args.n} tokens (untimed) then one n={args.n} block "
+              f"({args.mode}) of the reference's HF Jacobi path on CPU, bf16, {cores} threads; weights recycled from "
+              f"one N(0,0.02) pool (timing only)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(per_step)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, 1, "cpu"),
+        "iterations": iters, "tokens": toks, "iters_per_token": (iters / toks if toks else None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world: int, where: str) -> dict:
+    return {"workload": f"{args.model} random-init, block_size n={args.n}, {args.mode} greedy Jacobi "
+                        f"(K={args.K}, r={args.r}, pool={args.pool}), batch={args.batch} per GPU, "
+                        f"prompt={args.prompt}, gen={args.gen}, EOS disabled",
+            "baseline_config": "configs[1]: Qwen2.5-Coder-7B random-init, block_size=32, batch=1, 1xB200, greedy "
+                               "single-block Jacobi",
+            "parallelism": ("single GPU" if world == 1 else f"{world} independent replicas (one sequence batch per "
+                            "GPU, no data-path collective; tensor-parallel sharding not built yet)"),
+            "l2_policy": "inputs larger than L2: every forward streams 15.2 GB of weights (L2 = 126 MB)",
+            "where": where}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from jacobiforcing_b200.policy import MODES, PolicyKnobs, draw_choice_indices, draw_prefill_draft
+    from jacobiforcing_b200.runtime import JacobiRuntime
+
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    cfg = SHAPES[args.model]
+    B, P, G, n = args.batch, args.prompt, args.gen, args.n
+    rows_cap = max(P + n, B * n * (2 if args.mode == "multiblock" else 1) * max(1, args.pool if args.mode == "multiblock" else 1))
+    rows_cap = min(max(rows_cap, 64), 4096)
+    pages = (P + G + 3 * n + 255) // 256 + 1
+    rt = JacobiRuntime(cfg, device=local_rank, max_rows=rows_cap, max_seqs=B, num_kv_pages=pages * B,
+                       max_pages_per_seq=pages, gen_capacity=P + G + 4 * n + 8, max_calls=G // n + 8)
+    load_random_weights(rt, cfg, seed=1234 + rank, device=device)
+
+    knobs = PolicyKnobs(mode=MODES[args.mode], n=n, K=args.K, r=args.r, n_gram_pool_size=args.pool, eos=None, pad=0,
+                        max_iteration_count=128, max_new_tokens=G, max_calls=G // n + 4, vocab=cfg["vocab_size"])
+    g = torch.Generator().manual_seed(1 + rank)
+    prompts = torch.randint(0, cfg["vocab_size"], (B, P), generator=g).tolist()
+
+    def one_step(step_idx: int):
+        seqs, fcs, fcts, chs = [], [], [], []
+        t_pre = 0.0
+        for b in range(B):
+            rng = random.Random(2 + 1000 * step_idx + b)
+            s = rt.new_sequence()
+            fc, drafted, ms = rt.prefill(s, prompts[b], draw_prefill_draft(rng, prompts[b], n))
+            t_pre += ms
+            seqs.append(s); fcs.append(fc); fcts.append(drafted)
+            chs.append(draw_choice_indices(rng, P, n, G // n + 5))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        results, run = rt.jacobi_run(seqs, knobs, fcs, fcts, choice_idx=chs)     # host buffers in, host ids out
+        wall = time.perf_counter() - t0
+        toks = sum(len(r.tokens) for r in results)
+        iters = run["forwards"]
+        h2d = 4 * (B * P + B * n + B * len(chs[0]) * (n - 1) + B * pages + 3 * B) + 64 * B
+        d2h = 4 * (B * (G + 3 * n + 1) + 8 * B + B * rt.max_calls) + 16
+        for s in seqs:
+            rt.release(s)
+        return {"tokens": toks, "forwards": iters, "device_ms": run["device_ms"], "wall_s": wall, "rows": run["rows"],
+                "prefill_ms": t_pre, "h2d": h2d, "d2h": d2h,
+                "iters_per_seq": [r.total_iterations for r in results],
+                "stop": [r.stop_reason for r in results]}
+
+    for i in range(args.warmup):
+        one_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = rt.launches
+    t_begin = time.perf_counter()
+    steps = [one_step(args.warmup + i) for i in range(args.steps)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_total = time.perf_counter() - t_begin
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = rt.launches - launches0
+
+    toks = sum(s["tokens"] for s in steps)
+    dev_s = sum(s["device_ms"] for s in steps) / 1e3
+    wall_s = sum(s["wall_s"] for s in steps)
+    fwd = sum(s["forwards"] for s in steps)
+    rows = sum(s["rows"] for s in steps)
+    stats = torch.tensor([dev_s, wall_s, float(toks), float(fwd), float(rows), float(launches)], device=device,
+                         dtype=torch.float64)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_s_max, wall_s_max = float(mx[0]), float(mx[1])
+        toks_all, fwd_all, rows_all, launches_all = float(sm[2]), float(sm[3]), float(sm[4]), int(sm[5])
+    else:
+        dev_s_max, wall_s_max = dev_s, wall_s
+        toks_all, fwd_all, rows_all, launches_all = float(toks), float(fwd), float(rows), launches
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = toks_all / dev_s_max
+    e2e = toks_all / wall_s_max
+    peak, peak_src = measured_peaks()
+    # roofline of the dominant kernel (the persistent Jacobi kernel; one launch per step) on rank 0
+    mean_rows = rows / max(1, fwd)
+    mean_ctx = P + G / 2.0
+    groups_per_fwd = mean_rows / max(1.0, float(n)) if args.mode == "single" else max(1.0, mean_rows / (2.0 * n))
+    bytes_fwd = algorithmic_bytes_per_forward(cfg, mean_rows, mean_ctx, max(float(B), groups_per_fwd))
+    bytes_launch = bytes_fwd * fwd / max(1, len(steps))
+    launch_s = dev_s / max(1, len(steps))
+    achieved = bytes_launch / launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "jf_persistent_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_forward": bytes_fwd, "forwards_per_launch": fwd / max(1, len(steps)),
+                "ms_per_forward": 1e3 * dev_s / max(1, fwd)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle.cpu_baseline import build_timing_model, host_cores, time_reference_jacobi
+            cores = host_cores()
+            torch.set_num_threads(cores)
+            t0 = time.perf_counter()
+            model = build_timing_model(args.model, dtype=torch.bfloat16, seed=0)
+            res = time_reference_jacobi(model, prompts[0], n, mode=args.mode, max_new_tokens=n,
+                                        budget_s=args.ref_budget_s, K=args.K, r=args.r, pool=args.pool, pad=0)
+            cpu = {"value": res["tokens"] / res["seconds"] if res["seconds"] > 0 else 0.0, "unit": UNIT,
+                   "cores": cores, "kind": "port",
+                   "sample": f"one n={n} block ({res['tokens']} tokens, {res['iters']} Jacobi iterations, "
+                             f"{res['seconds']:.1f} s) after an untimed {P}+{n}-token prefill, HF transformers CPU bf16 "
+                             f"forward driven by the pinned policy restatement; model build+prefill "
+                             f"{time.perf_counter() - t0 - res['seconds']:.0f} s not counted",
+                   "iters_per_token": res["iters"] / max(1, res["tokens"])}
+            del model
+        except Exception as e:  # the baseline is a reported extra; never lose the GPU line over it
+            cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dev_s_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, world, "B200"),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": steps[0]["h2d"], "d2h_bytes_per_step": steps[0]["d2h"],
+                "ms_per_step": 1e3 * wall_s_max / max(1, args.steps)},
+        "gpu_launches": launches_all,
+        "iterations": {"forwards_total": fwd_all, "tokens_total": toks_all,
+                       "iters_per_token": fwd_all / max(1.0, toks_all) * (B if B > 0 else 1) / B,
+                       "tokens_per_forward_per_seq": toks_all / max(1.0, fwd_all) / B / 1.0,
+                       "iters_per_block_mean": (sum(sum(s["iters_per_seq"]) for s in steps) /
+                                                max(1.0, toks / float(n))),
+                       "rows_per_forward": mean_rows, "stop": steps[-1]["stop"][:4]},
+        "prefill_ms_per_step": sum(s["prefill_ms"] for s in steps) / max(1, len(steps)),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "timed_region_wall_s": t_total,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="qwen2.5-coder-7b", choices=sorted(SHAPES))
+    ap.add_argument("--mode", default="single", choices=["single", "multiblock"])
+    ap.add_argument("--n", type=int, default=32)
+    ap.add_argument("--K", type=int, default=2)
+    ap.add_argument("--r", type=float, default=0.85)
+    ap.add_argument("--pool", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--prompt", type=int, default=512)
+    ap.add_argument("--gen", type=int, default=512)
+    ap.add_argument("--ref-budget-s", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                                  # timing rule: at least three warm-up steps
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

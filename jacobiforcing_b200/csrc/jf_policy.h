@@ -530,7 +530,7 @@ JF_HD inline bool hf_advance(SeqState& s, const PolicyKnobs& kn, const DraftSour
     if (s.calls == 1) {                                             // :206-208
       for (int j = 0; j < kn.n; ++j) input_ids[j] = src.first_call_tokens[j];
     } else {                                                        // :209-215
-      if (src.choice_idx == nullptr || s.calls >= src.choice_rows) {
+      if (kn.n > 1 && (src.choice_idx == nullptr || s.calls >= src.choice_rows)) {
         s.error = PERR_DRAFT_SOURCE; s.finished = 1; s.stop_reason = STOP_ERROR; break;
       }
       input_ids[0] = s.first_correct;

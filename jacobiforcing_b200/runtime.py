@@ -247,10 +247,9 @@ class JacobiRuntime:
         fc = _i32(first_correct) if first_correct is not None else None
         fct = _i32(first_call_tokens).reshape(B, n) if first_call_tokens is not None else None
         ch, ch_rows = None, 0
-        if choice_idx is not None:
-            ch = _i32(choice_idx)
-            ch = ch.reshape(B, -1, max(n - 1, 1)) if n > 1 else ch
-            ch_rows = ch.shape[1] if n > 1 else 0
+        if choice_idx is not None and n > 1:
+            ch = _i32(choice_idx).reshape(B, -1, n - 1)
+            ch_rows = ch.shape[1]
         pad, pad_len = None, 0
         if pad_stream is not None:
             pad = _i32(pad_stream).reshape(B, -1)

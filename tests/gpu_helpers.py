@@ -44,6 +44,7 @@ class DeviceForward:
         self.last_L = 0
         self.sel = 0
         self.n_forwards = 0
+        self.rows_in_cache = 1
 
     def kv_len(self):
         return self.kv
@@ -64,13 +65,18 @@ class DeviceForward:
         groups = [(i * L, L, 0, self.kv) for i in range(B)]
         res = self.rt.forward(toks, groups, [self.seq], 0, B * L)
         self.base, self.last_L, self.sel = self.kv, L, 0
+        self.rows_in_cache = B
         self.kv += L
         self.n_forwards += 1
         g = res["greedy"]
         return [[int(t) for t in g[i * L:(i + 1) * L]] for i in range(B)]
 
     def select_row(self, r):
-        self.sel = r if self.last_L else 0
+        # DynamicCache semantics: the first narrowing after a forward picks the row; once the cache has one row,
+        # further narrowings (the pseudo spans' best_idx = 0, unified.py:487-502) are no-ops
+        if self.rows_in_cache > 1:
+            self.sel = r
+            self.rows_in_cache = 1
 
     def trim(self, n):
         if n > 0:
