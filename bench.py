@@ -102,9 +102,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def load_random_weights(rt, cfg: dict, seed: int, device: str):
-    """HF `_init_weights` shape of randomness (N(0, 0.02) linears / embeddings, unit norms, zero biases), drawn on the
-    GPU tensor by tensor and handed to jf_load_tensor by device pointer under the HF parameter names."""
+def random_weights(cfg: dict, seed: int, device: str):
+    """Yields (HF parameter name, bf16 tensor on `device`): HF `_init_weights` shape of randomness (N(0, 0.02) linears
+    and embeddings, unit norms, zero biases) from one seeded generator, so the GPU arm and the CPU reference arm hold
+    the SAME model when both draw on the same device type."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
     h, I, V = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"]
@@ -114,26 +115,49 @@ def load_random_weights(rt, cfg: dict, seed: int, device: str):
     def rnd(*shape):
         return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * 0.02).to(torch.bfloat16)
 
-    rt.load_tensor("model.embed_tokens.weight", rnd(V, h))
+    def ones(k):
+        return torch.ones(k, device=device, dtype=torch.bfloat16)
+
+    def zeros(k):
+        return torch.zeros(k, device=device, dtype=torch.bfloat16)
+
+    yield "model.embed_tokens.weight", rnd(V, h)
     if not cfg["tie_word_embeddings"]:
-        rt.load_tensor("lm_head.weight", rnd(V, h))
-    rt.load_tensor("model.norm.weight", torch.ones(h, device=device, dtype=torch.bfloat16))
+        yield "lm_head.weight", rnd(V, h)
+    yield "model.norm.weight", ones(h)
     for l in range(cfg["num_hidden_layers"]):
         p = f"model.layers.{l}."
-        rt.load_tensor(p + "self_attn.q_proj.weight", rnd(q, h))
-        rt.load_tensor(p + "self_attn.k_proj.weight", rnd(kv, h))
-        rt.load_tensor(p + "self_attn.v_proj.weight", rnd(kv, h))
-        rt.load_tensor(p + "self_attn.q_proj.bias", torch.zeros(q, device=device, dtype=torch.bfloat16))
-        rt.load_tensor(p + "self_attn.k_proj.bias", torch.zeros(kv, device=device, dtype=torch.bfloat16))
-        rt.load_tensor(p + "self_attn.v_proj.bias", torch.zeros(kv, device=device, dtype=torch.bfloat16))
-        rt.load_tensor(p + "self_attn.o_proj.weight", rnd(h, q))
-        rt.load_tensor(p + "mlp.gate_proj.weight", rnd(I, h))
-        rt.load_tensor(p + "mlp.up_proj.weight", rnd(I, h))
-        rt.load_tensor(p + "mlp.down_proj.weight", rnd(h, I))
-        rt.load_tensor(p + "input_layernorm.weight", torch.ones(h, device=device, dtype=torch.bfloat16))
-        rt.load_tensor(p + "post_attention_layernorm.weight", torch.ones(h, device=device, dtype=torch.bfloat16))
+        yield p + "self_attn.q_proj.weight", rnd(q, h)
+        yield p + "self_attn.k_proj.weight", rnd(kv, h)
+        yield p + "self_attn.v_proj.weight", rnd(kv, h)
+        yield p + "self_attn.q_proj.bias", zeros(q)
+        yield p + "self_attn.k_proj.bias", zeros(kv)
+        yield p + "self_attn.v_proj.bias", zeros(kv)
+        yield p + "self_attn.o_proj.weight", rnd(h, q)
+        yield p + "mlp.gate_proj.weight", rnd(I, h)
+        yield p + "mlp.up_proj.weight", rnd(I, h)
+        yield p + "mlp.down_proj.weight", rnd(h, I)
+        yield p + "input_layernorm.weight", ones(h)
+        yield p + "post_attention_layernorm.weight", ones(h)
+
+
+def load_random_weights(rt, cfg: dict, seed: int, device: str):
+    import torch
+    for name, t in random_weights(cfg, seed, device):
+        rt.load_tensor(name, t)
     rt.finalize()
     torch.cuda.synchronize()
+
+
+def build_cpu_reference_model(args, cfg: dict, seed: int):
+    """The oracle-side HF model holding the same weights as the GPU arm (drawn on cuda:0, copied to the host); falls
+    back to the recycled-pool timing model when no GPU is visible."""
+    import torch
+    from oracle.cpu_baseline import build_model_from_named_tensors, build_timing_model
+    if torch.cuda.is_available():
+        return build_model_from_named_tensors(args.model, ((n, t.cpu()) for n, t in random_weights(cfg, seed, "cuda:0"))), \
+            "same seeded N(0,0.02) weights as the GPU arm"
+    return build_timing_model(args.model, dtype=torch.bfloat16, seed=0), "weights recycled from one N(0,0.02) pool"
 
 
 def measured_peaks():
@@ -152,27 +176,27 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     import torch
-    from oracle.cpu_baseline import build_timing_model, host_cores, time_reference_jacobi
+    from oracle.cpu_baseline import host_cores, time_reference_jacobi
     cores = host_cores()
     torch.set_num_threads(cores)
     cfg = SHAPES[args.model]
-    model = build_timing_model(args.model, dtype=torch.bfloat16, seed=0)
+    model, wdesc = build_cpu_reference_model(args, cfg, 1234)
     g = torch.Generator().manual_seed(1)
     prompt = torch.randint(0, cfg["vocab_size"], (args.prompt,), generator=g).tolist()
     budget = args.ref_budget_s
     per_step = []
     for i in range(args.warmup + args.steps):
-        res = time_reference_jacobi(model, prompt, args.n, mode=args.mode, max_new_tokens=args.n, budget_s=budget,
-                                    K=args.K, r=args.r, pool=args.pool, pad=0, draft_seed=2 + i)
+        res = time_reference_jacobi(model, prompt, args.n, mode=args.mode, max_new_tokens=args.gen, budget_s=budget,
+                                    K=args.K, r=args.r, pool=args.pool, pad=0, draft_seed=2 + 1000 * i)
         if i >= args.warmup:
             per_step.append(res)
     toks = sum(r["tokens"] for r in per_step)
     secs = sum(r["seconds"] for r in per_step)
     iters = sum(r["iters"] for r in per_step)
     value = toks / secs if secs > 0 else 0.0
-    sample = (f"per step: prefill {args.prompt}+{args.n} tokens (untimed) then one n={args.n} block "
-              f"({args.mode}) of the reference's HF Jacobi path on CPU, bf16, {cores} threads; weights recycled from "
-              f"one N(0,0.02) pool (timing only)")
+    sample = (f"per step: prefill {args.prompt}+{args.n} tokens (untimed) then n={args.n} blocks ({args.mode}) of the "
+              f"reference's HF Jacobi path on CPU until {args.gen} tokens or {budget:.0f} s, bf16, {cores} threads; "
+              f"{wdesc}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(per_step)), "higher_is_better": True,
@@ -313,20 +337,22 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            from oracle.cpu_baseline import build_timing_model, host_cores, time_reference_jacobi
+            from oracle.cpu_baseline import host_cores, time_reference_jacobi
             cores = host_cores()
             torch.set_num_threads(cores)
             t0 = time.perf_counter()
-            model = build_timing_model(args.model, dtype=torch.bfloat16, seed=0)
-            res = time_reference_jacobi(model, prompts[0], n, mode=args.mode, max_new_tokens=n,
-                                        budget_s=args.ref_budget_s, K=args.K, r=args.r, pool=args.pool, pad=0)
+            model, wdesc = build_cpu_reference_model(args, cfg, 1234)
+            res = time_reference_jacobi(model, prompts[0], n, mode=args.mode, max_new_tokens=G,
+                                        budget_s=args.ref_budget_s, K=args.K, r=args.r, pool=args.pool, pad=0,
+                                        draft_seed=2 + 1000 * args.warmup)
             cpu = {"value": res["tokens"] / res["seconds"] if res["seconds"] > 0 else 0.0, "unit": UNIT,
                    "cores": cores, "kind": "port",
-                   "sample": f"one n={n} block ({res['tokens']} tokens, {res['iters']} Jacobi iterations, "
-                             f"{res['seconds']:.1f} s) after an untimed {P}+{n}-token prefill, HF transformers CPU bf16 "
-                             f"forward driven by the pinned policy restatement; model build+prefill "
-                             f"{time.perf_counter() - t0 - res['seconds']:.0f} s not counted",
-                   "iters_per_token": res["iters"] / max(1, res["tokens"])}
+                   "sample": f"{res['calls']} n={n} blocks ({res['tokens']} tokens, {res['iters']} Jacobi iterations, "
+                             f"{res['seconds']:.1f} s; budget {args.ref_budget_s:.0f} s) after an untimed {P}+{n}-token "
+                             f"prefill: HF transformers CPU bf16 forward driven by the pinned policy restatement, "
+                             f"{wdesc}; model build+prefill {time.perf_counter() - t0 - res['seconds']:.0f} s not counted",
+                   "iters_per_token": res["iters"] / max(1, res["tokens"]),
+                   "iters_per_s": res["iters"] / res["seconds"] if res["seconds"] > 0 else None}
             del model
         except Exception as e:  # the baseline is a reported extra; never lose the GPU line over it
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
@@ -339,6 +365,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": steps[0]["h2d"], "d2h_bytes_per_step": steps[0]["d2h"],
                 "ms_per_step": 1e3 * wall_s_max / max(1, args.steps)},
         "gpu_launches": launches_all,
+        "forwards_per_s": fwd_all / dev_s_max / max(1, world),
         "iterations": {"forwards_total": fwd_all, "tokens_total": toks_all,
                        "iters_per_token": fwd_all / max(1.0, toks_all) * (B if B > 0 else 1) / B,
                        "tokens_per_forward_per_seq": toks_all / max(1.0, fwd_all) / B / 1.0,

@@ -117,6 +117,12 @@ int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs* knobs, con
                   int32_t max_forwards, int32_t* out_tokens, int32_t out_capacity, int32_t* out_summary,
                   int32_t* iters_log, float* run_stats, int32_t* trace, int32_t* trace_len);
 
+/* Stage profile (the reference's PROFILE=1 ProfileTimer, engine/model_runner.py:26-152, without its synchronising
+ * side effects): record SM-clock stamps (arrival of CTA 0, barrier release) at every grid barrier of forward number
+ * `forward_index` of the following launches (-1 = off); read them back after a run.  sm_clock_khz converts to time. */
+int jf_profile_enable(jf_handle h, int32_t forward_index);
+int jf_profile_read(jf_handle h, int64_t* stamps, int32_t capacity, int32_t* n_stamps, int32_t* sm_clock_khz);
+
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches claim). */
 int64_t jf_launch_count(jf_handle h);
 

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libjacobi_b200.so")
 EXPORTS = [
     "jf_create", "jf_destroy", "jf_last_error", "jf_device_info", "jf_load_tensor", "jf_finalize_weights",
     "jf_set_rope_tables", "jf_kv_info", "jf_forward", "jf_commit_rows", "jf_jacobi_run", "jf_launch_count",
+    "jf_profile_enable", "jf_profile_read",
 ]
 
 JF_OK, JF_ERR_INVALID, JF_ERR_CUDA, JF_ERR_CAPACITY, JF_ERR_UNSUPPORTED, JF_ERR_POLICY = 0, -1, -2, -3, -4, -5
@@ -62,6 +63,8 @@ def load() -> C.CDLL:
     lib.jf_commit_rows.argtypes = [vp, i32, vp, i32, vp]
     lib.jf_jacobi_run.argtypes = [vp, i32, C.POINTER(PolicyKnobsC), vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32,
                                   vp, i32, vp, vp, vp, vp, i32p]
+    lib.jf_profile_enable.argtypes = [vp, i32]
+    lib.jf_profile_read.argtypes = [vp, i64p, i32, i32p, i32p]
     lib.jf_launch_count.argtypes = [vp]
     lib.jf_launch_count.restype = C.c_int64
     for name in EXPORTS:

@@ -234,9 +234,13 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.attn_o, (size_t)c.attn_slots_cap * md.n_q * md.d, h->bytes_act);
   ALLOC(c.attn_ml, (size_t)c.attn_slots_cap * md.n_q * 2, h->bytes_act);
   ALLOC(c.argmax_keys, c.T_cap, h->bytes_act);
+  ALLOC(c.row_ss, (size_t)c.T_cap * 8, h->bytes_act);
+  ALLOC(c.row_cnt, c.T_cap, h->bytes_act);
   ALLOC(c.hdr, 1, h->bytes_act);
   ALLOC(c.tok, c.T_cap, h->bytes_act);
   ALLOC(c.row_group, c.T_cap, h->bytes_act);
+  ALLOC(c.row_pos, c.T_cap, h->bytes_act);
+  ALLOC(c.row_attn, c.T_cap, h->bytes_act);
   ALLOC(c.groups, c.G_cap, h->bytes_act);
   ALLOC(c.commits, c.T_cap, h->bytes_act);
   ALLOC(c.greedy, c.T_cap, h->bytes_act);
@@ -290,6 +294,40 @@ extern "C" int jf_device_info(jf_handle h, int32_t* sm_count, int64_t* bw, int64
 }
 
 extern "C" int64_t jf_launch_count(jf_handle h) { return h ? h->launches : 0; }
+
+extern "C" int jf_profile_enable(jf_handle h, int32_t forward_index) {
+  if (!h) return JF_ERR_INVALID;
+  cudaSetDevice(h->device);
+  DevCtx& c = h->hctx;
+  if (forward_index >= 0 && c.prof == nullptr) {
+    c.prof_cap = 4096;
+    int rc = dev_alloc(h, &c.prof, (size_t)c.prof_cap, &h->bytes_act);
+    if (rc != JF_OK) return rc;
+    rc = dev_alloc(h, &c.prof_count, 4, &h->bytes_act);
+    if (rc != JF_OK) return rc;
+  }
+  c.prof_forward = forward_index;
+  long long* keep = c.prof;
+  if (forward_index < 0) c.prof = nullptr;
+  if (h->finalized) JF_CUDA(h, cudaMemcpy(h->dctx, &h->hctx, sizeof(DevCtx), cudaMemcpyHostToDevice));
+  c.prof = keep;
+  return JF_OK;
+}
+
+extern "C" int jf_profile_read(jf_handle h, int64_t* stamps, int32_t capacity, int32_t* n_stamps, int32_t* sm_clock_khz) {
+  if (!h || !stamps || !n_stamps) return JF_ERR_INVALID;
+  cudaSetDevice(h->device);
+  DevCtx& c = h->hctx;
+  *n_stamps = 0;
+  if (c.prof == nullptr) return JF_OK;
+  int n = 0;
+  JF_CUDA(h, cudaMemcpy(&n, c.prof_count, 4, cudaMemcpyDeviceToHost));
+  if (n > capacity) n = capacity;
+  if (n > 0) JF_CUDA(h, cudaMemcpy(stamps, c.prof, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  *n_stamps = n;
+  if (sm_clock_khz) cudaDeviceGetAttribute(sm_clock_khz, cudaDevAttrClockRate, h->device);
+  return JF_OK;
+}
 
 extern "C" int jf_kv_info(jf_handle h, int32_t* num_pages, int32_t* page_size, int64_t* bytes_per_page, void** base) {
   if (!h) return JF_ERR_INVALID;
@@ -500,7 +538,8 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
   if (lm_rows < 0 || lm_row0 < 0 || lm_row0 + lm_rows > T || (lm_row0 & 7)) { h->err = "lm rows must lie inside [0,T) and start at a multiple of 8"; return JF_ERR_INVALID; }
   if (logits && lm_rows > kArgmaxRows) { h->err = "logits are available for at most 256 rows per forward"; return JF_ERR_CAPACITY; }
   std::vector<Group> hg(G);
-  std::vector<int> row_group(T, -1);
+  std::vector<int> row_group(T, -1), row_pos(T, 0);
+  std::vector<int2> row_attn(T);
   int units = 0, slots = 0;
   for (int g = 0; g < G; ++g) {
     Group& gr = hg[g];
@@ -515,6 +554,8 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
     for (int i = 0; i < gr.len; ++i) {
       if (row_group[gr.row0 + i] != -1) { h->err = "groups overlap"; return JF_ERR_INVALID; }
       row_group[gr.row0 + i] = g;
+      row_pos[gr.row0 + i] = gr.ctx + i;
+      row_attn[gr.row0 + i] = make_int2(gr.slot0 + i * gr.nchunks, (gr.ctx + i) / c.attn_chunk);
     }
   }
   for (int t = 0; t < T; ++t) if (row_group[t] < 0) { h->err = "a row belongs to no group"; return JF_ERR_INVALID; }
@@ -545,6 +586,8 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
   JF_CUDA(h, cudaMemcpyAsync(c.hdr, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, h->stream));
   JF_CUDA(h, cudaMemcpyAsync(c.tok, tokens, (size_t)T * 4, cudaMemcpyHostToDevice, h->stream));
   JF_CUDA(h, cudaMemcpyAsync(c.row_group, row_group.data(), (size_t)T * 4, cudaMemcpyHostToDevice, h->stream));
+  JF_CUDA(h, cudaMemcpyAsync(c.row_pos, row_pos.data(), (size_t)T * 4, cudaMemcpyHostToDevice, h->stream));
+  JF_CUDA(h, cudaMemcpyAsync(c.row_attn, row_attn.data(), (size_t)T * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
   JF_CUDA(h, cudaMemcpyAsync(c.groups, hg.data(), (size_t)G * sizeof(Group), cudaMemcpyHostToDevice, h->stream));
   if (n_commit > 0) JF_CUDA(h, cudaMemcpyAsync(c.commits, hc.data(), (size_t)n_commit * sizeof(CommitEntry), cudaMemcpyHostToDevice, h->stream));
   JF_CUDA(h, cudaMemcpyAsync(c.block_tables, block_tables, (size_t)n_seqs * c.max_pages_per_seq * 4, cudaMemcpyHostToDevice, h->stream));

@@ -11,24 +11,36 @@
 
 namespace jf {
 
+template <bool kSleep = true>
 __device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned int target) {
-  if (ld_acquire_gpu_u32(counter) >= target) return;
-  const long long t0 = clock64();
-  while (ld_acquire_gpu_u32(counter) < target) {
-    __nanosleep(40);
-    if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+  if (ld_relaxed_gpu_u32(counter) < target) {
+    const long long t0 = clock64();
+    while (ld_relaxed_gpu_u32(counter) < target) {
+      if (kSleep) __nanosleep(40);
+      if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+    }
   }
+  fence_acq_rel_gpu();          // one acquire (one L1 invalidation) per barrier, not one per probe
 }
 
-__device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w, unsigned int& epoch) {
-  __threadfence();
+// Grid barrier of the worker warps.  Writer side: every worker's global stores are ordered before the CTA barrier,
+// and thread 0's release-add after it is cumulative over them (the cooperative-groups grid.sync pattern); the
+// per-thread proxy fence makes those stores visible to bulk-copy (async proxy) reads issued by other CTAs.
+__device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w, unsigned int& epoch,
+                                             int* prof_slot = nullptr) {
   fence_proxy_async_all();
   workers_sync();
   epoch += 1;
   if (w.wtid == 0) {
+    long long t_arrive = 0;
+    if (prof_slot) t_arrive = clock64();
     red_release_gpu_add_u32(c.bar_counter, 1u);
-    wait_epoch(c.bar_counter, epoch * (unsigned int)w.nctas);
-    __threadfence();
+    wait_epoch<false>(c.bar_counter, epoch * (unsigned int)w.nctas);   // critical path: spin, do not sleep
+    if (prof_slot && *prof_slot + 2 <= c.prof_cap) {      // (arrival of CTA 0, release of the barrier)
+      c.prof[*prof_slot] = t_arrive;
+      c.prof[*prof_slot + 1] = clock64();
+      *prof_slot += 2;
+    }
   }
   workers_sync();
 }
@@ -36,7 +48,7 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
 // ---------------------------------------------------------------------------------------------------------------
 // policy stages (CTA 0, worker warps)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void policy_stage_plan(const DevCtx& c, const WorkerCtx& w) {
+__device__ __noinline__ void policy_stage_plan(const DevCtx& c, const WorkerCtx& w) {
   PlanHdr* hdr = c.hdr;
   const int n_lm = __ldcg(&hdr->n_lm_tasks);
   for (int i = 0; i < n_lm; ++i) {
@@ -55,7 +67,7 @@ __device__ void policy_stage_plan(const DevCtx& c, const WorkerCtx& w) {
   }
 }
 
-__device__ void policy_stage_jacobi(const DevCtx& c, const WorkerCtx& w, bool first, int max_forwards) {
+__device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerCtx& w, bool first, int max_forwards) {
   PlanHdr* hdr = c.hdr;
   const int Tprev = first ? 0 : __ldcg(&hdr->T);
   for (int t = w.wtid; t < Tprev; t += kWorkerThreads) {
@@ -162,6 +174,9 @@ __device__ void policy_stage_jacobi(const DevCtx& c, const WorkerCtx& w, bool fi
       const int i = idx / sl.L, j = idx - i * sl.L;
       c.tok[sl.row0 + idx] = st.out_rows[i][j];
       c.row_group[sl.row0 + idx] = sl.g0 + i;
+      c.row_pos[sl.row0 + idx] = sl.ctx_at_forward + j;
+      const Group& g = c.groups[sl.g0 + i];
+      c.row_attn[sl.row0 + idx] = make_int2(g.slot0 + j * g.nchunks, (sl.ctx_at_forward + j) / c.attn_chunk);
     }
   }
 }
@@ -170,6 +185,7 @@ __device__ void policy_stage_jacobi(const DevCtx& c, const WorkerCtx& w, bool fi
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
 enum Role : int { ROLE_W = 0, ROLE_MMA = 1, ROLE_WORKER = 2, ROLE_X = 3 };
+constexpr int kPrefetchTiles = 24;    // 384 KiB per SM, 57 MB chip-wide: well inside the 126 MB L2
 
 struct IterPlan {
   int T, G, done, n_commit, attn_units, n_lm, want_logits;
@@ -187,10 +203,13 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   const int nt_qkv = (md.qkv_dim + 127) >> 7, nt_h = (md.h + 127) >> 7, nt_i = (md.inter + 127) >> 7;
   const int nt_v = (md.vocab + 127) >> 7;
   int nstages = 1, slot_bytes = 0;
+  int prof_n = 0;
+  int* prof_slot = nullptr;
 
-  auto gemm_stage = [&](const GemmTask& t, bool barrier_after) {
+  auto gemm_stage = [&](const GemmTask& t, bool barrier_after, const GemmTask* next = nullptr) {
     if (ROLE == ROLE_W) {
       gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
+      if (next != nullptr) gemm_prefetch_l2(*next, cta, nctas, kPrefetchTiles);
     } else if (ROLE == ROLE_X) {
       wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);
       fence_proxy_async_all();
@@ -201,12 +220,12 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       gemm_epilogue(t, gs, cta, nctas, acc);
     }
     if (barrier_after) {
-      if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch); else epoch += 1;
+      if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch, prof_slot); else epoch += 1;
     }
   };
 #define JF_SIMT_STAGE(body)                                   \
   do {                                                        \
-    if (ROLE == ROLE_WORKER) { body; grid_barrier(c, w, epoch); } else { epoch += 1; } \
+    if (ROLE == ROLE_WORKER) { body; grid_barrier(c, w, epoch, prof_slot); } else { epoch += 1; } \
   } while (0)
 
   if (run_mode == RUN_JACOBI) {
@@ -221,58 +240,100 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     ip.n_commit = __ldcg(&hdr->n_commit); ip.attn_units = __ldcg(&hdr->attn_units);
     ip.n_lm = __ldcg(&hdr->n_lm_tasks); ip.want_logits = __ldcg(&hdr->want_logits);
     if (ip.done) {
-      if (ROLE == ROLE_WORKER) stage_commit(c, w, ip.n_commit);
+      if (ROLE == ROLE_WORKER) {
+        if (prof_slot != nullptr && w.wtid == 0) *c.prof_count = prof_n;
+        stage_commit(c, w, ip.n_commit);
+      }
       break;
     }
     const int T = ip.T;
+    if (ROLE == ROLE_WORKER) {
+      if (prof_slot != nullptr && w.wtid == 0) *c.prof_count = prof_n;     // forward profiled: publish and stop
+      prof_slot = nullptr;
+      if (cta == 0 && c.prof != nullptr && __ldcg(&hdr->iter) == c.prof_forward) {
+        prof_n = 0;
+        prof_slot = &prof_n;
+        if (w.wtid == 0 && c.prof_cap >= 2) { c.prof[0] = clock64(); c.prof[1] = c.prof[0]; prof_n = 2; }
+      }
+    }
     slot_bytes = gemm_slot_bytes(min(kMaxRowsMMA, round_up16(T)));
     nstages = min(kMaxStages, ring_bytes / slot_bytes);
     pipe.stage = 0;
 
     JF_SIMT_STAGE(stage_commit(c, w, ip.n_commit); stage_rows_norm(c, w, T, true, 0, c.layer[0].ln1));
 
-    for (int l = 0; l < md.layers; ++l) {
-      const LayerW& lw = c.layer[l];
+    auto base_task = [&]() {
       GemmTask t;
       t.M = T; t.x_row0 = 0; t.xrows_cap = c.xrows_cap; t.M_cap = c.T_cap; t.out_rows_cap = c.xrows_cap;
-      // QKV projection (split-K partial sums)
-      t.W = lw.wqkv; t.X = c.xn; t.out = c.part; t.n_tiles = nt_qkv; t.k_chunks = kc_h; t.splits = c.splits_qkv;
+      return t;
+    };
+    auto task_qkv = [&](int l) {      // QKV projection (split-K partial sums)
+      GemmTask t = base_task();
+      t.W = c.layer[l].wqkv; t.X = c.xn; t.out = c.part; t.n_tiles = nt_qkv; t.k_chunks = kc_h; t.splits = c.splits_qkv;
       t.N = md.qkv_dim; t.epilogue = EPI_PARTIAL_F32;
-      gemm_stage(t, true);
+      return t;
+    };
+    auto task_o = [&](int l) {
+      GemmTask t = base_task();
+      t.W = c.layer[l].wo; t.X = c.xa; t.out = c.part; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
+      t.N = md.h; t.epilogue = EPI_PARTIAL_F32;
+      return t;
+    };
+    auto task_gu = [&](int l) {       // gate/up projection with the SwiGLU epilogue
+      GemmTask t = base_task();
+      t.W = c.layer[l].wgu; t.X = c.xn; t.out = c.xact; t.n_tiles = nt_i; t.k_chunks = kc_h; t.splits = 1;
+      t.N = md.inter; t.epilogue = EPI_SWIGLU_BF16;
+      return t;
+    };
+    auto task_down = [&](int l) {
+      GemmTask t = base_task();
+      t.W = c.layer[l].wd; t.X = c.xact; t.out = c.part; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
+      t.N = md.h; t.epilogue = EPI_PARTIAL_F32;
+      return t;
+    };
+    auto task_lm = [&](int i) {
+      GemmTask t = base_task();
+      t.W = c.lm_head; t.X = c.xn; t.out = c.argmax_keys; t.n_tiles = nt_v; t.k_chunks = kc_h; t.splits = 1;
+      t.M = __ldcg(&hdr->lm_rows[i]); t.x_row0 = __ldcg(&hdr->lm_row0[i]);
+      t.N = md.vocab; t.epilogue = EPI_ARGMAX;
+      return t;
+    };
+
+    for (int l = 0; l < md.layers; ++l) {
+      const LayerW& lw = c.layer[l];
+      const GemmTask tq = task_qkv(l), to = task_o(l), tg = task_gu(l), td = task_down(l);
+      gemm_stage(tq, true, &to);
       JF_SIMT_STAGE(stage_qkv_rope(c, w, T, l));
       JF_SIMT_STAGE(stage_attention(c, w, l, ip.G, ip.attn_units));
       JF_SIMT_STAGE(stage_attn_combine(c, w, T));
-      // O projection
-      t.W = lw.wo; t.X = c.xa; t.out = c.part; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
-      t.N = md.h; t.epilogue = EPI_PARTIAL_F32;
-      gemm_stage(t, true);
+      gemm_stage(to, true, &tg);
       JF_SIMT_STAGE(stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2));
-      // gate/up projection with the SwiGLU epilogue
-      t.W = lw.wgu; t.X = c.xn; t.out = c.xact; t.n_tiles = nt_i; t.k_chunks = kc_h; t.splits = 1;
-      t.N = md.inter; t.epilogue = EPI_SWIGLU_BF16;
-      gemm_stage(t, true);
-      // down projection
-      t.W = lw.wd; t.X = c.xact; t.out = c.part; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
-      t.N = md.h; t.epilogue = EPI_PARTIAL_F32;
-      gemm_stage(t, true);
+      gemm_stage(tg, true, &td);
+      if (l + 1 < md.layers) {
+        const GemmTask tn = task_qkv(l + 1);
+        gemm_stage(td, true, &tn);
+      } else if (ip.n_lm > 0) {
+        const GemmTask tn = task_lm(0);
+        gemm_stage(td, true, &tn);
+      } else {
+        gemm_stage(td, true);
+      }
       JF_SIMT_STAGE(stage_rows_norm(c, w, T, false, c.splits_down,
                                     (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm));
     }
 
     // LM head: fused bf16-rounded argmax (no logits in HBM); optional fp32 logits for the tolerance checks
     for (int i = 0; i < ip.n_lm; ++i) {
-      GemmTask t;
-      t.W = c.lm_head; t.X = c.xn; t.out = c.argmax_keys; t.n_tiles = nt_v; t.k_chunks = kc_h; t.splits = 1;
-      t.M = __ldcg(&hdr->lm_rows[i]); t.x_row0 = __ldcg(&hdr->lm_row0[i]); t.xrows_cap = c.xrows_cap;
-      t.N = md.vocab; t.M_cap = c.T_cap; t.epilogue = EPI_ARGMAX; t.out_rows_cap = c.xrows_cap;
-      gemm_stage(t, false);
+      GemmTask t = task_lm(i);
+      const GemmTask tn = task_qkv(0);               // the next forward's first weights (harmless if there is none)
+      gemm_stage(t, false, (i + 1 == ip.n_lm) ? &tn : nullptr);
       if (i == 0 && ip.want_logits) {
         t.out = c.logits - (size_t)t.x_row0 * md.vocab;
         t.epilogue = EPI_PARTIAL_F32;
         gemm_stage(t, false);
       }
     }
-    if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch); else epoch += 1;
+    if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch, prof_slot); else epoch += 1;
 
     JF_SIMT_STAGE(if (cta == 0) {
       if (run_mode == RUN_JACOBI) policy_stage_jacobi(c, w, false, max_forwards); else policy_stage_plan(c, w);

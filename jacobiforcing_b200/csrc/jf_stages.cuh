@@ -55,68 +55,96 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// rows: (embedding | split-K reduce + residual add) -> hidden, then RMSNorm -> packed X operand of the next GEMM
+// rows: (embedding | split-K reduce + residual add) -> hidden, then RMSNorm -> packed X operand of the next GEMM.
+// A row is cut into slices of 1024 columns (one CTA each, one 8-column group per thread, every load in flight at
+// once); each slice publishes its sum of squares, and the CTA that arrives last for a row adds the slice sums in slice
+// order (deterministic, independent of who is last) and normalises the whole row.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w, int T, bool embed, int splits,
-                                const __nv_bfloat16* normw) {
+__device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w, int T, bool embed, int splits,
+                                             const __nv_bfloat16* normw) {
   const int h = c.md.h;
   const int nvec = h >> 3;
-  for (int t = w.cta; t < T; t += w.nctas) {
-    float x[8][8];
-    float ss = 0.f;
-    const __nv_bfloat16* erow = nullptr;
-    if (embed) {
-      int tk = __ldcg(&c.tok[t]);
-      tk = tk < 0 ? 0 : (tk >= c.md.vocab ? c.md.vocab - 1 : tk);
-      erow = c.embed + (size_t)tk * h;
-    }
+  const int NS = (nvec + kWorkerThreads - 1) / kWorkerThreads;     // slices per row (<= 8)
+  const int items = T * NS;
+  for (int item = w.cta; item < items; item += w.nctas) {
+    const int t = item / NS, sl = item - t * NS;
+    const int v = sl * kWorkerThreads + w.wtid;
     __nv_bfloat16* hrow = c.hidden + (size_t)t * h;
+    float ss = 0.f;
+    if (v < nvec) {
+      float x[8];
+      if (embed) {
+        int tk = __ldcg(&c.tok[t]);
+        tk = tk < 0 ? 0 : (tk >= c.md.vocab ? c.md.vocab - 1 : tk);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(c.embed + (size_t)tk * h) + v), x);
+      } else {
+        const uint4 rr = __ldcg(reinterpret_cast<const uint4*>(hrow) + v);
+        float4 pa[8], pb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int v = w.wtid + i * kWorkerThreads;
-      if (v < nvec) {
-        if (embed) {
-          unpack8(__ldg(reinterpret_cast<const uint4*>(erow) + v), x[i]);
-        } else {
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int s = 0; s < splits; ++s) {
-            const float4* p = reinterpret_cast<const float4*>(c.part + ((size_t)s * c.T_cap + t) * h) + v * 2;
-            const float4 a = __ldcg(p), b = __ldcg(p + 1);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        for (int s2 = 0; s2 < 8; ++s2) {
+          if (s2 < splits) {
+            const float4* p = reinterpret_cast<const float4*>(c.part + ((size_t)s2 * c.T_cap + t) * h) + v * 2;
+            pa[s2] = __ldcg(p);
+            pb[s2] = __ldcg(p + 1);
           }
-          float r[8];
-          unpack8(__ldcg(reinterpret_cast<const uint4*>(hrow) + v), r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[i][j] = bf16_round(r[j] + bf16_round(acc[j]));
         }
-        reinterpret_cast<uint4*>(hrow)[v] = pack8(x[i]);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss += x[i][j] * x[i][j];
+        for (int s2 = 0; s2 < 8; ++s2) {                    // slice order: deterministic
+          if (s2 < splits) {
+            acc[0] += pa[s2].x; acc[1] += pa[s2].y; acc[2] += pa[s2].z; acc[3] += pa[s2].w;
+            acc[4] += pb[s2].x; acc[5] += pb[s2].y; acc[6] += pb[s2].z; acc[7] += pb[s2].w;
+          }
+        }
+        float r[8];
+        unpack8(rr, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = bf16_round(r[j] + bf16_round(acc[j]));
       }
+      reinterpret_cast<uint4*>(hrow)[v] = pack8(x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += x[j] * x[j];
     }
     ss = block_sum_128(ss, w);
-    const float rstd = 1.0f / sqrtf(ss / (float)h + c.md.eps);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int v = w.wtid + i * kWorkerThreads;
-      if (v < nvec) {
-        float wt[8], o[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(normw) + v), wt);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = wt[j] * bf16_round(x[i][j] * rstd);
-        uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(v >> 3) * c.xrows_cap + t) * 128 +
-                       (((v & 7) ^ (t & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = pack8(o);
+    if (w.wtid == 0) {
+      int last = 1;
+      if (NS > 1) {
+        c.row_ss[t * 8 + sl] = ss;
+        __threadfence();   // cumulative over the slice's stores of the other threads (ordered by the barrier above)
+        last = (atomicAdd(&c.row_cnt[t], 1) == NS - 1) ? 1 : 0;
+        if (last) { __threadfence(); c.row_cnt[t] = 0; }
       }
+      reinterpret_cast<int*>(w.red)[8] = last;
+    }
+    named_bar_sync(kBarReduce, kWorkerThreads);
+    const bool last = reinterpret_cast<const int*>(w.red)[8] != 0;
+    named_bar_sync(kBarReduce, kWorkerThreads);
+    if (!last) continue;
+    float total = ss;
+    if (NS > 1) {
+      total = 0.f;
+      for (int s2 = 0; s2 < NS; ++s2) total += __ldcg(&c.row_ss[t * 8 + s2]);
+    }
+    const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
+#pragma unroll 4
+    for (int vv = w.wtid; vv < nvec; vv += kWorkerThreads) {
+      float x[8], wt[8], o[8];
+      unpack8(__ldcg(reinterpret_cast<const uint4*>(hrow) + vv), x);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(normw) + vv), wt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wt[j] * bf16_round(x[j] * rstd);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(vv >> 3) * c.xrows_cap + t) * 128 +
+                     (((vv & 7) ^ (t & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst) = pack8(o);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// q/k/v: split-K reduce + bias -> bf16, rotary embedding in bf16 arithmetic, scatter to qbuf / in-flight KV scratch
+// q/k/v: split-K reduce + bias -> bf16, rotary embedding in bf16 arithmetic, scatter to qbuf / in-flight KV scratch.
+// One warp per (row, head slot); two items are processed together so both items' loads are in flight at once.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w, int T, int layer) {
+__device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w, int T, int layer) {
   const ModelDims& md = c.md;
   const int d = md.d, half = d >> 1, ppl = d >> 6;     // pairs per lane: 1 (d=64) or 2 (d=128)
   const int nslots = md.n_q + 2 * md.n_kv;
@@ -124,50 +152,69 @@ __device__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w, int T, int l
   const int splits = c.splits_qkv;
   const float* bias = c.layer[layer].bqkv;
   const int items = T * nslots;
-  for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
-    const int t = item / nslots, slot = item - t * nslots;
-    const int col0 = slot * d;
-    const int g = __ldcg(&c.row_group[t]);
-    int pos = __ldcg(&c.groups[g].ctx) + (t - __ldcg(&c.groups[g].row0));
-    pos = pos < 0 ? 0 : (pos >= md.max_pos ? md.max_pos - 1 : pos);
-    float lo[2], hi[2];
+  const int stride = w.nctas * 4;
+  const size_t sstride = (size_t)c.T_cap * N;
+  for (int item0 = w.cta * 4 + w.wwarp; item0 < items; item0 += 2 * stride) {
+    float lo[2][2], hi[2][2];
+    int tt[2], slot[2], pos[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (j < ppl) {
-        const int e = w.lane * ppl + j;
-        float sl = 0.f, sh = 0.f;
-        for (int s = 0; s < splits; ++s) {
-          const float* p = c.part + ((size_t)s * c.T_cap + t) * N + col0;
-          sl += __ldcg(p + e);
-          sh += __ldcg(p + half + e);
+    for (int q = 0; q < 2; ++q) {
+      const int item = item0 + q * stride;
+      lo[q][0] = lo[q][1] = hi[q][0] = hi[q][1] = 0.f;
+      tt[q] = -1;
+      if (item < items) {
+        const int t = item / nslots;
+        tt[q] = t; slot[q] = item - t * nslots;
+        pos[q] = __ldcg(&c.row_pos[t]);
+        const float* p0 = c.part + (size_t)t * N + slot[q] * d + w.lane * ppl;
+        if (ppl == 2) {
+          float2 vl[8], vh[8];
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2)
+            if (s2 < splits) {
+              vl[s2] = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * sstride));
+              vh[s2] = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * sstride + half));
+            }
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2)
+            if (s2 < splits) { lo[q][0] += vl[s2].x; lo[q][1] += vl[s2].y; hi[q][0] += vh[s2].x; hi[q][1] += vh[s2].y; }
+        } else {
+          float vl[8], vh[8];
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2)
+            if (s2 < splits) { vl[s2] = __ldcg(p0 + s2 * sstride); vh[s2] = __ldcg(p0 + s2 * sstride + half); }
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2)
+            if (s2 < splits) { lo[q][0] += vl[s2]; hi[q][0] += vh[s2]; }
         }
-        lo[j] = bf16_round(sl + __ldg(bias + col0 + e));
-        hi[j] = bf16_round(sh + __ldg(bias + col0 + half + e));
       }
     }
-    if (slot < md.n_q + md.n_kv) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (tt[q] < 0) continue;
+      const int t = tt[q], col0 = slot[q] * d;
+      int p = pos[q];
+      p = p < 0 ? 0 : (p >= md.max_pos ? md.max_pos - 1 : p);
+      __nv_bfloat16* dst;
+      if (slot[q] < md.n_q) dst = c.qbuf + (size_t)t * md.q_dim + col0;
+      else if (slot[q] < md.n_q + md.n_kv) dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, t, slot[q] - md.n_q);
+      else dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, t, slot[q] - md.n_q - md.n_kv);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         if (j < ppl) {
           const int e = w.lane * ppl + j;
-          const float cs = __bfloat162float(__ldg(c.rope_cos + (size_t)pos * half + e));
-          const float sn = __bfloat162float(__ldg(c.rope_sin + (size_t)pos * half + e));
-          const float nlo = bf16_round(bf16_round(lo[j] * cs) - bf16_round(hi[j] * sn));
-          const float nhi = bf16_round(bf16_round(hi[j] * cs) + bf16_round(lo[j] * sn));
-          lo[j] = nlo; hi[j] = nhi;
+          float l = bf16_round(lo[q][j] + __ldg(bias + col0 + e));
+          float hv = bf16_round(hi[q][j] + __ldg(bias + col0 + half + e));
+          if (slot[q] < md.n_q + md.n_kv) {
+            const float cs = __bfloat162float(__ldg(c.rope_cos + (size_t)p * half + e));
+            const float sn = __bfloat162float(__ldg(c.rope_sin + (size_t)p * half + e));
+            const float nlo = bf16_round(bf16_round(l * cs) - bf16_round(hv * sn));
+            const float nhi = bf16_round(bf16_round(hv * cs) + bf16_round(l * sn));
+            l = nlo; hv = nhi;
+          }
+          dst[e] = __float2bfloat16_rn(l);
+          dst[half + e] = __float2bfloat16_rn(hv);
         }
-      }
-    }
-    __nv_bfloat16* dst;
-    if (slot < md.n_q) dst = c.qbuf + (size_t)t * md.q_dim + col0;
-    else if (slot < md.n_q + md.n_kv) dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, t, slot - md.n_q);
-    else dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, t, slot - md.n_q - md.n_kv);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (j < ppl) {
-        const int e = w.lane * ppl + j;
-        dst[e] = __float2bfloat16_rn(lo[j]);
-        dst[half + e] = __float2bfloat16_rn(hi[j]);
       }
     }
   }
@@ -179,11 +226,12 @@ __device__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w, int T, int l
 // committed pages and in-flight scratch rows (AR decoding and Jacobi decoding of the same prefix agree bit for bit).
 // ---------------------------------------------------------------------------------------------------------------
 template <int D>
-__device__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, const Group& grp, int g_kvh, int chunk,
+__device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, const Group& grp, int g_kvh, int chunk,
                                int qs) {
   constexpr int LDS = D + 8;                  // padded smem row (bf16 elements) -> conflict-free fragment loads
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem);
   __nv_bfloat16* Vs = Ks + kAttnSub * LDS;
+  const uint32_t ks_addr = smem_u32(Ks), vs_addr = smem_u32(Vs);
   const ModelDims& md = c.md;
   const int ctx = grp.ctx, len = grp.len, row0 = grp.row0;
   const int nkeys = ctx + len;
@@ -230,37 +278,48 @@ __device__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, c
       const int k0 = key_lo + sub * kAttnSub;
       if (!(nsub == 1 && tb > 0)) {
         workers_sync();                                   // previous readers of Ks / Vs are done
-        constexpr int VPR = D / 8;                        // uint4 per row
+        constexpr int VPR = D / 8;                        // 16-byte chunks per row
+        // a 64-key sub-tile never straddles a page (kPage % kAttnSub == 0): one table lookup, then plain strides
+        const __nv_bfloat16* cbase[2] = {nullptr, nullptr};
+        if (k0 < ctx) {
+          const int page = __ldcg(bt + (k0 / kPage));
+          cbase[0] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 0, page, g_kvh, k0 % kPage);
+          cbase[1] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 1, page, g_kvh, k0 % kPage);
+        }
+        const __nv_bfloat16* sbase[2] = {c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, row0, g_kvh),
+                                         c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, row0, g_kvh)};
+        const size_t srow = (size_t)md.n_kv * D;           // scratch stride between consecutive tokens
+#pragma unroll 4
         for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
           const int kv = idx / (kAttnSub * VPR);
           const int rem = idx - kv * (kAttnSub * VPR);
           const int jr = rem / VPR, v = rem - jr * VPR;
           const int pos = k0 + jr;
-          uint4 val = make_uint4(0, 0, 0, 0);
-          if (pos < ctx) {
-            const int page = __ldcg(bt + (pos / kPage));
-            val = __ldcg(reinterpret_cast<const uint4*>(
-                             c.kv_cache + kv_cache_offset(md, c.num_pages, layer, kv, page, g_kvh, pos % kPage)) + v);
-          } else if (pos < nkeys) {
-            val = __ldcg(reinterpret_cast<const uint4*>(
-                             c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, kv, row0 + pos - ctx, g_kvh)) + v);
-          }
-          *reinterpret_cast<uint4*>((kv ? Vs : Ks) + jr * LDS + v * 8) = val;
+          const __nv_bfloat16* src = sbase[kv];
+          uint32_t nbytes = 0;
+          if (pos < ctx) { src = cbase[kv] + (size_t)jr * D + v * 8; nbytes = 16; }
+          else if (pos < nkeys) { src = sbase[kv] + (size_t)(pos - ctx) * srow + v * 8; nbytes = 16; }
+          cp_async_16((kv ? Vs : Ks) + jr * LDS + v * 8, src, nbytes);
         }
+        cp_async_commit();
+        cp_async_wait_all();
         workers_sync();
       }
       if (!tactive || k0 > ctx + min(i0 + 15, len - 1)) continue;
 
       float s[8][4];
+      // K fragments with ldmatrix: matrix m of one x4 = keys nt*8..+7 (rows) x dims (ks2*32 + m*8)..+7, i.e. (b0, b1) of
+      // k-steps 2*ks2 and 2*ks2+1 for n-tile nt
+      const uint32_t k_lane = ks_addr + (uint32_t)(((w.lane & 7) * LDS + (w.lane >> 3) * 8) * 2);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const __nv_bfloat16* kr = Ks + (nt * 8 + r0) * LDS + c2;
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-          mma_bf16_16816(s[nt], qf[ks], b0, b1);
+        for (int ks2 = 0; ks2 < D / 32; ++ks2) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(k_lane + (uint32_t)((nt * 8 * LDS + ks2 * 32) * 2), b0, b1, b2, b3);
+          mma_bf16_16816(s[nt], qf[2 * ks2], b0, b1);
+          mma_bf16_16816(s[nt], qf[2 * ks2 + 1], b2, b3);
         }
       }
       // scale, causal mask, running max
@@ -306,12 +365,16 @@ __device__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, c
         pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
         pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
         pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-        const uint16_t* v0 = reinterpret_cast<const uint16_t*>(Vs + (kk * 16 + c2) * LDS + r0);
+        // V fragments with ldmatrix.trans: matrix m = keys kk*16 + (m&1)*8..+7 (rows) x dims (nd2*16 + (m>>1)*8)..+7,
+        // transposed on load -> (b0, b1) of dim tiles 2*nd2 and 2*nd2+1 for key step kk
+        const uint32_t v_lane = vs_addr + (uint32_t)((((kk * 16 + (w.lane & 7) + ((w.lane >> 3) & 1) * 8) * LDS) +
+                                                     (w.lane >> 4) * 8) * 2);
 #pragma unroll
-        for (int nd = 0; nd < D / 8; ++nd) {
-          const uint32_t b0 = (uint32_t)v0[nd * 8] | ((uint32_t)v0[LDS + nd * 8] << 16);
-          const uint32_t b1 = (uint32_t)v0[8 * LDS + nd * 8] | ((uint32_t)v0[9 * LDS + nd * 8] << 16);
-          mma_bf16_16816(o[nd], pa, b0, b1);
+        for (int nd2 = 0; nd2 < D / 16; ++nd2) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(v_lane + (uint32_t)(nd2 * 16 * 2), b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * nd2], pa, b0, b1);
+          mma_bf16_16816(o[2 * nd2 + 1], pa, b2, b3);
         }
       }
     }
@@ -348,7 +411,7 @@ __device__ __forceinline__ Group load_group(const DevCtx& c, int g) {
   return grp;
 }
 
-__device__ void stage_attention(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
+__device__ __noinline__ void stage_attention(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
   for (int u = w.cta; u < units; u += w.nctas) {
     int g = 0;
     Group grp = load_group(c, 0);
@@ -368,34 +431,63 @@ __device__ void stage_attention(const DevCtx& c, const WorkerCtx& w, int layer, 
   }
 }
 
-// merge the per-chunk partials of every (token, head) in chunk order; write bf16 into the O-projection operand
-__device__ void stage_attn_combine(const DevCtx& c, const WorkerCtx& w, int T) {
+// merge the per-chunk partials of every (token, head) in chunk order; write bf16 into the O-projection operand.
+// One warp per (token, head); lane ch holds the statistics of chunk ch, the chunk vectors are fetched 16 at a time.
+__device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerCtx& w, int T) {
   const ModelDims& md = c.md;
   const int D = md.d;
   const int vpl = D >> 5;                                  // floats per lane: 4 (d=128) or 2 (d=64)
   const int items = T * md.n_q;
+  const size_t cstride = md.n_q;                            // slots of consecutive chunks are adjacent
   for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
     const int t = item / md.n_q, head = item - t * md.n_q;
-    const Group grp = load_group(c, __ldcg(&c.row_group[t]));
-    const int i = t - grp.row0;
-    const int cmax = (grp.ctx + i) / c.attn_chunk;         // last chunk holding a visible key
-    const size_t base = ((size_t)(grp.slot0 + i * grp.nchunks) * md.n_q + head);
-    const size_t cstride = md.n_q;                          // slots of consecutive chunks are adjacent
+    const int2 ra = __ldcg(&c.row_attn[t]);
+    const int cmax = ra.y;                                  // last chunk holding a visible key
+    const size_t base = (size_t)ra.x * md.n_q + head;
     float m = -INFINITY;
-    for (int ch = 0; ch <= cmax; ++ch) m = fmaxf(m, __ldcg(c.attn_ml + (base + ch * cstride) * 2));
     float l = 0.f;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ch = 0; ch <= cmax; ++ch) {
-      const float2 ml = __ldcg(reinterpret_cast<const float2*>(c.attn_ml + (base + ch * cstride) * 2));
-      const float wgt = (ml.x == -INFINITY) ? 0.f : __expf(ml.x - m);
-      l += wgt * ml.y;
-      const float* op = c.attn_o + (base + ch * cstride) * D + w.lane * vpl;
-      if (vpl == 4) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(op));
-        acc[0] += wgt * v.x; acc[1] += wgt * v.y; acc[2] += wgt * v.z; acc[3] += wgt * v.w;
-      } else {
-        const float2 v = __ldcg(reinterpret_cast<const float2*>(op));
-        acc[0] += wgt * v.x; acc[1] += wgt * v.y;
+    // pass 1 (only when more than 32 chunks): global maximum
+    if (cmax >= 32) {
+      for (int c0 = 0; c0 <= cmax; c0 += 32) {
+        const int ch = c0 + w.lane;
+        float mc = (ch <= cmax) ? __ldcg(c.attn_ml + (base + ch * cstride) * 2) : -INFINITY;
+        m = fmaxf(m, mc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    for (int c0 = 0; c0 <= cmax; c0 += 32) {
+      const int chl = c0 + w.lane;
+      float2 ml = make_float2(-INFINITY, 0.f);
+      if (chl <= cmax) ml = __ldcg(reinterpret_cast<const float2*>(c.attn_ml + (base + chl * cstride) * 2));
+      if (cmax < 32) {
+        m = ml.x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      }
+      const float wl = (ml.x == -INFINITY) ? 0.f : __expf(ml.x - m);
+      const float ll = wl * ml.y;
+      const int nch = min(32, cmax + 1 - c0);
+      for (int cc = 0; cc < nch; cc += 16) {                // sixteen chunks' vectors in flight at a time
+        float4 v4[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          if (cc + u < nch) {
+            const float* op = c.attn_o + (base + (size_t)(c0 + cc + u) * cstride) * D + w.lane * vpl;
+            if (vpl == 4) v4[u] = __ldcg(reinterpret_cast<const float4*>(op));
+            else { const float2 t2 = __ldcg(reinterpret_cast<const float2*>(op)); v4[u] = make_float4(t2.x, t2.y, 0.f, 0.f); }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {                      // chunk order: deterministic
+          const float wgt = __shfl_sync(0xffffffffu, wl, (cc + u) & 31);
+          const float lc = __shfl_sync(0xffffffffu, ll, (cc + u) & 31);
+          if (cc + u < nch) {
+            l += lc;
+            acc[0] += wgt * v4[u].x; acc[1] += wgt * v4[u].y; acc[2] += wgt * v4[u].z; acc[3] += wgt * v4[u].w;
+          }
+        }
       }
     }
     const float inv = 1.0f / l;
@@ -413,7 +505,7 @@ __device__ void stage_attn_combine(const DevCtx& c, const WorkerCtx& w, int T) {
 }
 
 // accepted in-flight K/V rows -> their pages (all layers)
-__device__ void stage_commit(const DevCtx& c, const WorkerCtx& w, int n_commit) {
+__device__ __noinline__ void stage_commit(const DevCtx& c, const WorkerCtx& w, int n_commit) {
   const ModelDims& md = c.md;
   const int per = md.layers * 2;
   const int items = n_commit * per;

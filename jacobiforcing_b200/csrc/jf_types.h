@@ -99,11 +99,15 @@ struct DevCtx {
   int attn_slots_cap;
   int attn_chunk;                    // keys per attention unit (multiple of kAttnSub)
   unsigned long long* argmax_keys;   // [T_cap]
+  float* row_ss;                     // [T_cap][8] per-slice sums of squares of the row being normalised
+  int* row_cnt;                      // [T_cap] slices arrived (the last arriver normalises the row)
   int splits_qkv, splits_o, splits_down;
   // ---- plan (written by the host in plan mode, by the policy stage in Jacobi mode)
   PlanHdr* hdr;
   int* tok;                          // [T_cap]
   int* row_group;                    // [T_cap]
+  int* row_pos;                      // [T_cap] absolute position of the row's token
+  int2* row_attn;                    // [T_cap] {first partial slot of the row, last key chunk it can see}
   Group* groups;                     // [G_cap]
   CommitEntry* commits;              // [T_cap]
   // ---- outputs / policy
@@ -123,6 +127,11 @@ struct DevCtx {
   int* trace_len;
   // ---- sync
   unsigned int* bar_counter;
+  // ---- optional stage profile: SM-clock stamps taken by CTA 0 after every grid barrier of forward `prof_forward`
+  long long* prof;
+  int prof_cap;
+  int prof_forward;
+  int* prof_count;
 };
 
 enum RunMode : int { RUN_PLAN = 0, RUN_JACOBI = 1 };

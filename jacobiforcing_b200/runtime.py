@@ -103,12 +103,41 @@ class JacobiRuntime:
         _cabi.check(self.lib.jf_device_info(self.h, C.byref(sm), C.byref(bw), C.byref(bkv), C.byref(bact)), self.h)
         return {"sm_count": sm.value, "bytes_weights": bw.value, "bytes_kv": bkv.value, "bytes_act": bact.value}
 
+    # ---- stage profile (ProfileTimer equivalent, model_runner.py:26-152) -------------------------------------------
+    def profile_enable(self, forward_index: int) -> None:
+        _cabi.check(self.lib.jf_profile_enable(self.h, forward_index), self.h)
+
+    def profile_read(self) -> dict:
+        """Per grid barrier of the profiled forward: microseconds CTA 0 spent working in the stage that ends at the
+        barrier and waiting at it; stage names follow the kernel's static schedule."""
+        stamps = np.zeros(4096, np.int64)
+        n, khz = C.c_int32(0), C.c_int32(0)
+        _cabi.check(self.lib.jf_profile_read(self.h, stamps.ctypes.data_as(C.POINTER(C.c_int64)), 4096, C.byref(n),
+                                             C.byref(khz)), self.h)
+        st = stamps[:n.value].astype(np.float64) / (khz.value / 1e3)       # microseconds
+        names = ["start", "embed+norm"]
+        per_layer = ["qkv_gemm", "qkv_rope", "attention", "attn_combine", "o_gemm", "o_reduce_norm", "gate_up_gemm",
+                     "down_gemm", "down_reduce_norm"]
+        for l in range(self.model_cfg.num_hidden_layers):
+            names += [f"L{l}.{s}" for s in per_layer]
+        names += ["lm_head_argmax", "policy"]
+        rows = []
+        for i in range(1, n.value // 2):
+            arrive, release = st[2 * i], st[2 * i + 1]
+            prev_release = st[2 * i - 1]
+            rows.append({"stage": names[i] if i < len(names) else f"#{i}", "work_us": arrive - prev_release,
+                         "wait_us": release - arrive})
+        return {"sm_clock_khz": khz.value, "stages": rows}
+
     # ---- weights (loader.py:27-47 loop stays with the caller; this is the per-tensor weight_loader) ---------------
     def load_tensor(self, name: str, t) -> None:
         import torch
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t)
         t = t.detach().contiguous()
+        if t.is_cuda:
+            # the library copies on its own stream: the producer kernels on torch's stream must have finished
+            torch.cuda.current_stream(t.device).synchronize()
         if t.dtype == torch.bfloat16:
             dt = _cabi.DTYPE_BF16
         elif t.dtype == torch.float16:

@@ -49,6 +49,32 @@ def build_timing_model(name: str, dtype=torch.bfloat16, seed: int = 0, **overrid
     return model.to(dtype).eval()
 
 
+def build_model_from_named_tensors(name: str, named_tensors, dtype=torch.bfloat16, **overrides):
+    """HF Qwen2 on CPU whose parameters are exactly the given (HF name, tensor) pairs."""
+    from transformers import Qwen2ForCausalLM
+    from transformers.models.qwen2.modeling_qwen2 import Qwen2RotaryEmbedding
+    cfg = make_config(name, **overrides)
+    cfg._attn_implementation = "sdpa"
+    with torch.device("meta"):
+        model = Qwen2ForCausalLM(cfg)
+    model = model.to_empty(device="cpu")
+    params = dict(model.named_parameters())
+    seen = set()
+    with torch.no_grad():
+        for pname, t in named_tensors:
+            p = params[pname]
+            assert tuple(p.shape) == tuple(t.shape), pname
+            p.data = t.to(dtype).contiguous()
+            seen.add(pname)
+        model.model.rotary_emb = Qwen2RotaryEmbedding(config=cfg)
+    if cfg.tie_word_embeddings:
+        model.tie_weights()
+        seen.add("lm_head.weight")
+    missing = [k for k in params if k not in seen]
+    assert not missing, f"tensors missing for {missing[:3]}"
+    return model.to(dtype).eval()
+
+
 def time_reference_jacobi(model, prompt: List[int], n: int, mode: str = "single", max_new_tokens: Optional[int] = None,
                           budget_s: float = 20.0, K: int = 2, r: float = 0.85, pool: int = 4, pad: int = 0,
                           draft_seed: int = 2) -> Dict[str, float]:

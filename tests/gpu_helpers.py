@@ -9,9 +9,9 @@ from jacobiforcing_b200.runtime import JacobiRuntime
 from oracle.hf_model import build_model, rope_tables, state_dict_bf16
 
 
-def make_pair(name: str, seed: int = 0, **rt_kw):
+def make_pair(name: str, seed: int = 0, model_overrides=None, **rt_kw):
     """(hf_model_fp32_with_bf16_rounded_weights, runtime).  Both sides hold bit-identical weights."""
-    model = build_model(name, seed=seed, dtype=torch.float32)
+    model = build_model(name, seed=seed, dtype=torch.float32, **(model_overrides or {}))
     sd = state_dict_bf16(model)
     with torch.no_grad():                       # round the oracle's weights to bf16 too
         for k, v in model.state_dict().items():
