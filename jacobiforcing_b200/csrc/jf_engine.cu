@@ -15,6 +15,7 @@
 using namespace jf;
 
 static_assert(sizeof(jf_policy_knobs) == sizeof(PolicyKnobs), "jf_policy_knobs must mirror jf::PolicyKnobs");
+static_assert(sizeof(DevCtx) % 16 == 0 && sizeof(DevCtx) <= 4608, "DevCtx is staged in shared memory");
 
 static thread_local std::string g_create_error;
 
@@ -31,6 +32,11 @@ struct jf_engine {
   std::vector<void*> allocs;
   std::string err;
   int64_t bytes_weights = 0, bytes_kv = 0, bytes_act = 0;
+  // arenas: one cudaMalloc per class (weights / KV cache / activations+state) so each class sits in few, densely
+  // used 2 MB pages; mode 0 = direct cudaMalloc, 1 = measuring, 2 = carving
+  int arena_mode = 0;
+  uint8_t* arena_base[3] = {nullptr, nullptr, nullptr};
+  size_t arena_off[3] = {0, 0, 0};
   int64_t launches = 0;
   // weight bookkeeping
   std::vector<uint8_t> seen_layer;   // bitmask per layer
@@ -55,11 +61,22 @@ struct jf_engine {
 
 template <typename T>
 static int dev_alloc(jf_engine* h, T** out, size_t count, int64_t* tally, bool zero = true) {
+  const size_t bytes = ((count * sizeof(T) > 0 ? count * sizeof(T) : 16) + 1023) & ~(size_t)1023;
+  if (h->arena_mode != 0) {
+    const int a = (tally == &h->bytes_weights) ? 0 : (tally == &h->bytes_kv) ? 1 : 2;
+    if (h->arena_mode == 2) {
+      *out = reinterpret_cast<T*>(h->arena_base[a] + h->arena_off[a]);
+      if (tally) *tally += (int64_t)bytes;
+    } else {
+      *out = nullptr;
+    }
+    h->arena_off[a] += bytes;
+    return JF_OK;
+  }
   void* p = nullptr;
-  const size_t bytes = count * sizeof(T);
-  cudaError_t e = cudaMalloc(&p, bytes > 0 ? bytes : 16);
+  cudaError_t e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return JF_ERR_CUDA; }
-  if (zero) cudaMemsetAsync(p, 0, bytes > 0 ? bytes : 16, h->stream);
+  if (zero) cudaMemsetAsync(p, 0, bytes, h->stream);
   h->allocs.push_back(p);
   if (tally) *tally += (int64_t)bytes;
   *out = reinterpret_cast<T*>(p);
@@ -190,8 +207,9 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   c.splits_down = pick_splits(nt_h, kc_i, h->sm_count);
   h->max_splits = std::max(c.splits_qkv, std::max(c.splits_o, c.splits_down));
 
-  int rc;
-#define ALLOC(ptr, count, tally) if ((rc = dev_alloc(h, &(ptr), (size_t)(count), &(tally))) != JF_OK) return fail(rc, h->err)
+  int rc = JF_OK;
+#define ALLOC(ptr, count, tally) if ((rc = dev_alloc(h, &(ptr), (size_t)(count), &(tally))) != JF_OK) return rc
+  auto layout = [&]() -> int {
   // ---- weights
   __nv_bfloat16 *embed, *lm_head, *final_norm, *cosb, *sinb;
   ALLOC(embed, (size_t)md.vocab * md.h, h->bytes_weights);
@@ -214,12 +232,12 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   h->seen_layer.assign(md.layers, 0);
   {
     const int n = md.max_pos * (md.d / 2);
-    rope_table_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(cosb, sinb, md.max_pos, md.d / 2, md.rope_theta, md.d);
+    if (h->arena_mode == 2)
+      rope_table_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(cosb, sinb, md.max_pos, md.d / 2, md.rope_theta, md.d);
   }
   // ---- KV
   c.num_pages = rt.num_kv_pages; c.max_pages_per_seq = rt.max_pages_per_seq;
   ALLOC(c.kv_cache, (size_t)md.layers * 2 * rt.num_kv_pages * md.n_kv * kPage * md.d, h->bytes_kv);
-  ALLOC(c.kv_scratch, (size_t)md.layers * 2 * rt.max_rows * md.n_kv * md.d, h->bytes_kv);
   ALLOC(c.block_tables, (size_t)rt.max_seqs * rt.max_pages_per_seq, h->bytes_act);
   // ---- activations
   c.T_cap = rt.max_rows; c.xrows_cap = rt.max_rows; c.S_cap = rt.max_seqs; c.G_cap = rt.max_seqs * kRowsMax;
@@ -227,12 +245,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.hidden, (size_t)c.T_cap * md.h, h->bytes_act);
   ALLOC(c.xn, (size_t)kc_h * c.xrows_cap * 64, h->bytes_act);
   ALLOC(c.xa, (size_t)kc_q * c.xrows_cap * 64, h->bytes_act);
-  ALLOC(c.xact, (size_t)kc_i * c.xrows_cap * 64, h->bytes_act);
-  ALLOC(c.part, (size_t)h->max_splits * c.T_cap * std::max(md.qkv_dim, md.h), h->bytes_act);
   ALLOC(c.qbuf, (size_t)c.T_cap * md.q_dim, h->bytes_act);
   c.attn_slots_cap = rt.attn_slots; c.attn_chunk = rt.attn_chunk;
-  ALLOC(c.attn_o, (size_t)c.attn_slots_cap * md.n_q * md.d, h->bytes_act);
-  ALLOC(c.attn_ml, (size_t)c.attn_slots_cap * md.n_q * 2, h->bytes_act);
   ALLOC(c.argmax_keys, c.T_cap, h->bytes_act);
   ALLOC(c.row_ss, (size_t)c.T_cap * 8, h->bytes_act);
   ALLOC(c.row_cnt, c.T_cap, h->bytes_act);
@@ -245,6 +259,12 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.commits, c.T_cap, h->bytes_act);
   ALLOC(c.greedy, c.T_cap, h->bytes_act);
   c.logits = nullptr;
+  {
+    const char* e1 = getenv("JF_DEBUG_SKIP");
+    c.debug_skip = e1 ? atoi(e1) : 0;
+    const char* e2 = getenv("JF_PREFETCH_TILES");
+    c.prefetch_tiles = e2 ? atoi(e2) : 0;   // measured: no gain from L2 prefetch on B200 (profiles/r01_stage_experiments.txt)
+  }
   ALLOC(c.seq_state, c.S_cap, h->bytes_act);
   ALLOC(c.seq_slot, c.S_cap, h->bytes_act);
   ALLOC(c.knobs, c.S_cap, h->bytes_act);
@@ -257,10 +277,33 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.trace_len, 4, h->bytes_act);
   ALLOC(c.bar_counter, 4, h->bytes_act);
   ALLOC(h->dctx, 1, h->bytes_act);
+  // large, sparsely touched buffers last: the small hot ones above share the arena's first pages
+  c.part_splits = h->max_splits; c.part_n = std::max(md.qkv_dim, md.h);
+  ALLOC(c.part, (size_t)c.T_cap * c.part_splits * c.part_n, h->bytes_act);
+  ALLOC(c.attn_ml, (size_t)c.attn_slots_cap * md.n_q * 2, h->bytes_act);
+  ALLOC(c.attn_o, (size_t)c.attn_slots_cap * md.n_q * md.d, h->bytes_act);
+  ALLOC(c.xact, (size_t)kc_i * c.xrows_cap * 64, h->bytes_act);
+  ALLOC(c.kv_scratch, (size_t)md.layers * 2 * rt.max_rows * md.n_kv * md.d, h->bytes_act);
   // staging: the largest single HF tensor (embedding / lm_head or gate/up/down)
   h->stage_elems = std::max((size_t)md.vocab * md.h, (size_t)md.inter * md.h);
-  ALLOC(h->stage, h->stage_elems, h->bytes_act);
-  ALLOC(h->bias_stage, md.qkv_dim + 128, h->bytes_act);
+    return JF_OK;
+  };
+  h->arena_mode = 1;
+  if ((rc = layout()) != JF_OK) return fail(rc, h->err);
+  for (int a2 = 0; a2 < 3; ++a2) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, h->arena_off[a2] + 4096);
+    if (e != cudaSuccess) return fail(JF_ERR_CUDA, std::string("cudaMalloc (arena): ") + cudaGetErrorString(e));
+    cudaMemsetAsync(p, 0, h->arena_off[a2] + 4096, h->stream);
+    h->allocs.push_back(p);
+    h->arena_base[a2] = reinterpret_cast<uint8_t*>(p);
+    h->arena_off[a2] = 0;
+  }
+  h->arena_mode = 2;
+  if ((rc = layout()) != JF_OK) return fail(rc, h->err);
+  h->arena_mode = 0;
+  if ((rc = dev_alloc(h, &h->stage, h->stage_elems, (int64_t*)nullptr)) != JF_OK) return fail(rc, h->err);
+  if ((rc = dev_alloc(h, &h->bias_stage, (size_t)md.qkv_dim + 128, (int64_t*)nullptr)) != JF_OK) return fail(rc, h->err);
 #undef ALLOC
   if (cudaFuncSetAttribute(jf_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin) != cudaSuccess)
     return fail(JF_ERR_CUDA, "cannot opt in to the full shared memory carve-out");
@@ -305,6 +348,10 @@ extern "C" int jf_profile_enable(jf_handle h, int32_t forward_index) {
     if (rc != JF_OK) return rc;
     rc = dev_alloc(h, &c.prof_count, 4, &h->bytes_act);
     if (rc != JF_OK) return rc;
+    rc = dev_alloc(h, &c.prof_marks, 8192, &h->bytes_act);
+    if (rc != JF_OK) return rc;
+    rc = dev_alloc(h, &c.prof_marks_n, 4, &h->bytes_act);
+    if (rc != JF_OK) return rc;
   }
   c.prof_forward = forward_index;
   long long* keep = c.prof;
@@ -325,6 +372,16 @@ extern "C" int jf_profile_read(jf_handle h, int64_t* stamps, int32_t capacity, i
   if (n > capacity) n = capacity;
   if (n > 0) JF_CUDA(h, cudaMemcpy(stamps, c.prof, (size_t)n * 8, cudaMemcpyDeviceToHost));
   *n_stamps = n;
+  if (const char* path = getenv("JF_PROF_MARKS")) {          // developer aid: dump the fine-grained marks as text
+    int nm = 0;
+    cudaMemcpy(&nm, c.prof_marks_n, 4, cudaMemcpyDeviceToHost);
+    std::vector<long long> mk(nm > 0 ? nm : 1);
+    if (nm > 0) cudaMemcpy(mk.data(), c.prof_marks, (size_t)nm * 8, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(path, "w")) {
+      for (int i = 0; i + 1 < nm; i += 2) fprintf(f, "%lld %lld\n", mk[i], mk[i + 1]);
+      fclose(f);
+    }
+  }
   if (sm_clock_khz) cudaDeviceGetAttribute(sm_clock_khz, cudaDevAttrClockRate, h->device);
   return JF_OK;
 }

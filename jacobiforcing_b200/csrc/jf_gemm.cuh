@@ -49,8 +49,9 @@ struct GemmTask {
   int M;                     // live rows of this task
   int x_row0;                // first row inside X / first output row (multiple of 8)
   int xrows_cap;             // row capacity of the packed X buffer
-  int N;                     // PARTIAL: out row stride = real feature count; ARGMAX: vocab size; SWIGLU: intermediate size
-  int M_cap;                 // PARTIAL: row capacity of out (slot stride = M_cap * N)
+  int N;                     // real feature count (PARTIAL) / vocab size (ARGMAX) / intermediate size (SWIGLU)
+  int out_row_stride;        // PARTIAL: floats between consecutive rows of out
+  int out_split_stride;      // PARTIAL: floats between the k-split slices of one row
   int epilogue;
   int out_rows_cap;          // SWIGLU: xrows_cap of the destination packed buffer
 };
@@ -62,7 +63,8 @@ struct GemmSmem {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad_;
-  unsigned long long best[4][kArgmaxRows];   // EPI_ARGMAX running best key per epilogue warp and row
+  unsigned long long* best;   // [4][kArgmaxRows] EPI_ARGMAX running best key per epilogue warp and row (aliases
+                              // the attention tile buffer: the LM head never overlaps an attention stage)
 };
 
 struct PipeState {      // smem ring position.  Phase parity is tracked PER SLOT (bit i = parity of slot i) so the ring
@@ -268,7 +270,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
   const int rows_mma = task_rows_mma(t);
   const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
   if (t.epilogue == EPI_ARGMAX) {
-    for (int m = lane; m < t.M; m += 32) gs->best[q][m] = 0ull;
+    for (int m = lane; m < t.M; m += 32) gs->best[q * kArgmaxRows + m] = 0ull;
     __syncwarp();
   }
   for (int u = cta; u < units; u += nctas) {
@@ -282,7 +284,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
       tc_fence_after();
       const uint32_t taddr = gs->tmem_base + acc.buf * 256u + ((uint32_t)(q * 32) << 16);
       if (t.epilogue == EPI_PARTIAL_F32) {
-        float* out = reinterpret_cast<float*>(t.out) + (size_t)r.split * t.M_cap * t.N;
+        float* out = reinterpret_cast<float*>(t.out) + (size_t)r.split * t.out_split_stride;
         const bool nvalid = n < t.N;
         for (int c0 = 0; c0 < mpad; c0 += 16) {
           uint32_t v[16];
@@ -291,7 +293,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int m = t.x_row0 + m0 + c0 + j;
-            if (nvalid && c0 + j < mlive) out[(size_t)m * t.N + n] = __uint_as_float(v[j]);
+            if (nvalid && c0 + j < mlive) out[(size_t)m * t.out_row_stride + n] = __uint_as_float(v[j]);
           }
         }
       } else if (t.epilogue == EPI_SWIGLU_BF16) {
@@ -338,7 +340,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
             if (lane == j) mine = key;
           }
           const int m = m0 + c0 + lane;
-          if (lane < 16 && c0 + lane < mlive && mine > gs->best[q][m]) gs->best[q][m] = mine;
+          if (lane < 16 && c0 + lane < mlive && mine > gs->best[q * kArgmaxRows + m]) gs->best[q * kArgmaxRows + m] = mine;
           __syncwarp();
         }
       }
@@ -351,7 +353,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
     __syncwarp();
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(t.out);
     for (int m = lane; m < t.M; m += 32) {
-      const unsigned long long k = gs->best[q][m];
+      const unsigned long long k = gs->best[q * kArgmaxRows + m];
       if (k != 0ull) atomicMax(&keys[t.x_row0 + m], k);
     }
   }

@@ -34,6 +34,7 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
   if (w.wtid == 0) {
     long long t_arrive = 0;
     if (prof_slot) t_arrive = clock64();
+    prof_mark(c, w, 900);
     red_release_gpu_add_u32(c.bar_counter, 1u);
     wait_epoch<false>(c.bar_counter, epoch * (unsigned int)w.nctas);   // critical path: spin, do not sleep
     if (prof_slot && *prof_slot + 2 <= c.prof_cap) {      // (arrival of CTA 0, release of the barrier)
@@ -41,6 +42,7 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
       c.prof[*prof_slot + 1] = clock64();
       *prof_slot += 2;
     }
+    prof_mark(c, w, 901);
   }
   workers_sync();
 }
@@ -192,8 +194,9 @@ struct IterPlan {
 };
 
 template <int ROLE>
-__device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring_bytes, const WorkerCtx& w,
+__device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring_bytes, const WorkerCtx& w_in,
                          int run_mode, int max_forwards) {
+  WorkerCtx w = w_in;
   const int cta = blockIdx.x, nctas = gridDim.x;
   unsigned int epoch = 0;
   PipeState pipe;
@@ -208,8 +211,9 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
 
   auto gemm_stage = [&](const GemmTask& t, bool barrier_after, const GemmTask* next = nullptr) {
     if (ROLE == ROLE_W) {
+      if (c.debug_skip & 16) wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);   // experiment: no run-ahead
       gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
-      if (next != nullptr) gemm_prefetch_l2(*next, cta, nctas, kPrefetchTiles);
+      if (next != nullptr) gemm_prefetch_l2(*next, cta, nctas, c.prefetch_tiles);
     } else if (ROLE == ROLE_X) {
       wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);
       fence_proxy_async_all();
@@ -250,9 +254,12 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     if (ROLE == ROLE_WORKER) {
       if (prof_slot != nullptr && w.wtid == 0) *c.prof_count = prof_n;     // forward profiled: publish and stop
       prof_slot = nullptr;
+      w.prof_on = 0;
       if (cta == 0 && c.prof != nullptr && __ldcg(&hdr->iter) == c.prof_forward) {
         prof_n = 0;
         prof_slot = &prof_n;
+        w.prof_on = 1;
+        if (w.wtid == 0 && c.prof_marks_n) *c.prof_marks_n = 0;
         if (w.wtid == 0 && c.prof_cap >= 2) { c.prof[0] = clock64(); c.prof[1] = c.prof[0]; prof_n = 2; }
       }
     }
@@ -264,7 +271,8 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
 
     auto base_task = [&]() {
       GemmTask t;
-      t.M = T; t.x_row0 = 0; t.xrows_cap = c.xrows_cap; t.M_cap = c.T_cap; t.out_rows_cap = c.xrows_cap;
+      t.M = T; t.x_row0 = 0; t.xrows_cap = c.xrows_cap; t.out_rows_cap = c.xrows_cap;
+      t.out_row_stride = c.part_splits * c.part_n; t.out_split_stride = c.part_n;
       return t;
     };
     auto task_qkv = [&](int l) {      // QKV projection (split-K partial sums)
@@ -303,11 +311,11 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       const LayerW& lw = c.layer[l];
       const GemmTask tq = task_qkv(l), to = task_o(l), tg = task_gu(l), td = task_down(l);
       gemm_stage(tq, true, &to);
-      JF_SIMT_STAGE(stage_qkv_rope(c, w, T, l));
-      JF_SIMT_STAGE(stage_attention(c, w, l, ip.G, ip.attn_units));
-      JF_SIMT_STAGE(stage_attn_combine(c, w, T));
+      JF_SIMT_STAGE(if (!(c.debug_skip & 1)) stage_qkv_rope(c, w, T, l); if (c.debug_skip & 32) { workers_sync(); stage_qkv_rope(c, w, T, l); });
+      JF_SIMT_STAGE(if (!(c.debug_skip & 2)) stage_attention(c, w, l, ip.G, ip.attn_units));
+      JF_SIMT_STAGE(if (!(c.debug_skip & 4)) stage_attn_combine(c, w, T));
       gemm_stage(to, true, &tg);
-      JF_SIMT_STAGE(stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2));
+      JF_SIMT_STAGE(if (!(c.debug_skip & 8)) stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2));
       gemm_stage(tg, true, &td);
       if (l + 1 < md.layers) {
         const GemmTask tn = task_qkv(l + 1);
@@ -329,7 +337,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       gemm_stage(t, false, (i + 1 == ip.n_lm) ? &tn : nullptr);
       if (i == 0 && ip.want_logits) {
         t.out = c.logits - (size_t)t.x_row0 * md.vocab;
-        t.epilogue = EPI_PARTIAL_F32;
+        t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = md.vocab; t.out_split_stride = 0;
         gemm_stage(t, false);
       }
     }
@@ -345,11 +353,24 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
 __global__ void __launch_bounds__(kNumThreads, 1)
 jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mode, int max_forwards) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const DevCtx& c = *ctxp;
   GemmSmem* gs = reinterpret_cast<GemmSmem*>(smem);
   float* red = reinterpret_cast<float*>(smem + ((sizeof(GemmSmem) + 15) & ~(size_t)15));
-  uint8_t* attn = reinterpret_cast<uint8_t*>(red + 16);
-  const int attn_bytes = 2 * kAttnSub * (c.md.d + 8) * 2;
+  // The context (pointers, dims, per-layer weight table) is copied into shared memory once: every stage reads a dozen
+  // of its fields, and from global memory each of them costs an L2 round trip after every grid barrier (the barrier's
+  // acquire invalidates L1).
+  DevCtx* sctx = reinterpret_cast<DevCtx*>(red + 16);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(ctxp);
+    uint4* dst = reinterpret_cast<uint4*>(sctx);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevCtx) / 16); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const DevCtx& c = *sctx;
+  uint8_t* attn = reinterpret_cast<uint8_t*>(sctx) + ((sizeof(DevCtx) + 15) & ~(size_t)15);
+  const int attn_need = 2 * kAttnSub * (c.md.d + 8) * 2;
+  const int best_need = 4 * kArgmaxRows * 8;
+  const int attn_bytes = attn_need > best_need ? attn_need : best_need;
+  if (threadIdx.x == 0) gs->best = reinterpret_cast<unsigned long long*>(attn);
   const uint32_t base_addr = smem_u32(smem);     // the ring must be 1024-byte aligned in the shared window (sw128)
   const size_t tiles_off = (((size_t)base_addr + (size_t)(attn - smem) + attn_bytes + 1023) & ~(size_t)1023) - base_addr;
   uint8_t* tiles = smem + tiles_off;
@@ -359,7 +380,7 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WorkerCtx w;
-  w.cta = blockIdx.x; w.nctas = gridDim.x; w.lane = lane; w.red = red; w.attn_smem = attn;
+  w.cta = blockIdx.x; w.nctas = gridDim.x; w.lane = lane; w.red = red; w.attn_smem = attn; w.prof_on = 0;
   w.wwarp = warp - kWarpWorker0; w.wtid = (int)threadIdx.x - kWarpWorker0 * 32;
 
   if (warp == kWarpW) {

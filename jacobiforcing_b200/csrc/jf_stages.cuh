@@ -22,7 +22,15 @@ struct WorkerCtx {
   int lane;
   float* red;      // [8] block-reduction scratch
   uint8_t* attn_smem;
+  int prof_on;     // CTA 0, forward being profiled
 };
+
+__device__ __forceinline__ void prof_mark(const DevCtx& c, const WorkerCtx& w, int id) {
+  if (w.prof_on && w.wtid == 0 && c.prof_marks != nullptr) {
+    const int n = *c.prof_marks_n;
+    if (n + 2 <= 8192) { c.prof_marks[n] = id; c.prof_marks[n + 1] = clock64(); *c.prof_marks_n = n + 2; }
+  }
+}
 
 constexpr uint32_t kBarWorkers = 1;   // named barrier ids (0 is __syncthreads)
 constexpr uint32_t kBarReduce  = 2;
@@ -66,6 +74,7 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w
   const int nvec = h >> 3;
   const int NS = (nvec + kWorkerThreads - 1) / kWorkerThreads;     // slices per row (<= 8)
   const int items = T * NS;
+  prof_mark(c, w, 200);
   for (int item = w.cta; item < items; item += w.nctas) {
     const int t = item / NS, sl = item - t * NS;
     const int v = sl * kWorkerThreads + w.wtid;
@@ -83,7 +92,7 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w
 #pragma unroll
         for (int s2 = 0; s2 < 8; ++s2) {
           if (s2 < splits) {
-            const float4* p = reinterpret_cast<const float4*>(c.part + ((size_t)s2 * c.T_cap + t) * h) + v * 2;
+            const float4* p = reinterpret_cast<const float4*>(c.part + ((size_t)t * c.part_splits + s2) * c.part_n) + v * 2;
             pa[s2] = __ldcg(p);
             pb[s2] = __ldcg(p + 1);
           }
@@ -105,7 +114,9 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss += x[j] * x[j];
     }
+    prof_mark(c, w, 201);
     ss = block_sum_128(ss, w);
+    prof_mark(c, w, 202);
     if (w.wtid == 0) {
       int last = 1;
       if (NS > 1) {
@@ -119,6 +130,7 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w
     named_bar_sync(kBarReduce, kWorkerThreads);
     const bool last = reinterpret_cast<const int*>(w.red)[8] != 0;
     named_bar_sync(kBarReduce, kWorkerThreads);
+    prof_mark(c, w, 203);
     if (!last) continue;
     float total = ss;
     if (NS > 1) {
@@ -137,6 +149,7 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w
                      (((vv & 7) ^ (t & 7)) << 4);
       *reinterpret_cast<uint4*>(dst) = pack8(o);
     }
+    prof_mark(c, w, 204);
   }
 }
 
@@ -148,12 +161,12 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
   const ModelDims& md = c.md;
   const int d = md.d, half = d >> 1, ppl = d >> 6;     // pairs per lane: 1 (d=64) or 2 (d=128)
   const int nslots = md.n_q + 2 * md.n_kv;
-  const int N = md.qkv_dim;
   const int splits = c.splits_qkv;
   const float* bias = c.layer[layer].bqkv;
   const int items = T * nslots;
   const int stride = w.nctas * 4;
-  const size_t sstride = (size_t)c.T_cap * N;
+  const size_t sstride = (size_t)c.part_n;
+  prof_mark(c, w, 100);
   for (int item0 = w.cta * 4 + w.wwarp; item0 < items; item0 += 2 * stride) {
     float lo[2][2], hi[2][2];
     int tt[2], slot[2], pos[2];
@@ -166,7 +179,7 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
         const int t = item / nslots;
         tt[q] = t; slot[q] = item - t * nslots;
         pos[q] = __ldcg(&c.row_pos[t]);
-        const float* p0 = c.part + (size_t)t * N + slot[q] * d + w.lane * ppl;
+        const float* p0 = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane * ppl;
         if (ppl == 2) {
           float2 vl[8], vh[8];
 #pragma unroll
@@ -189,6 +202,8 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
         }
       }
     }
+    if (lo[0][0] == 12345.678f) prof_mark(c, w, 199);   // keep the mark after the loads' first use
+    prof_mark(c, w, 101);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       if (tt[q] < 0) continue;
@@ -218,6 +233,7 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
       }
     }
   }
+  prof_mark(c, w, 102);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -439,10 +455,13 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerCtx
   const int vpl = D >> 5;                                  // floats per lane: 4 (d=128) or 2 (d=64)
   const int items = T * md.n_q;
   const size_t cstride = md.n_q;                            // slots of consecutive chunks are adjacent
+  prof_mark(c, w, 300);
   for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
     const int t = item / md.n_q, head = item - t * md.n_q;
     const int2 ra = __ldcg(&c.row_attn[t]);
     const int cmax = ra.y;                                  // last chunk holding a visible key
+    if (cmax == -77) prof_mark(c, w, 399);
+    prof_mark(c, w, 301);
     const size_t base = (size_t)ra.x * md.n_q + head;
     float m = -INFINITY;
     float l = 0.f;
@@ -490,6 +509,8 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerCtx
         }
       }
     }
+    if (l == 12345.678f) prof_mark(c, w, 398);
+    prof_mark(c, w, 302);
     const float inv = 1.0f / l;
     const int f = head * D + w.lane * vpl;                  // feature index = k index of the O projection
     uint8_t* dst = reinterpret_cast<uint8_t*>(c.xa) + ((size_t)(f >> 6) * c.xrows_cap) * 128 + sw128_offset(t, f & 63);

@@ -7,7 +7,7 @@
 namespace jf {
 
 constexpr int kPage        = 256;    // KV page size in tokens (reference: kvcache_block_size % 256 == 0, config.py:46)
-constexpr int kMaxLayers   = 64;
+constexpr int kMaxLayers   = 64;     // the per-layer weight table lives in shared memory (56 B per layer)
 constexpr int kAttnSub     = 64;     // keys per mma.sync sub-tile
 constexpr int kMaxLmTasks  = 16;     // LM-head row tiles of kArgmaxRows per forward
 constexpr int kQTokPerUnit = 64;     // query tokens one attention unit covers
@@ -71,7 +71,7 @@ struct SeqSlot {             // per-sequence bookkeeping owned by the policy sta
   int commit_src_row, commit_n, commit_pos;
 };
 
-struct DevCtx {
+struct alignas(16) DevCtx {
   ModelDims md;
   // ---- weights
   const __nv_bfloat16* embed;        // [vocab][h] row-major
@@ -92,7 +92,9 @@ struct DevCtx {
   __nv_bfloat16* xn;                 // packed [h/64][xrows_cap x 64]   normed hidden (GEMM X operand)
   __nv_bfloat16* xa;                 // packed [q_dim/64][...]          attention output
   __nv_bfloat16* xact;               // packed [inter/64][...]          silu(gate)*up
-  float* part;                       // [max_splits][T_cap][max(qkv_dim, h)] split-K partial sums
+  float* part;                       // [T_cap][part_splits][part_n] split-K partial sums, row-major by ROW so the live
+                                     // rows of a forward share a few 2 MB pages (TLB reach matters: see DESIGN.md)
+  int part_splits, part_n;
   __nv_bfloat16* qbuf;               // [T_cap][q_dim] rotated queries
   float* attn_o;                     // [attn_slots_cap][n_q][d] unnormalised partial outputs
   float* attn_ml;                    // [attn_slots_cap][n_q][2] (running max, running sum)
@@ -132,6 +134,10 @@ struct DevCtx {
   int prof_cap;
   int prof_forward;
   int* prof_count;
+  long long* prof_marks;             // fine-grained (id, clock) pairs recorded by CTA 0 / worker thread 0
+  int* prof_marks_n;
+  int debug_skip;                    // timing experiments only: bit s = skip the body of SIMT stage s (results invalid)
+  int prefetch_tiles;                // weight tiles per SM the W producer pulls into L2 ahead of the next GEMM
 };
 
 enum RunMode : int { RUN_PLAN = 0, RUN_JACOBI = 1 };
