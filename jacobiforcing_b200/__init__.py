@@ -5,3 +5,15 @@ Host side (Python) of the hot path: a mirror of the reference's `inference_engin
 include/jacobi_b200.h).  There is no CPU fallback: importing the runtime without the built library raises.
 """
 __version__ = "0.1.0"
+
+from .sampling_params import SamplingParams   # noqa: E402,F401
+
+
+def __getattr__(name):                       # lazy: importing the package must not need the built library
+    if name == "LLM":
+        from .llm import LLM
+        return LLM
+    if name == "Config":
+        from .config import Config
+        return Config
+    raise AttributeError(name)

@@ -1,0 +1,55 @@
+"""Config — the reference's engine configuration (inference_engine/config.py:7-52), plus two ways to run without a
+checkpoint directory (there are no model files offline): `hf_config` may be passed in, and `state_dict` may carry
+HF-named tensors for the loader."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Any, Optional
+
+
+@dataclass
+class Config:
+    model: Optional[str]
+    max_num_batched_tokens: int = 16384
+    max_num_seqs: int = 512
+    max_model_len: int = 8192
+    gpu_memory_utilization: float = 0.9
+    tensor_parallel_size: int = 1
+    enforce_eager: bool = False
+    hf_config: Any = None
+    eos: int = -1
+    pad: int = -1
+    kvcache_block_size: int = 256
+    num_kvcache_blocks: int = -1
+
+    jacobi_enabled: bool = True
+    jacobi_block_len: int = 64
+    jacobi_max_blocks: int = 2
+    jacobi_spawn_ratio: float = 0.8
+    jacobi_lookahead_start_ratio: float = 0.0
+    jacobi_n_gram_pool_size: int = 4
+    jacobi_max_iterations: int = 128
+
+    # extensions of this build
+    state_dict: Any = field(default=None, repr=False)     # HF-named tensors instead of a checkpoint directory
+    jacobi_multiblock_enabled: bool = False                # serve "jacobi_multiblock_rejection_recycling" on device
+    draft_seed: int = 0                                    # seeds every random draft token (reference: unseeded RNGs)
+    device: int = 0
+
+    def __post_init__(self):
+        model_path = self.model
+        if model_path is not None and os.path.isdir(model_path):
+            ckpts = [d for d in os.listdir(model_path)
+                     if d.startswith("checkpoint-") and os.path.isdir(os.path.join(model_path, d))]
+            if ckpts:                                      # config.py:31-41: latest DeepSpeed checkpoint sub-directory
+                model_path = os.path.join(model_path, max(ckpts, key=lambda x: int(x.split("-")[1])))
+                self.model = model_path
+        assert self.kvcache_block_size % 256 == 0
+        assert 1 <= self.tensor_parallel_size <= 8
+        if self.hf_config is None:
+            assert model_path is not None and os.path.isdir(model_path), f"Model path does not exist: {model_path}"
+            from transformers import AutoConfig
+            self.hf_config = AutoConfig.from_pretrained(model_path)
+        self.max_model_len = min(self.max_model_len, self.hf_config.max_position_embeddings)
+        assert self.max_num_batched_tokens >= self.max_model_len

@@ -199,5 +199,101 @@ def main():
     run_case("multi_n8_k3_quirk", "tiny", 0, 24, 8, 40, "multiblock", K=3, r=0.5, pool=4, max_iteration_count=40)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--engine" not in sys.argv:
     main()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# engine convention: the reference JacobiDecoder itself (inference_engine/engine/jacobi_decoding.py:303-445), run on CPU
+# through its forward_step callback with the HF forward; torch.randint is wrapped so the padding stream is recorded.
+# --------------------------------------------------------------------------------------------------------------------
+def run_engine_case(name, model_name, seed, prompt_len, L, max_tokens, max_iters=128, eos=None, with_prefill_draft=True):
+    sys.path.insert(0, ref_shim.REFERENCE_ROOT)
+    from inference_engine.engine.jacobi_decoding import JacobiDecoder
+    from inference_engine.engine.sequence import Sequence
+    from inference_engine.sampling_params import SamplingParams
+    model = build_model(model_name, seed=seed, dtype=torch.float32)
+    V = model.config.vocab_size
+    g = torch.Generator().manual_seed(1)
+    prompt = torch.randint(0, V, (prompt_len,), generator=g).tolist()
+    forwards = []
+
+    @torch.no_grad()
+    def forward_step(seq, q_draft):
+        toks = list(seq.token_ids)
+        S = len(toks)
+        draft = q_draft[0].tolist()
+        assert draft[0] == toks[-1]                       # model_runner.py:1157-1162
+        ids = torch.tensor([toks[:-1] + draft], dtype=torch.long)
+        logits = model(input_ids=ids, use_cache=False).logits[:, S - 1:, :].float()      # L positions
+        forwards.append({"kv_before": S - 1, "rows": [draft], "greedy": [torch.argmax(logits[0], -1).tolist()]})
+        seq.num_cached_tokens = (S - 1) + len(draft)      # model_runner.py: sets (len-1)+L; trimmed by the decoder
+        return logits[:, :-1, :]
+
+    pad_stream = []
+    real_randint = torch.randint
+
+    def rec_randint(*a, **k):
+        out = real_randint(*a, **k)
+        pad_stream.extend(out.flatten().tolist())
+        return out
+
+    class FakeBM:                                          # the decoder only needs these three calls
+        def may_append_batch(self, seq, n):
+            pass
+
+        def may_append(self, seq):
+            pass
+
+        def trim_kv_only_fast(self, seq, n):
+            seq.num_cached_tokens -= n
+
+    sp = SamplingParams(temperature=0.0, max_tokens=max_tokens, decode_strategy="jacobi", jacobi_block_len=L,
+                        jacobi_max_iterations=max_iters)
+    seq = Sequence(prompt, sp)
+    seq.num_cached_tokens = len(prompt)
+    prefill_draft = None
+    if with_prefill_draft:
+        # model_runner.py:797-918: append L random prompt tokens, greedy draft = argmax(logits[P-1 : P+L-1])
+        rng = random.Random(2)
+        rnd = [rng.choice(prompt) for _ in range(L)]
+        with torch.no_grad():
+            lg = model(input_ids=torch.tensor([prompt + rnd]), use_cache=False).logits[0].float()
+        prefill_draft = torch.argmax(lg[prompt_len - 1: prompt_len + L - 1], -1).tolist()
+        seq._prefill_draft = list(prefill_draft)
+    dec = JacobiDecoder(FakeBM(), forward_step=forward_step, eos_token_id=eos, pad_token_id=0, vocab_size=V,
+                        device=torch.device("cpu"))
+    torch.manual_seed(1234)
+    torch.randint = rec_randint
+    try:
+        accepted = dec.generate_chunk(seq)
+    finally:
+        torch.randint = real_randint
+    from oracle.hf_model import greedy_ar
+    ar = greedy_ar(model, prompt, len(accepted)) if eos is None else None
+    out = {"case": name, "mode": "engine", "model": model_name, "model_seed": seed, "dtype": "float32",
+           "prompt": prompt, "L": L, "max_tokens": max_tokens, "max_iterations": max_iters, "eos": eos,
+           "prefill_draft": prefill_draft, "pad_stream": pad_stream, "accepted": accepted,
+           "iters": dec.stats["num_jacobi_iterations"], "tokens_per_iteration": dec.stats["tokens_per_iteration"],
+           "equals_greedy_ar": (None if ar is None else bool(ar == accepted)), "forwards": forwards,
+           "reference": "hao-ai-lab/JacobiForcing @ 028dbd6, inference_engine JacobiDecoder run unmodified on CPU"}
+    path = os.path.join(GOLDEN_DIR, name + ".json")
+    with open(path, "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print(f"{name}: {len(accepted)} tokens in {out['iters']} iterations, pads used {len(pad_stream)}, "
+          f"==AR {out['equals_greedy_ar']} -> {os.path.relpath(path, ROOT)}")
+    return out
+
+
+def main_engine():
+    base = run_engine_case("engine_L8", "tiny", 0, 24, 8, 40)
+    run_engine_case("engine_L16_nodraft_tiny128", "tiny128", 3, 40, 16, 64, with_prefill_draft=False)
+    run_engine_case("engine_L8_maxiter", "tiny", 0, 24, 8, 200, max_iters=12)
+    gen = base["accepted"]
+    eos = next((t for i, t in enumerate(gen) if i >= 12 and t not in gen[:i] and t not in base["prompt"]), None)
+    if eos is not None:
+        run_engine_case("engine_L8_eos", "tiny", 0, 24, 8, 40, eos=eos)
+
+
+if __name__ == "__main__" and "--engine" in sys.argv:
+    main_engine()

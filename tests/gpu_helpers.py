@@ -81,3 +81,26 @@ class DeviceForward:
     def trim(self, n):
         if n > 0:
             self.kv -= n
+
+
+class DeviceEngineForward:
+    """forward_step callback of oracle.jacobi_policy.engine_fixed_len on the device forward: draft[0] is the last
+    committed token at position S-1; what the policy accepted of the previous draft is committed lazily."""
+
+    def __init__(self, rt: JacobiRuntime, seq):
+        self.rt, self.seq = rt, seq
+        self.cached = seq.ctx          # tokens physically in the cache
+        self.last_base = None
+        self.n_forwards = 0
+
+    def __call__(self, token_ids, draft):
+        S = len(token_ids)
+        base = S - 1
+        if self.last_base is not None and base > self.last_base:
+            self.rt.commit_rows([self.seq], [(p - self.last_base, 0, p) for p in range(self.last_base, base)])
+        L = len(draft)
+        self.rt.ensure_capacity(self.seq, base + L)
+        res = self.rt.forward(list(draft), [(0, L, 0, base)], [self.seq], 0, L)
+        self.last_base = base
+        self.n_forwards += 1
+        return [int(t) for t in res["greedy"][:L - 1]]

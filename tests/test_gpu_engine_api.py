@@ -1,0 +1,143 @@
+"""GPU tests of the reference-facing engine surface (LLM / SamplingParams / ModelRunner.run), modelled on the reference's
+own script tests (inference_engine/tests/test_jacobi_decoding_greedy.py): Jacobi greedy == autoregressive greedy on the
+first N tokens (:180-206), batch consistency (:209-302, here 100 % instead of the reference's >= 50 % bar because rows
+are bit-independent of the batch), the multiblock strategy error (:97-115), and the decoder statistics (:152-176)."""
+import random
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def llm():
+    from jacobiforcing_b200 import LLM
+    from oracle.hf_model import build_model, state_dict_bf16
+    model = build_model("tiny", seed=0, dtype=torch.float32)
+    eng = LLM(None, hf_config=model.config, state_dict=state_dict_bf16(model), max_model_len=2048,
+              num_kvcache_blocks=64, max_num_seqs=8, max_num_batched_tokens=2048, draft_seed=7)
+    eng.config.eos, eng.config.pad = -1, 0
+    eng.scheduler.eos = -1
+    yield eng
+    eng.exit()
+
+
+def prompts(n, seed=0, V=1000):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randint(0, V, (16 + 5 * i,), generator=g).tolist() for i in range(n)]
+
+
+def reset(llm):
+    llm.scheduler.waiting.clear()
+    llm.scheduler.running.clear()
+    llm.model_runner.jacobi_decoder.reset()
+
+
+def test_single_sequence_jacobi_equals_autoregressive(llm):
+    from jacobiforcing_b200 import SamplingParams
+    p = prompts(1)
+    reset(llm)
+    ar = llm.generate(p, SamplingParams(temperature=0.0, max_tokens=96, decode_strategy="autoregressive"), use_tqdm=False)
+    reset(llm)
+    jc = llm.generate(p, SamplingParams(temperature=0.0, max_tokens=96, decode_strategy="jacobi", jacobi_block_len=16,
+                                        jacobi_max_iterations=128), use_tqdm=False)
+    assert len(ar[0]["token_ids"]) == 96
+    assert jc[0]["token_ids"][:96] == ar[0]["token_ids"][:96]
+    st = llm.model_runner.jacobi_decoder.stats
+    assert set(st) == {"num_chunk_calls", "num_jacobi_iterations", "tokens_accepted", "tokens_per_call",
+                       "tokens_per_iteration", "iterations_per_call"}
+    assert st["tokens_accepted"] == sum(st["tokens_per_call"]) == len(jc[0]["token_ids"])
+    assert st["num_jacobi_iterations"] == sum(st["iterations_per_call"]) == len(st["tokens_per_iteration"])
+    assert st["num_jacobi_iterations"] <= st["tokens_accepted"]          # TPF >= 1
+
+
+def test_batch_jacobi_equals_autoregressive(llm):
+    from jacobiforcing_b200 import SamplingParams
+    p = prompts(6, seed=3)
+    reset(llm)
+    ar = llm.generate(p, SamplingParams(temperature=0.0, max_tokens=48, decode_strategy="autoregressive"), use_tqdm=False)
+    reset(llm)
+    jc = llm.generate(p, SamplingParams(temperature=0.0, max_tokens=48, decode_strategy="jacobi", jacobi_block_len=8),
+                      use_tqdm=False)
+    for a, j in zip(ar, jc):
+        assert j["token_ids"][:48] == a["token_ids"][:48]
+
+
+def test_multiblock_strategy_error_then_enabled(llm):
+    from jacobiforcing_b200 import SamplingParams
+    p = prompts(2, seed=5)
+    sp = SamplingParams(temperature=0.0, max_tokens=40, decode_strategy="jacobi_multiblock_rejection_recycling",
+                        jacobi_block_len=8, jacobi_max_blocks=2, jacobi_spawn_ratio=0.85, jacobi_n_gram_pool_size=4)
+    reset(llm)
+    with pytest.raises(NotImplementedError, match="jacobi_multiblock_rejection_recycling"):
+        llm.generate(p, sp, use_tqdm=False)                    # reference behaviour (test_jacobi_decoding_greedy.py:97-115)
+    for s in list(llm.scheduler.running):
+        llm.scheduler.block_manager.deallocate(s)
+    reset(llm)
+    ar = llm.generate(p, SamplingParams(temperature=0.0, max_tokens=40, decode_strategy="autoregressive"), use_tqdm=False)
+    llm.config.jacobi_multiblock_enabled = True
+    try:
+        reset(llm)
+        mb = llm.generate(p, sp, use_tqdm=False)
+    finally:
+        llm.config.jacobi_multiblock_enabled = False
+    for a, m in zip(ar, mb):
+        assert m["token_ids"][:40] == a["token_ids"][:40]
+
+
+def test_mixed_strategies_and_sampling_rejected(llm):
+    from jacobiforcing_b200 import SamplingParams
+    p = prompts(2, seed=9)
+    reset(llm)
+    with pytest.raises(NotImplementedError, match="Mixed decode strategies"):
+        llm.generate(p, [SamplingParams(temperature=0.0, decode_strategy="jacobi", jacobi_block_len=8),
+                         SamplingParams(temperature=0.0, decode_strategy="autoregressive")], use_tqdm=False)
+    for s in list(llm.scheduler.running):
+        llm.scheduler.block_manager.deallocate(s)
+    reset(llm)
+    with pytest.raises(NotImplementedError):
+        llm.generate(p[:1], SamplingParams(temperature=0.8, decode_strategy="jacobi", jacobi_block_len=8), use_tqdm=False)
+    for s in list(llm.scheduler.running):
+        llm.scheduler.block_manager.deallocate(s)
+    reset(llm)
+
+
+@pytest.mark.parametrize("L,max_tokens,max_iters", [(8, 40, 128), (16, 64, 128), (8, 200, 10)])
+def test_engine_policy_device_loop_bit_exact(L, max_tokens, max_iters):
+    """Mode 2 on the device == the oracle's engine_fixed_len (pinned against the reference JacobiDecoder) consuming the
+    device forward's argmaxes: same accepted ids, iteration count and padding consumption."""
+    from jacobiforcing_b200.policy import MODES, PolicyKnobs
+    from oracle import jacobi_policy as jp
+    from tests.gpu_helpers import DeviceEngineForward, make_pair
+    model, rt = make_pair("tiny")
+    V = model.config.vocab_size
+    g = torch.Generator().manual_seed(11)
+    prompt = torch.randint(0, V, (30,), generator=g).tolist()
+    rng = random.Random(5)
+    pre = [rng.choice(prompt) for _ in range(L)]
+    pads = [rng.randrange(V) for _ in range(max_iters * L + L)]
+    # device loop
+    s = rt.new_sequence()
+    _, drafted, _ = rt.prefill(s, prompt, pre)
+    s.ctx = len(prompt) - 1
+    kn = PolicyKnobs(mode=MODES["engine"], n=L, eos=None, pad=0, max_iteration_count=max_iters,
+                     max_new_tokens=max_tokens, vocab=V)
+    res, run = rt.jacobi_run([s], kn, [0], [drafted], pad_stream=[pads])
+    # oracle policy on the device forward
+    s2 = rt.new_sequence()
+    _, drafted2, _ = rt.prefill(s2, prompt, pre)
+    assert drafted2 == drafted
+    left = list(pads)
+
+    def randint(k):
+        out = left[:k]
+        del left[:k]
+        return out
+    toks = list(prompt)
+    acc, iters, _ = jp.engine_fixed_len(DeviceEngineForward(rt, s2), toks, list(drafted), L, max_tokens, max_iters, V,
+                                        randint)
+    assert res[0].tokens == acc
+    assert res[0].total_iterations == iters == run["forwards"]
+    assert res[0].stop_reason == ("max_iterations" if iters >= max_iters and len(acc) < max_tokens else "max_new_tokens")
+    rt.close()

@@ -120,3 +120,45 @@ def test_live_reference_matches_golden(case):
                                dtype=getattr(torch, g["dtype"]))
     assert out["generated"] == g["generated"] and out["iters"] == g["iters"]
     assert [f["rows"] for f in out["forwards"]] == [f["rows"] for f in g["forwards"]]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# engine convention: goldens recorded from the reference JacobiDecoder itself (oracle/make_golden.py --engine)
+# ---------------------------------------------------------------------------------------------------------------------
+ENGINE_CASES = [os.path.splitext(os.path.basename(p))[0] for p in GOLDEN if json.load(open(p)).get("mode") == "engine"]
+
+
+@pytest.mark.parametrize("case", ENGINE_CASES)
+def test_engine_policy_replay_matches_reference(case):
+    g = load(case)
+    fwds = g["forwards"]
+    state = {"i": 0}
+
+    def forward_step(token_ids, draft):
+        rec = fwds[state["i"]]
+        assert rec["kv_before"] == len(token_ids) - 1
+        assert rec["rows"][0] == list(draft), f"forward {state['i']}: draft differs from the reference"
+        state["i"] += 1
+        return rec["greedy"][0][:-1]
+
+    pads = list(g["pad_stream"])
+
+    def randint(k):
+        out = pads[:k]
+        del pads[:k]
+        assert len(out) == k
+        return out
+
+    toks = list(g["prompt"])
+    acc, iters, per_iter = jp.engine_fixed_len(forward_step, toks, g["prefill_draft"], g["L"], g["max_tokens"],
+                                               g["max_iterations"], 0, randint, eos=g["eos"])
+    assert acc == g["accepted"]
+    assert iters == g["iters"] == len(fwds) == state["i"]
+    assert toks == g["prompt"] + g["accepted"]
+    assert not pads                                           # consumed the padding stream exactly
+    if g["eos"] is None:
+        assert g["equals_greedy_ar"] is True
+
+
+def test_engine_goldens_exist():
+    assert len(ENGINE_CASES) >= 3

@@ -89,3 +89,37 @@ def test_device_policy_replays_reference(path):
     assert total_new == g["total_new_tokens"]
     assert used == nfw
     assert total_iters == sum(g["iters"])
+
+
+ENGINE_GOLDEN = [p for p in GOLDEN if json.load(open(p)).get("mode") == "engine"]
+
+
+@pytest.mark.parametrize("path", ENGINE_GOLDEN, ids=[os.path.basename(p)[:-5] for p in ENGINE_GOLDEN])
+def test_device_engine_policy_replays_reference(path):
+    """csrc/jf_policy.h eng_advance (mode 2) against forwards recorded from the reference JacobiDecoder."""
+    g = json.load(open(path))
+    lib = _load_harness()
+    kn = PolicyKnobs(mode=MODES["engine"], n=g["L"], eos=g["eos"], pad=0, max_iteration_count=g["max_iterations"],
+                     max_new_tokens=g["max_tokens"])
+    prompt = g["prompt"]
+    fws = g["forwards"]
+    kv = _arr([f["kv_before"] for f in fws]); fB = _arr([1] * len(fws)); fL = _arr([g["L"]] * len(fws))
+    offs = _arr([i * g["L"] for i in range(len(fws))], np.int64)
+    rows = _arr([t for f in fws for t in f["rows"][0]]); greedy = _arr([t for f in fws for t in f["greedy"][0]])
+    gen_cap = len(prompt) + g["max_tokens"] + 4 * g["L"]
+    gen = np.zeros(gen_cap, np.int32); iters = np.zeros(8, np.int32); res = np.zeros(8, np.int32)
+    knobs = _arr(kn.as_ints()); pr = _arr(prompt)
+    fct = _arr(g["prefill_draft"][:g["L"] - 1] + [0]) if g["prefill_draft"] is not None else None
+    pads = _arr(g["pad_stream"] + [0])
+    rc = lib.jf_policy_replay(_p(knobs), _p(pr), len(prompt), len(prompt) - 1, 0, _p(fct) if fct is not None else None,
+                              None, 0, _p(pads), len(g["pad_stream"]), len(fws), _p(kv), _p(fB), _p(fL), _p(offs),
+                              _p(rows), _p(greedy), _p(gen), gen_cap, _p(iters), len(iters), _p(res))
+    assert rc == 0, f"policy diverged from the reference at forward {rc - 100}" if rc >= 100 else "ran out of forwards"
+    gen_len, calls, stop, total_new, err, used, total_iters, ctx = [int(x) for x in res]
+    assert err == 0
+    assert gen[len(prompt):gen_len].tolist() == g["accepted"]
+    assert used == len(fws) == g["iters"] == total_iters
+    assert total_new == len(g["accepted"])
+    assert ctx == gen_len - 1
+    expected_stop = "eos" if g["eos"] is not None else ("max_iterations" if g["iters"] >= g["max_iterations"] and len(g["accepted"]) < g["max_tokens"] else "max_new_tokens")
+    assert STOP_REASONS[stop] == expected_stop
