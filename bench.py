@@ -330,7 +330,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            per_fwd = json.load(open(prof)).get("dram_bytes_per_forward")
+            # ncu capture was one 32-forward launch; a bench launch runs `forwards_per_launch` forwards of the same shape
+            roofline["traffic"] = per_fwd * roofline["forwards_per_launch"] if per_fwd else None
+            roofline["achieved_bytes_per_launch"] = bytes_launch
         except Exception:
             pass
 
