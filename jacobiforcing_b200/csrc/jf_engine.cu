@@ -247,6 +247,7 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.xa, (size_t)kc_q * c.xrows_cap * 64, h->bytes_act);
   ALLOC(c.qbuf, (size_t)c.T_cap * md.q_dim, h->bytes_act);
   c.attn_slots_cap = rt.attn_slots; c.attn_chunk = rt.attn_chunk;
+  c.attn_hsplit = md.n_rep >= 4 ? 2 : 1;
   ALLOC(c.argmax_keys, c.T_cap, h->bytes_act);
   ALLOC(c.row_ss, (size_t)c.T_cap * 8, h->bytes_act);
   ALLOC(c.row_cnt, c.T_cap, h->bytes_act);
@@ -606,7 +607,7 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
     gr.nchunks = (gr.ctx + gr.len + c.attn_chunk - 1) / c.attn_chunk;
     gr.qsplit = (gr.len + kQTokPerUnit - 1) / kQTokPerUnit;
     gr.unit0 = units; gr.slot0 = slots;
-    units += md.n_kv * gr.nchunks * gr.qsplit;
+    units += md.n_kv * gr.nchunks * gr.qsplit * c.attn_hsplit;
     slots += gr.len * gr.nchunks;
     for (int i = 0; i < gr.len; ++i) {
       if (row_group[gr.row0 + i] != -1) { h->err = "groups overlap"; return JF_ERR_INVALID; }

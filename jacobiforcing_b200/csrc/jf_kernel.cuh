@@ -52,28 +52,28 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void policy_stage_plan(const DevCtx& c, const WorkerCtx& w) {
   PlanHdr* hdr = c.hdr;
-  const int n_lm = __ldcg(&hdr->n_lm_tasks);
+  const int n_lm = ld_weak(&hdr->n_lm_tasks);
   for (int i = 0; i < n_lm; ++i) {
-    const int r0 = __ldcg(&hdr->lm_row0[i]), rn = __ldcg(&hdr->lm_rows[i]);
+    const int r0 = ld_weak(&hdr->lm_row0[i]), rn = ld_weak(&hdr->lm_rows[i]);
     for (int t = r0 + w.wtid; t < r0 + rn; t += kWorkerThreads) {
-      const unsigned long long key = __ldcg(&c.argmax_keys[t]);
+      const unsigned long long key = ld_weak(&c.argmax_keys[t]);
       c.greedy[t] = argmax_key_index(key);
       c.argmax_keys[t] = 0ull;
     }
   }
   if (w.wtid == 0) {
-    hdr->n_commit = __ldcg(&hdr->n_commit_after);
-    hdr->iter = __ldcg(&hdr->iter) + 1;
-    hdr->rows_total = __ldcg(&hdr->rows_total) + __ldcg(&hdr->T);
+    hdr->n_commit = ld_weak(&hdr->n_commit_after);
+    hdr->iter = ld_weak(&hdr->iter) + 1;
+    hdr->rows_total = ld_weak(&hdr->rows_total) + ld_weak(&hdr->T);
     hdr->done = 1;
   }
 }
 
 __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerCtx& w, bool first, int max_forwards) {
   PlanHdr* hdr = c.hdr;
-  const int Tprev = first ? 0 : __ldcg(&hdr->T);
+  const int Tprev = first ? 0 : ld_weak(&hdr->T);
   for (int t = w.wtid; t < Tprev; t += kWorkerThreads) {
-    const unsigned long long key = __ldcg(&c.argmax_keys[t]);
+    const unsigned long long key = ld_weak(&c.argmax_keys[t]);
     c.greedy[t] = argmax_key_index(key);
     c.argmax_keys[t] = 0ull;
   }
@@ -106,7 +106,7 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerCt
   __threadfence_block();
   workers_sync();
   if (w.wtid == 0) {
-    const int iter_done = first ? 0 : __ldcg(&hdr->iter) + 1;
+    const int iter_done = first ? 0 : ld_weak(&hdr->iter) + 1;
     int T = 0, G = 0, nc = 0, units = 0, slots = 0, err = 0;
     const int CH = c.attn_chunk;
     for (int s = 0; s < c.n_seqs; ++s) {
@@ -136,7 +136,7 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerCt
         Group& g = c.groups[G];
         g.row0 = T + i * L; g.len = L; g.seq = s; g.ctx = st.ctx;
         g.nchunks = nchunks; g.qsplit = qsplit; g.unit0 = units; g.slot0 = slots;
-        units += c.md.n_kv * nchunks * qsplit;
+        units += c.md.n_kv * nchunks * qsplit * c.attn_hsplit;
         slots += L * nchunks;
         ++G;
       }
@@ -151,7 +151,7 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerCt
       }
       T += B * L;
     }
-    hdr->rows_total = (first ? 0 : __ldcg(&hdr->rows_total)) + T;
+    hdr->rows_total = (first ? 0 : ld_weak(&hdr->rows_total)) + T;
     hdr->T = T; hdr->G = G; hdr->n_commit = nc; hdr->attn_units = units; hdr->attn_slots = slots;
     hdr->iter = iter_done;
     hdr->want_logits = 0;
@@ -240,9 +240,9 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     if (ROLE != ROLE_WORKER) wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);
     const PlanHdr* hdr = c.hdr;
     IterPlan ip;
-    ip.T = __ldcg(&hdr->T); ip.G = __ldcg(&hdr->G); ip.done = __ldcg(&hdr->done);
-    ip.n_commit = __ldcg(&hdr->n_commit); ip.attn_units = __ldcg(&hdr->attn_units);
-    ip.n_lm = __ldcg(&hdr->n_lm_tasks); ip.want_logits = __ldcg(&hdr->want_logits);
+    ip.T = ld_weak(&hdr->T); ip.G = ld_weak(&hdr->G); ip.done = ld_weak(&hdr->done);
+    ip.n_commit = ld_weak(&hdr->n_commit); ip.attn_units = ld_weak(&hdr->attn_units);
+    ip.n_lm = ld_weak(&hdr->n_lm_tasks); ip.want_logits = ld_weak(&hdr->want_logits);
     if (ip.done) {
       if (ROLE == ROLE_WORKER) {
         if (prof_slot != nullptr && w.wtid == 0) *c.prof_count = prof_n;
@@ -255,7 +255,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       if (prof_slot != nullptr && w.wtid == 0) *c.prof_count = prof_n;     // forward profiled: publish and stop
       prof_slot = nullptr;
       w.prof_on = 0;
-      if (cta == 0 && c.prof != nullptr && __ldcg(&hdr->iter) == c.prof_forward) {
+      if (cta == 0 && c.prof != nullptr && ld_weak(&hdr->iter) == c.prof_forward) {
         prof_n = 0;
         prof_slot = &prof_n;
         w.prof_on = 1;
@@ -302,7 +302,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     auto task_lm = [&](int i) {
       GemmTask t = base_task();
       t.W = c.lm_head; t.X = c.xn; t.out = c.argmax_keys; t.n_tiles = nt_v; t.k_chunks = kc_h; t.splits = 1;
-      t.M = __ldcg(&hdr->lm_rows[i]); t.x_row0 = __ldcg(&hdr->lm_row0[i]);
+      t.M = ld_weak(&hdr->lm_rows[i]); t.x_row0 = ld_weak(&hdr->lm_row0[i]);
       t.N = md.vocab; t.epilogue = EPI_ARGMAX;
       return t;
     };

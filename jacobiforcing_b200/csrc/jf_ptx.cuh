@@ -204,6 +204,12 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c
   return r * 128u + chunk * 16u + (c & 7) * 2u;
 }
 
+// Plain (weak, L1-cacheable) global load.  Every stage boundary is a grid barrier whose acquire fence invalidates the
+// SM's L1, so data written by other CTAs BEFORE the barrier is read correctly; unlike ld.global.cg ("strong" loads,
+// which the hardware keeps in order - measured ~0.3 us EACH inside this kernel) weak loads overlap freely.
+template <typename T>
+__device__ __forceinline__ T ld_weak(const T* p) { return *p; }
+
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 }  // namespace jf

@@ -68,8 +68,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // once); each slice publishes its sum of squares, and the CTA that arrives last for a row adds the slice sums in slice
 // order (deterministic, independent of who is last) and normalises the whole row.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w, int T, bool embed, int splits,
-                                             const __nv_bfloat16* normw) {
+template <int SPLITS>     // SPLITS == 0: embedding lookup instead of a split-K reduce
+__device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx& w, int T, const __nv_bfloat16* normw) {
   const int h = c.md.h;
   const int nvec = h >> 3;
   const int NS = (nvec + kWorkerThreads - 1) / kWorkerThreads;     // slices per row (<= 8)
@@ -82,28 +82,23 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w
     float ss = 0.f;
     if (v < nvec) {
       float x[8];
-      if (embed) {
-        int tk = __ldcg(&c.tok[t]);
+      if (SPLITS == 0) {
+        int tk = ld_weak(&c.tok[t]);
         tk = tk < 0 ? 0 : (tk >= c.md.vocab ? c.md.vocab - 1 : tk);
         unpack8(__ldg(reinterpret_cast<const uint4*>(c.embed + (size_t)tk * h) + v), x);
       } else {
-        const uint4 rr = __ldcg(reinterpret_cast<const uint4*>(hrow) + v);
-        float4 pa[8], pb[8];
+        // every split-K slice of this 8-column group is in flight before the first add; the sum runs in slice order
+        const uint4 rr = ld_weak(reinterpret_cast<const uint4*>(hrow) + v);
+        const float4* p = reinterpret_cast<const float4*>(c.part + (size_t)t * c.part_splits * c.part_n) + v * 2;
+        const size_t sstride4 = (size_t)c.part_n >> 2;
+        float4 pa[SPLITS > 0 ? SPLITS : 1], pb[SPLITS > 0 ? SPLITS : 1];
 #pragma unroll
-        for (int s2 = 0; s2 < 8; ++s2) {
-          if (s2 < splits) {
-            const float4* p = reinterpret_cast<const float4*>(c.part + ((size_t)t * c.part_splits + s2) * c.part_n) + v * 2;
-            pa[s2] = __ldcg(p);
-            pb[s2] = __ldcg(p + 1);
-          }
-        }
+        for (int s2 = 0; s2 < SPLITS; ++s2) { pa[s2] = ld_weak(p + s2 * sstride4); pb[s2] = ld_weak(p + s2 * sstride4 + 1); }
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int s2 = 0; s2 < 8; ++s2) {                    // slice order: deterministic
-          if (s2 < splits) {
-            acc[0] += pa[s2].x; acc[1] += pa[s2].y; acc[2] += pa[s2].z; acc[3] += pa[s2].w;
-            acc[4] += pb[s2].x; acc[5] += pb[s2].y; acc[6] += pb[s2].z; acc[7] += pb[s2].w;
-          }
+        for (int s2 = 0; s2 < SPLITS; ++s2) {
+          acc[0] += pa[s2].x; acc[1] += pa[s2].y; acc[2] += pa[s2].z; acc[3] += pa[s2].w;
+          acc[4] += pb[s2].x; acc[5] += pb[s2].y; acc[6] += pb[s2].z; acc[7] += pb[s2].w;
         }
         float r[8];
         unpack8(rr, r);
@@ -135,13 +130,13 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w
     float total = ss;
     if (NS > 1) {
       total = 0.f;
-      for (int s2 = 0; s2 < NS; ++s2) total += __ldcg(&c.row_ss[t * 8 + s2]);
+      for (int s2 = 0; s2 < NS; ++s2) total += ld_weak(&c.row_ss[t * 8 + s2]);
     }
     const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
 #pragma unroll 4
     for (int vv = w.wtid; vv < nvec; vv += kWorkerThreads) {
       float x[8], wt[8], o[8];
-      unpack8(__ldcg(reinterpret_cast<const uint4*>(hrow) + vv), x);
+      unpack8(ld_weak(reinterpret_cast<const uint4*>(hrow) + vv), x);
       unpack8(__ldg(reinterpret_cast<const uint4*>(normw) + vv), wt);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = wt[j] * bf16_round(x[j] * rstd);
@@ -153,15 +148,30 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w
   }
 }
 
+__device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w, int T, bool embed, int splits,
+                                             const __nv_bfloat16* normw) {
+  if (embed) { rows_norm_impl<0>(c, w, T, normw); return; }
+  switch (splits) {
+    case 1: rows_norm_impl<1>(c, w, T, normw); break;
+    case 2: rows_norm_impl<2>(c, w, T, normw); break;
+    case 3: rows_norm_impl<3>(c, w, T, normw); break;
+    case 4: rows_norm_impl<4>(c, w, T, normw); break;
+    case 5: rows_norm_impl<5>(c, w, T, normw); break;
+    case 6: rows_norm_impl<6>(c, w, T, normw); break;
+    case 7: rows_norm_impl<7>(c, w, T, normw); break;
+    default: rows_norm_impl<8>(c, w, T, normw); break;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // q/k/v: split-K reduce + bias -> bf16, rotary embedding in bf16 arithmetic, scatter to qbuf / in-flight KV scratch.
 // One warp per (row, head slot); two items are processed together so both items' loads are in flight at once.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w, int T, int layer) {
+template <int SPLITS, int PPL>
+__device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& w, int T, int layer) {
   const ModelDims& md = c.md;
-  const int d = md.d, half = d >> 1, ppl = d >> 6;     // pairs per lane: 1 (d=64) or 2 (d=128)
+  const int d = md.d, half = d >> 1;
   const int nslots = md.n_q + 2 * md.n_kv;
-  const int splits = c.splits_qkv;
   const float* bias = c.layer[layer].bqkv;
   const int items = T * nslots;
   const int stride = w.nctas * 4;
@@ -170,39 +180,51 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
   for (int item0 = w.cta * 4 + w.wwarp; item0 < items; item0 += 2 * stride) {
     float lo[2][2], hi[2][2];
     int tt[2], slot[2], pos[2];
+    const float* p0[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const int item = item0 + q * stride;
-      lo[q][0] = lo[q][1] = hi[q][0] = hi[q][1] = 0.f;
-      tt[q] = -1;
-      if (item < items) {
-        const int t = item / nslots;
-        tt[q] = t; slot[q] = item - t * nslots;
-        pos[q] = __ldcg(&c.row_pos[t]);
-        const float* p0 = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane * ppl;
-        if (ppl == 2) {
-          float2 vl[8], vh[8];
+      int item = item0 + q * stride;
+      tt[q] = item < items ? 1 : -1;
+      if (item >= items) item = item0;                    // keep the second lane of work well-formed; result unused
+      const int t = item / nslots;
+      if (tt[q] > 0) tt[q] = t;
+      slot[q] = item - t * nslots;
+      pos[q] = ld_weak(&c.row_pos[t]);
+      p0[q] = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane * PPL;
+    }
+    if (PPL == 2) {
+      float2 vl[2][SPLITS], vh[2][SPLITS];
 #pragma unroll
-          for (int s2 = 0; s2 < 8; ++s2)
-            if (s2 < splits) {
-              vl[s2] = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * sstride));
-              vh[s2] = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * sstride + half));
-            }
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int s2 = 0; s2 < 8; ++s2)
-            if (s2 < splits) { lo[q][0] += vl[s2].x; lo[q][1] += vl[s2].y; hi[q][0] += vh[s2].x; hi[q][1] += vh[s2].y; }
-        } else {
-          float vl[8], vh[8];
+        for (int s2 = 0; s2 < SPLITS; ++s2) {
+          vl[q][s2] = ld_weak(reinterpret_cast<const float2*>(p0[q] + s2 * sstride));
+          vh[q][s2] = ld_weak(reinterpret_cast<const float2*>(p0[q] + s2 * sstride + half));
+        }
 #pragma unroll
-          for (int s2 = 0; s2 < 8; ++s2)
-            if (s2 < splits) { vl[s2] = __ldcg(p0 + s2 * sstride); vh[s2] = __ldcg(p0 + s2 * sstride + half); }
+      for (int q = 0; q < 2; ++q) {
+        lo[q][0] = lo[q][1] = hi[q][0] = hi[q][1] = 0.f;
 #pragma unroll
-          for (int s2 = 0; s2 < 8; ++s2)
-            if (s2 < splits) { lo[q][0] += vl[s2]; hi[q][0] += vh[s2]; }
+        for (int s2 = 0; s2 < SPLITS; ++s2) {             // slice order: deterministic
+          lo[q][0] += vl[q][s2].x; lo[q][1] += vl[q][s2].y; hi[q][0] += vh[q][s2].x; hi[q][1] += vh[q][s2].y;
         }
       }
+    } else {
+      float vl[2][SPLITS], vh[2][SPLITS];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int s2 = 0; s2 < SPLITS; ++s2) {
+          vl[q][s2] = ld_weak(p0[q] + s2 * sstride);
+          vh[q][s2] = ld_weak(p0[q] + s2 * sstride + half);
+        }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        lo[q][0] = lo[q][1] = hi[q][0] = hi[q][1] = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < SPLITS; ++s2) { lo[q][0] += vl[q][s2]; hi[q][0] += vh[q][s2]; }
+      }
     }
-    if (lo[0][0] == 12345.678f) prof_mark(c, w, 199);   // keep the mark after the loads' first use
     prof_mark(c, w, 101);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -215,25 +237,38 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
       else if (slot[q] < md.n_q + md.n_kv) dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, t, slot[q] - md.n_q);
       else dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, t, slot[q] - md.n_q - md.n_kv);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (j < ppl) {
-          const int e = w.lane * ppl + j;
-          float l = bf16_round(lo[q][j] + __ldg(bias + col0 + e));
-          float hv = bf16_round(hi[q][j] + __ldg(bias + col0 + half + e));
-          if (slot[q] < md.n_q + md.n_kv) {
-            const float cs = __bfloat162float(__ldg(c.rope_cos + (size_t)p * half + e));
-            const float sn = __bfloat162float(__ldg(c.rope_sin + (size_t)p * half + e));
-            const float nlo = bf16_round(bf16_round(l * cs) - bf16_round(hv * sn));
-            const float nhi = bf16_round(bf16_round(hv * cs) + bf16_round(l * sn));
-            l = nlo; hv = nhi;
-          }
-          dst[e] = __float2bfloat16_rn(l);
-          dst[half + e] = __float2bfloat16_rn(hv);
+      for (int j = 0; j < PPL; ++j) {
+        const int e = w.lane * PPL + j;
+        float l = bf16_round(lo[q][j] + __ldg(bias + col0 + e));
+        float hv = bf16_round(hi[q][j] + __ldg(bias + col0 + half + e));
+        if (slot[q] < md.n_q + md.n_kv) {
+          const float cs = __bfloat162float(__ldg(c.rope_cos + (size_t)p * half + e));
+          const float sn = __bfloat162float(__ldg(c.rope_sin + (size_t)p * half + e));
+          const float nlo = bf16_round(bf16_round(l * cs) - bf16_round(hv * sn));
+          const float nhi = bf16_round(bf16_round(hv * cs) + bf16_round(l * sn));
+          l = nlo; hv = nhi;
         }
+        dst[e] = __float2bfloat16_rn(l);
+        dst[half + e] = __float2bfloat16_rn(hv);
       }
     }
   }
   prof_mark(c, w, 102);
+}
+
+__device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w, int T, int layer) {
+  const int splits = c.splits_qkv;
+#define JF_ROPE_CASE(S)                                                                   \
+  case S:                                                                                 \
+    if (c.md.d == 128) qkv_rope_impl<S, 2>(c, w, T, layer); else qkv_rope_impl<S, 1>(c, w, T, layer); \
+    break;
+  switch (splits) {
+    JF_ROPE_CASE(1) JF_ROPE_CASE(2) JF_ROPE_CASE(3) JF_ROPE_CASE(4) JF_ROPE_CASE(5) JF_ROPE_CASE(6) JF_ROPE_CASE(7)
+    default:
+      if (c.md.d == 128) qkv_rope_impl<8, 2>(c, w, T, layer); else qkv_rope_impl<8, 1>(c, w, T, layer);
+      break;
+  }
+#undef JF_ROPE_CASE
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -243,8 +278,9 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
 // ---------------------------------------------------------------------------------------------------------------
 template <int D>
 __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, const Group& grp, int g_kvh, int chunk,
-                               int qs) {
+                               int qs, int hs) {
   constexpr int LDS = D + 8;                  // padded smem row (bf16 elements) -> conflict-free fragment loads
+  constexpr int VPR = D / 8;                  // 16-byte chunks per row
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem);
   __nv_bfloat16* Vs = Ks + kAttnSub * LDS;
   const uint32_t ks_addr = smem_u32(Ks), vs_addr = smem_u32(Vs);
@@ -256,17 +292,51 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
   const int q0 = qs * kQTokPerUnit;
   const int qn = min(kQTokPerUnit, len - q0);
   const int ntt = (qn + 15) >> 4;
-  const int tiles = md.n_rep * ntt;
+  const int hp = (md.n_rep + c.attn_hsplit - 1) / c.attn_hsplit;      // q heads of this kv head handled by one unit
+  const int j_lo = hs * hp, j_hi = min(md.n_rep, j_lo + hp);
+  const int tiles = max(0, j_hi - j_lo) * ntt;
   const int nsub = (key_hi - key_lo + kAttnSub - 1) / kAttnSub;
   const int* bt = c.block_tables + (size_t)grp.seq * c.max_pages_per_seq;
   const float scale = rsqrtf((float)D);
   const int r0 = w.lane >> 2, c2 = (w.lane & 3) * 2;
 
+  // K/V sub-tile fill: asynchronous 16-byte copies, one page-table lookup per 64-key sub-tile (kPage % kAttnSub == 0)
+  auto fill_issue = [&](int k0) {
+    const __nv_bfloat16* cbase[2] = {nullptr, nullptr};
+    if (k0 < ctx) {
+      const int page = ld_weak(bt + (k0 / kPage));
+      cbase[0] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 0, page, g_kvh, k0 % kPage);
+      cbase[1] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 1, page, g_kvh, k0 % kPage);
+    }
+    const __nv_bfloat16* sbase[2] = {c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, row0, g_kvh),
+                                     c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, row0, g_kvh)};
+    const size_t srow = (size_t)md.n_kv * D;             // scratch stride between consecutive tokens
+#pragma unroll 4
+    for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
+      const int kv = idx / (kAttnSub * VPR);
+      const int rem = idx - kv * (kAttnSub * VPR);
+      const int jr = rem / VPR, v = rem - jr * VPR;
+      const int pos = k0 + jr;
+      const __nv_bfloat16* src = sbase[kv];
+      uint32_t nbytes = 0;
+      if (pos < ctx) { src = cbase[kv] + (size_t)jr * D + v * 8; nbytes = 16; }
+      else if (pos < nkeys) { src = sbase[kv] + (size_t)(pos - ctx) * srow + v * 8; nbytes = 16; }
+      cp_async_16((kv ? Vs : Ks) + jr * LDS + v * 8, src, nbytes);
+    }
+    cp_async_commit();
+  };
+
+  if (tiles <= 0) return;
+  prof_mark(c, w, 400);
+  if (nsub == 1) {                                         // the common case: issue the fill first, overlap it with Q loads
+    workers_sync();                                        // previous readers of Ks / Vs are done
+    fill_issue(key_lo);
+  }
   for (int tb = 0; tb * 4 < tiles; ++tb) {
     const int tile = tb * 4 + w.wwarp;
     const bool tvalid = tile < tiles;
-    const int j = tvalid ? tile / ntt : 0;
-    const int tt = tvalid ? tile - j * ntt : 0;
+    const int j = j_lo + (tvalid ? tile / ntt : 0);
+    const int tt = tvalid ? tile % ntt : 0;
     const int i0 = q0 + tt * 16;
     const int head = g_kvh * md.n_rep + j;
     const int ia = i0 + r0, ib = i0 + r0 + 8;          // token indices of this thread's two fragment rows
@@ -279,11 +349,16 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
       const __nv_bfloat16* qb = c.qbuf + (size_t)(row0 + min(ib, len - 1)) * md.q_dim + head * D;
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks) {
-        qf[ks][0] = __ldcg(reinterpret_cast<const unsigned int*>(qa + ks * 16 + c2));
-        qf[ks][1] = __ldcg(reinterpret_cast<const unsigned int*>(qb + ks * 16 + c2));
-        qf[ks][2] = __ldcg(reinterpret_cast<const unsigned int*>(qa + ks * 16 + 8 + c2));
-        qf[ks][3] = __ldcg(reinterpret_cast<const unsigned int*>(qb + ks * 16 + 8 + c2));
+        qf[ks][0] = ld_weak(reinterpret_cast<const unsigned int*>(qa + ks * 16 + c2));
+        qf[ks][1] = ld_weak(reinterpret_cast<const unsigned int*>(qb + ks * 16 + c2));
+        qf[ks][2] = ld_weak(reinterpret_cast<const unsigned int*>(qa + ks * 16 + 8 + c2));
+        qf[ks][3] = ld_weak(reinterpret_cast<const unsigned int*>(qb + ks * 16 + 8 + c2));
       }
+    }
+    if (nsub == 1 && tb == 0) {
+      cp_async_wait_all();
+      workers_sync();
+      prof_mark(c, w, 401);
     }
     float o[D / 8][4];
 #pragma unroll
@@ -292,32 +367,9 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
 
     for (int sub = 0; sub < nsub; ++sub) {
       const int k0 = key_lo + sub * kAttnSub;
-      if (!(nsub == 1 && tb > 0)) {
-        workers_sync();                                   // previous readers of Ks / Vs are done
-        constexpr int VPR = D / 8;                        // 16-byte chunks per row
-        // a 64-key sub-tile never straddles a page (kPage % kAttnSub == 0): one table lookup, then plain strides
-        const __nv_bfloat16* cbase[2] = {nullptr, nullptr};
-        if (k0 < ctx) {
-          const int page = __ldcg(bt + (k0 / kPage));
-          cbase[0] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 0, page, g_kvh, k0 % kPage);
-          cbase[1] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 1, page, g_kvh, k0 % kPage);
-        }
-        const __nv_bfloat16* sbase[2] = {c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, row0, g_kvh),
-                                         c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, row0, g_kvh)};
-        const size_t srow = (size_t)md.n_kv * D;           // scratch stride between consecutive tokens
-#pragma unroll 4
-        for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
-          const int kv = idx / (kAttnSub * VPR);
-          const int rem = idx - kv * (kAttnSub * VPR);
-          const int jr = rem / VPR, v = rem - jr * VPR;
-          const int pos = k0 + jr;
-          const __nv_bfloat16* src = sbase[kv];
-          uint32_t nbytes = 0;
-          if (pos < ctx) { src = cbase[kv] + (size_t)jr * D + v * 8; nbytes = 16; }
-          else if (pos < nkeys) { src = sbase[kv] + (size_t)(pos - ctx) * srow + v * 8; nbytes = 16; }
-          cp_async_16((kv ? Vs : Ks) + jr * LDS + v * 8, src, nbytes);
-        }
-        cp_async_commit();
+      if (nsub > 1) {
+        workers_sync();
+        fill_issue(k0);
         cp_async_wait_all();
         workers_sync();
       }
@@ -338,6 +390,7 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
           mma_bf16_16816(s[nt], qf[2 * ks2 + 1], b2, b3);
         }
       }
+      prof_mark(c, w, 402);
       // scale, causal mask, running max
       const int qpa = ctx + ia, qpb = ctx + ib;
       float mxa = -INFINITY, mxb = -INFINITY;
@@ -395,6 +448,7 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
       }
     }
 
+    prof_mark(c, w, 403);
     if (tactive) {
       l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
       l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
@@ -421,106 +475,159 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
 __device__ __forceinline__ Group load_group(const DevCtx& c, int g) {
   Group grp;
   const int4* p = reinterpret_cast<const int4*>(c.groups + g);
-  const int4 a = __ldcg(p), b = __ldcg(p + 1);
+  const int4 a = ld_weak(p), b = ld_weak(p + 1);
   grp.row0 = a.x; grp.len = a.y; grp.seq = a.z; grp.ctx = a.w;
   grp.nchunks = b.x; grp.qsplit = b.y; grp.unit0 = b.z; grp.slot0 = b.w;
   return grp;
 }
 
 __device__ __noinline__ void stage_attention(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
+  const int hsplit = c.attn_hsplit;
   for (int u = w.cta; u < units; u += w.nctas) {
     int g = 0;
     Group grp = load_group(c, 0);
     while (g + 1 < G) {                                   // groups are few; linear scan over unit ranges
-      const int per = c.md.n_kv * grp.nchunks * grp.qsplit;
+      const int per = c.md.n_kv * grp.nchunks * grp.qsplit * hsplit;
       if (u < grp.unit0 + per) break;
       ++g;
       grp = load_group(c, g);
     }
-    const int local = u - grp.unit0;
-    const int kvh = local % c.md.n_kv;
-    const int rest = local / c.md.n_kv;
-    const int chunk = rest % grp.nchunks;
-    const int qs = rest / grp.nchunks;
-    if (c.md.d == 128) attention_unit<128>(c, w, layer, grp, kvh, chunk, qs);
-    else attention_unit<64>(c, w, layer, grp, kvh, chunk, qs);
+    int local = u - grp.unit0;
+    const int kvh = local % c.md.n_kv; local /= c.md.n_kv;
+    const int hs = local % hsplit; local /= hsplit;
+    const int chunk = local % grp.nchunks;
+    const int qs = local / grp.nchunks;
+    if (c.md.d == 128) attention_unit<128>(c, w, layer, grp, kvh, chunk, qs, hs);
+    else attention_unit<64>(c, w, layer, grp, kvh, chunk, qs, hs);
   }
 }
 
 // merge the per-chunk partials of every (token, head) in chunk order; write bf16 into the O-projection operand.
-// One warp per (token, head); lane ch holds the statistics of chunk ch, the chunk vectors are fetched 16 at a time.
+// One warp per (token, head), two items in flight per warp; lane ch holds the statistics of chunk ch, the chunk
+// vectors are fetched 8 at a time per item.  (Rows with more than 32 visible chunks take the generic two-pass path.)
+__device__ __forceinline__ void combine_store(const DevCtx& c, int t, int head, int lane, int vpl, int D,
+                                              const float (&acc)[4], float l) {
+  const float inv = 1.0f / l;
+  const int f = head * D + lane * vpl;                      // feature index = k index of the O projection
+  uint8_t* dst = reinterpret_cast<uint8_t*>(c.xa) + ((size_t)(f >> 6) * c.xrows_cap) * 128 + sw128_offset(t, f & 63);
+  if (vpl == 4) {
+    uint2 pk;
+    pk.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+    pk.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+    *reinterpret_cast<uint2*>(dst) = pk;
+  } else {
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+  }
+}
+
 __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerCtx& w, int T) {
   const ModelDims& md = c.md;
   const int D = md.d;
   const int vpl = D >> 5;                                  // floats per lane: 4 (d=128) or 2 (d=64)
   const int items = T * md.n_q;
   const size_t cstride = md.n_q;                            // slots of consecutive chunks are adjacent
+  const int stride = w.nctas * 4;
   prof_mark(c, w, 300);
-  for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
-    const int t = item / md.n_q, head = item - t * md.n_q;
-    const int2 ra = __ldcg(&c.row_attn[t]);
-    const int cmax = ra.y;                                  // last chunk holding a visible key
-    if (cmax == -77) prof_mark(c, w, 399);
+  for (int item0 = w.cta * 4 + w.wwarp; item0 < items; item0 += 2 * stride) {
+    int tt[2], hh[2], cmax[2];
+    size_t base[2];
+    float wl[2], ll[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int item = item0 + q * stride;
+      tt[q] = -1; cmax[q] = -1; base[q] = 0; hh[q] = 0;
+      if (item < items) {
+        tt[q] = item / md.n_q; hh[q] = item - tt[q] * md.n_q;
+        const int2 ra = ld_weak(&c.row_attn[tt[q]]);
+        cmax[q] = ra.y;
+        base[q] = (size_t)ra.x * md.n_q + hh[q];
+      }
+    }
     prof_mark(c, w, 301);
-    const size_t base = (size_t)ra.x * md.n_q + head;
-    float m = -INFINITY;
-    float l = 0.f;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    // pass 1 (only when more than 32 chunks): global maximum
-    if (cmax >= 32) {
-      for (int c0 = 0; c0 <= cmax; c0 += 32) {
-        const int ch = c0 + w.lane;
-        float mc = (ch <= cmax) ? __ldcg(c.attn_ml + (base + ch * cstride) * 2) : -INFINITY;
-        m = fmaxf(m, mc);
-      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    }
-    for (int c0 = 0; c0 <= cmax; c0 += 32) {
-      const int chl = c0 + w.lane;
+    for (int q = 0; q < 2; ++q) {                            // statistics of the first 32 chunks of both items
       float2 ml = make_float2(-INFINITY, 0.f);
-      if (chl <= cmax) ml = __ldcg(reinterpret_cast<const float2*>(c.attn_ml + (base + chl * cstride) * 2));
-      if (cmax < 32) {
-        m = ml.x;
+      if (tt[q] >= 0 && w.lane <= cmax[q]) ml = ld_weak(reinterpret_cast<const float2*>(c.attn_ml + (base[q] + w.lane * cstride) * 2));
+      float mx = ml.x;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      }
-      const float wl = (ml.x == -INFINITY) ? 0.f : __expf(ml.x - m);
-      const float ll = wl * ml.y;
-      const int nch = min(32, cmax + 1 - c0);
-      for (int cc = 0; cc < nch; cc += 16) {                // sixteen chunks' vectors in flight at a time
-        float4 v4[16];
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      wl[q] = (ml.x == -INFINITY) ? 0.f : __expf(ml.x - mx);
+      ll[q] = wl[q] * ml.y;
+    }
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float l[2] = {0.f, 0.f};
+    const int cm0 = (tt[0] >= 0 && cmax[0] < 32) ? cmax[0] : -1;     // -1: nothing to do on the fast path
+    const int cm1 = (tt[1] >= 0 && cmax[1] < 32) ? cmax[1] : -1;
+    const int nmax = max(cm0, cm1) + 1;
+    const float* ob[2] = {c.attn_o + base[0] * D + w.lane * vpl, c.attn_o + base[1] * D + w.lane * vpl};
+    const size_t ostride = cstride * D;
+    for (int cc = 0; cc < nmax; cc += 8) {
+      // Loads are unconditional (chunk index clamped, weight zeroed) so the batch stays in registers and in flight.
+      float4 v4[2][8];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          if (cc + u < nch) {
-            const float* op = c.attn_o + (base + (size_t)(c0 + cc + u) * cstride) * D + w.lane * vpl;
-            if (vpl == 4) v4[u] = __ldcg(reinterpret_cast<const float4*>(op));
-            else { const float2 t2 = __ldcg(reinterpret_cast<const float2*>(op)); v4[u] = make_float4(t2.x, t2.y, 0.f, 0.f); }
-          }
+      for (int q = 0; q < 2; ++q) {
+        const int cm = q ? cm1 : cm0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int ch = max(0, min(cc + u, cm));
+          const float* op = ob[q] + (size_t)ch * ostride;
+          if (vpl == 4) v4[q][u] = ld_weak(reinterpret_cast<const float4*>(op));
+          else { const float2 t2 = ld_weak(reinterpret_cast<const float2*>(op)); v4[q][u] = make_float4(t2.x, t2.y, 0.f, 0.f); }
         }
+      }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {                      // chunk order: deterministic
-          const float wgt = __shfl_sync(0xffffffffu, wl, (cc + u) & 31);
-          const float lc = __shfl_sync(0xffffffffu, ll, (cc + u) & 31);
-          if (cc + u < nch) {
-            l += lc;
-            acc[0] += wgt * v4[u].x; acc[1] += wgt * v4[u].y; acc[2] += wgt * v4[u].z; acc[3] += wgt * v4[u].w;
-          }
+      for (int q = 0; q < 2; ++q) {
+        const int cm = q ? cm1 : cm0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {                        // chunk order: deterministic
+          float wgt = __shfl_sync(0xffffffffu, wl[q], (cc + u) & 31);
+          float lc = __shfl_sync(0xffffffffu, ll[q], (cc + u) & 31);
+          if (cc + u > cm) { wgt = 0.f; lc = 0.f; }
+          l[q] += lc;
+          acc[q][0] += wgt * v4[q][u].x; acc[q][1] += wgt * v4[q][u].y;
+          acc[q][2] += wgt * v4[q][u].z; acc[q][3] += wgt * v4[q][u].w;
         }
       }
     }
-    if (l == 12345.678f) prof_mark(c, w, 398);
     prof_mark(c, w, 302);
-    const float inv = 1.0f / l;
-    const int f = head * D + w.lane * vpl;                  // feature index = k index of the O projection
-    uint8_t* dst = reinterpret_cast<uint8_t*>(c.xa) + ((size_t)(f >> 6) * c.xrows_cap) * 128 + sw128_offset(t, f & 63);
-    if (vpl == 4) {
-      uint2 pk;
-      pk.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
-      pk.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-      *reinterpret_cast<uint2*>(dst) = pk;
-    } else {
-      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (tt[q] < 0) continue;
+      if (cmax[q] >= 32) {                                   // long contexts: generic two-pass merge over all chunks
+        float mg = -INFINITY;
+        for (int c0 = 0; c0 <= cmax[q]; c0 += 32) {
+          const int ch = c0 + w.lane;
+          const float mc = (ch <= cmax[q]) ? ld_weak(c.attn_ml + (base[q] + ch * cstride) * 2) : -INFINITY;
+          mg = fmaxf(mg, mc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+        float lg = 0.f;
+        float ag[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c0 = 0; c0 <= cmax[q]; c0 += 32) {
+          const int chl = c0 + w.lane;
+          float2 ml = make_float2(-INFINITY, 0.f);
+          if (chl <= cmax[q]) ml = ld_weak(reinterpret_cast<const float2*>(c.attn_ml + (base[q] + chl * cstride) * 2));
+          const float wq = (ml.x == -INFINITY) ? 0.f : __expf(ml.x - mg);
+          const float lq = wq * ml.y;
+          const int nch = min(32, cmax[q] + 1 - c0);
+          for (int u = 0; u < nch; ++u) {
+            const float wgt = __shfl_sync(0xffffffffu, wq, u);
+            lg += __shfl_sync(0xffffffffu, lq, u);
+            const float* op = c.attn_o + (base[q] + (size_t)(c0 + u) * cstride) * D + w.lane * vpl;
+            if (vpl == 4) {
+              const float4 v = ld_weak(reinterpret_cast<const float4*>(op));
+              ag[0] += wgt * v.x; ag[1] += wgt * v.y; ag[2] += wgt * v.z; ag[3] += wgt * v.w;
+            } else {
+              const float2 v = ld_weak(reinterpret_cast<const float2*>(op));
+              ag[0] += wgt * v.x; ag[1] += wgt * v.y;
+            }
+          }
+        }
+        combine_store(c, tt[q], hh[q], w.lane, vpl, D, ag, lg);
+      } else {
+        combine_store(c, tt[q], hh[q], w.lane, vpl, D, acc[q], l[q]);
+      }
     }
   }
 }
@@ -534,14 +641,14 @@ __device__ __noinline__ void stage_commit(const DevCtx& c, const WorkerCtx& w, i
   for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
     const int e = item / per, lk = item - e * per;
     const int layer = lk >> 1, kv = lk & 1;
-    const int src_row = __ldcg(&c.commits[e].src_row);
-    const int seq = __ldcg(&c.commits[e].seq);
-    const int pos = __ldcg(&c.commits[e].pos);
-    const int page = __ldcg(c.block_tables + (size_t)seq * c.max_pages_per_seq + pos / kPage);
+    const int src_row = ld_weak(&c.commits[e].src_row);
+    const int seq = ld_weak(&c.commits[e].seq);
+    const int pos = ld_weak(&c.commits[e].pos);
+    const int page = ld_weak(c.block_tables + (size_t)seq * c.max_pages_per_seq + pos / kPage);
     for (int kvh = 0; kvh < md.n_kv; ++kvh) {
       const uint4* src = reinterpret_cast<const uint4*>(c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, kv, src_row, kvh));
       uint4* dst = reinterpret_cast<uint4*>(c.kv_cache + kv_cache_offset(md, c.num_pages, layer, kv, page, kvh, pos % kPage));
-      for (int v = w.lane; v < vpr; v += 32) dst[v] = __ldcg(src + v);
+      for (int v = w.lane; v < vpr; v += 32) dst[v] = ld_weak(src + v);
     }
   }
 }

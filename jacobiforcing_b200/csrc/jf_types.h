@@ -38,7 +38,7 @@ struct Group {
   int row0, len, seq, ctx;
   int nchunks;               // ceil((ctx + len) / attn_chunk)
   int qsplit;                // ceil(len / kQTokPerUnit)
-  int unit0;                 // first attention unit of this group (units = n_kv * nchunks * qsplit)
+  int unit0;                 // first attention unit of this group (units = n_kv * nchunks * qsplit * attn_hsplit)
   int slot0;                 // first partial slot (slots = len * nchunks)
 };
 
@@ -100,6 +100,7 @@ struct alignas(16) DevCtx {
   float* attn_ml;                    // [attn_slots_cap][n_q][2] (running max, running sum)
   int attn_slots_cap;
   int attn_chunk;                    // keys per attention unit (multiple of kAttnSub)
+  int attn_hsplit;                   // attention units per kv head along its q heads (2 when n_rep >= 4)
   unsigned long long* argmax_keys;   // [T_cap]
   float* row_ss;                     // [T_cap][8] per-slice sums of squares of the row being normalised
   int* row_cnt;                      // [T_cap] slices arrived (the last arriver normalises the row)
