@@ -250,7 +250,6 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   c.attn_hsplit = md.n_rep >= 4 ? 2 : 1;
   ALLOC(c.argmax_keys, c.T_cap, h->bytes_act);
   ALLOC(c.row_ss, (size_t)c.T_cap * 8, h->bytes_act);
-  ALLOC(c.row_cnt, c.T_cap, h->bytes_act);
   ALLOC(c.hdr, 1, h->bytes_act);
   ALLOC(c.tok, c.T_cap, h->bytes_act);
   ALLOC(c.row_group, c.T_cap, h->bytes_act);
@@ -564,6 +563,9 @@ extern "C" int jf_set_rope_tables(jf_handle h, const float* cosv, const float* s
 // ---------------------------------------------------------------------------------------------------------------
 static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float* elapsed_ms) {
   JF_CUDA(h, cudaMemsetAsync(h->hctx.bar_counter, 0, 16, h->stream));
+  h->hctx.launch_id = (h->hctx.launch_id + 1u) & 0xffu;
+  JF_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->dctx) + offsetof(DevCtx, launch_id), &h->hctx.launch_id, 4,
+                             cudaMemcpyHostToDevice, h->stream));
   const DevCtx* dctx = h->dctx;
   int smem_total = h->smem_optin;
   void* args[] = {(void*)&dctx, (void*)&smem_total, (void*)&run_mode, (void*)&max_forwards};

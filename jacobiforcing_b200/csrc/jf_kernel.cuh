@@ -27,8 +27,8 @@ __device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned
 // and thread 0's release-add after it is cumulative over them (the cooperative-groups grid.sync pattern); the
 // per-thread proxy fence makes those stores visible to bulk-copy (async proxy) reads issued by other CTAs.
 __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w, unsigned int& epoch,
-                                             int* prof_slot = nullptr) {
-  fence_proxy_async_all();
+                                             int* prof_slot = nullptr, bool tma_consumer = true) {
+  if (tma_consumer) fence_proxy_async_all();   // only stages whose output a bulk copy (async proxy) will read need it
   workers_sync();
   epoch += 1;
   if (w.wtid == 0) {
@@ -224,14 +224,15 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       gemm_epilogue(t, gs, cta, nctas, acc);
     }
     if (barrier_after) {
-      if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch, prof_slot); else epoch += 1;
+      if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch, prof_slot, t.epilogue == EPI_SWIGLU_BF16); else epoch += 1;
     }
   };
-#define JF_SIMT_STAGE(body)                                   \
+#define JF_SIMT_STAGE_X(tma_out, body)                         \
   do {                                                        \
-    if (ROLE == ROLE_WORKER) { body; grid_barrier(c, w, epoch, prof_slot); } else { epoch += 1; } \
+    if (ROLE == ROLE_WORKER) { w.tag = (c.launch_id << 24) ^ (epoch + 1u); body; grid_barrier(c, w, epoch, prof_slot, tma_out); } else { epoch += 1; } \
   } while (0)
 
+#define JF_SIMT_STAGE(body) JF_SIMT_STAGE_X(true, body)
   if (run_mode == RUN_JACOBI) {
     JF_SIMT_STAGE(if (cta == 0) policy_stage_jacobi(c, w, true, max_forwards));
   }
@@ -311,8 +312,8 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       const LayerW& lw = c.layer[l];
       const GemmTask tq = task_qkv(l), to = task_o(l), tg = task_gu(l), td = task_down(l);
       gemm_stage(tq, true, &to);
-      JF_SIMT_STAGE(if (!(c.debug_skip & 1)) stage_qkv_rope(c, w, T, l); if (c.debug_skip & 32) { workers_sync(); stage_qkv_rope(c, w, T, l); });
-      JF_SIMT_STAGE(if (!(c.debug_skip & 2)) stage_attention(c, w, l, ip.G, ip.attn_units));
+      JF_SIMT_STAGE_X(false, if (!(c.debug_skip & 1)) stage_qkv_rope(c, w, T, l));
+      JF_SIMT_STAGE_X(false, if (!(c.debug_skip & 2)) stage_attention(c, w, l, ip.G, ip.attn_units));
       JF_SIMT_STAGE(if (!(c.debug_skip & 4)) stage_attn_combine(c, w, T));
       gemm_stage(to, true, &tg);
       JF_SIMT_STAGE(if (!(c.debug_skip & 8)) stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2));
@@ -348,6 +349,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     });
   }
 #undef JF_SIMT_STAGE
+#undef JF_SIMT_STAGE_X
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1)

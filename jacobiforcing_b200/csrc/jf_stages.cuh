@@ -23,6 +23,7 @@ struct WorkerCtx {
   float* red;      // [8] block-reduction scratch
   uint8_t* attn_smem;
   int prof_on;     // CTA 0, forward being profiled
+  unsigned int tag; // unique id of the stage instance being executed (launch id, barrier count)
 };
 
 __device__ __forceinline__ void prof_mark(const DevCtx& c, const WorkerCtx& w, int id) {
@@ -72,7 +73,7 @@ template <int SPLITS>     // SPLITS == 0: embedding lookup instead of a split-K 
 __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx& w, int T, const __nv_bfloat16* normw) {
   const int h = c.md.h;
   const int nvec = h >> 3;
-  const int NS = (nvec + kWorkerThreads - 1) / kWorkerThreads;     // slices per row (<= 8)
+  const int NS = (nvec + kWorkerThreads - 1) / kWorkerThreads;     // slices per row (<= 8), one CTA each
   const int items = T * NS;
   prof_mark(c, w, 200);
   for (int item = w.cta; item < items; item += w.nctas) {
@@ -80,8 +81,9 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
     const int v = sl * kWorkerThreads + w.wtid;
     __nv_bfloat16* hrow = c.hidden + (size_t)t * h;
     float ss = 0.f;
+    float x[8], wt[8];
     if (v < nvec) {
-      float x[8];
+      const uint4 wraw = __ldg(reinterpret_cast<const uint4*>(normw) + v);       // needed last: fetch first
       if (SPLITS == 0) {
         int tk = ld_weak(&c.tok[t]);
         tk = tk < 0 ? 0 : (tk >= c.md.vocab ? c.md.vocab - 1 : tk);
@@ -105,6 +107,7 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = bf16_round(r[j] + bf16_round(acc[j]));
       }
+      unpack8(wraw, wt);
       reinterpret_cast<uint4*>(hrow)[v] = pack8(x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss += x[j] * x[j];
@@ -112,36 +115,35 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
     prof_mark(c, w, 201);
     ss = block_sum_128(ss, w);
     prof_mark(c, w, 202);
-    if (w.wtid == 0) {
-      int last = 1;
-      if (NS > 1) {
-        c.row_ss[t * 8 + sl] = ss;
-        __threadfence();   // cumulative over the slice's stores of the other threads (ordered by the barrier above)
-        last = (atomicAdd(&c.row_cnt[t], 1) == NS - 1) ? 1 : 0;
-        if (last) { __threadfence(); c.row_cnt[t] = 0; }
-      }
-      reinterpret_cast<int*>(w.red)[8] = last;
-    }
-    named_bar_sync(kBarReduce, kWorkerThreads);
-    const bool last = reinterpret_cast<const int*>(w.red)[8] != 0;
-    named_bar_sync(kBarReduce, kWorkerThreads);
-    prof_mark(c, w, 203);
-    if (!last) continue;
+    // The slices of a row exchange their sums of squares through one 64-bit word each, {stage tag, value}: a single
+    // relaxed store / polling load carries flag and payload together, so no fences, atomics or resets are needed.
     float total = ss;
     if (NS > 1) {
+      unsigned long long* slots = c.row_ss + (size_t)t * 8;
+      if (w.wtid == 0)
+        st_relaxed_gpu_u64(slots + sl, ((unsigned long long)w.tag << 32) | (unsigned long long)__float_as_uint(ss));
+      if (w.wtid < NS) {
+        unsigned long long word = ld_relaxed_gpu_u64(slots + w.wtid);
+        const long long t0 = clock64();
+        while ((unsigned int)(word >> 32) != w.tag) {
+          word = ld_relaxed_gpu_u64(slots + w.wtid);
+          if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+        }
+        w.red[8 + w.wtid] = __uint_as_float((unsigned int)(word & 0xffffffffull));
+      }
+      named_bar_sync(kBarReduce, kWorkerThreads);
       total = 0.f;
-      for (int s2 = 0; s2 < NS; ++s2) total += ld_weak(&c.row_ss[t * 8 + s2]);
+      for (int s2 = 0; s2 < NS; ++s2) total += w.red[8 + s2];            // slice order: the same on every CTA
+      named_bar_sync(kBarReduce, kWorkerThreads);
     }
-    const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
-#pragma unroll 4
-    for (int vv = w.wtid; vv < nvec; vv += kWorkerThreads) {
-      float x[8], wt[8], o[8];
-      unpack8(ld_weak(reinterpret_cast<const uint4*>(hrow) + vv), x);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(normw) + vv), wt);
+    prof_mark(c, w, 203);
+    if (v < nvec) {
+      const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
+      float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = wt[j] * bf16_round(x[j] * rstd);
-      uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(vv >> 3) * c.xrows_cap + t) * 128 +
-                     (((vv & 7) ^ (t & 7)) << 4);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(v >> 3) * c.xrows_cap + t) * 128 +
+                     (((v & 7) ^ (t & 7)) << 4);
       *reinterpret_cast<uint4*>(dst) = pack8(o);
     }
     prof_mark(c, w, 204);

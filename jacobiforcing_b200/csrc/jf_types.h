@@ -102,8 +102,8 @@ struct alignas(16) DevCtx {
   int attn_chunk;                    // keys per attention unit (multiple of kAttnSub)
   int attn_hsplit;                   // attention units per kv head along its q heads (2 when n_rep >= 4)
   unsigned long long* argmax_keys;   // [T_cap]
-  float* row_ss;                     // [T_cap][8] per-slice sums of squares of the row being normalised
-  int* row_cnt;                      // [T_cap] slices arrived (the last arriver normalises the row)
+  unsigned long long* row_ss;        // [T_cap][8] per-slice {stage tag, sum of squares} words of the row being normalised
+  unsigned int launch_id;            // makes the stage tags unique across launches
   int splits_qkv, splits_o, splits_down;
   // ---- plan (written by the host in plan mode, by the policy stage in Jacobi mode)
   PlanHdr* hdr;
