@@ -162,8 +162,18 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   if (!coop) return fail(JF_ERR_UNSUPPORTED, "device lacks cooperative launch");
 
   ModelDims& md = h->md;
-  md.h = m->hidden_size; md.layers = m->num_hidden_layers; md.n_q = m->num_attention_heads;
-  md.n_kv = m->num_key_value_heads; md.d = m->head_dim; md.inter = m->intermediate_size; md.vocab = m->vocab_size;
+  const int tp = r->tp_size > 1 ? r->tp_size : 1;
+  const int tpr = r->tp_size > 1 ? r->tp_rank : 0;
+  if (tp != 1 && tp != 2 && tp != 4) { g_create_error = "tp_size must be 1, 2 or 4"; delete h; return JF_ERR_UNSUPPORTED; }
+  if (tpr < 0 || tpr >= tp) { g_create_error = "tp_rank outside [0, tp_size)"; delete h; return JF_ERR_INVALID; }
+  if (m->num_attention_heads % tp || m->num_key_value_heads % tp || m->intermediate_size % tp || m->vocab_size % tp) {
+    g_create_error = "heads / kv heads / intermediate_size / vocab_size must be divisible by tp_size "
+                     "(reference: inference_engine/models/qwen3.py:31,34)";
+    delete h; return JF_ERR_INVALID;
+  }
+  md.h = m->hidden_size; md.layers = m->num_hidden_layers; md.n_q = m->num_attention_heads / tp;
+  md.n_kv = m->num_key_value_heads / tp; md.d = m->head_dim; md.inter = m->intermediate_size / tp;
+  md.vocab = m->vocab_size / tp; md.vocab_embed = m->vocab_size; md.vocab_offset = tpr * (m->vocab_size / tp);
   md.q_dim = md.n_q * md.d; md.kv_dim = md.n_kv * md.d; md.qkv_dim = md.q_dim + 2 * md.kv_dim;
   md.n_rep = md.n_kv > 0 ? md.n_q / md.n_kv : 0;
   md.tie = m->tie_word_embeddings; md.eps = m->rms_norm_eps; md.rope_theta = m->rope_theta;
@@ -171,7 +181,7 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   if (md.layers < 1 || md.layers > kMaxLayers) return fail(JF_ERR_INVALID, "num_hidden_layers outside [1, 64]");
   if (md.d != 64 && md.d != 128) return fail(JF_ERR_UNSUPPORTED, "head_dim must be 64 or 128");
   if (md.h % 64 || md.h > 8192) return fail(JF_ERR_UNSUPPORTED, "hidden_size must be a multiple of 64 and <= 8192");
-  if (md.inter % 64) return fail(JF_ERR_UNSUPPORTED, "intermediate_size must be a multiple of 64");
+  if (md.inter % 64) return fail(JF_ERR_UNSUPPORTED, "intermediate_size (per rank) must be a multiple of 64");
   if (md.n_kv < 1 || md.n_q % md.n_kv) return fail(JF_ERR_INVALID, "num_attention_heads must be a multiple of num_key_value_heads");
   if (md.vocab < 1 || md.max_pos < 1) return fail(JF_ERR_INVALID, "vocab_size / max_position_embeddings must be positive");
 
@@ -205,6 +215,10 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   c.splits_qkv = pick_splits(nt_qkv, kc_h, h->sm_count);
   c.splits_o = pick_splits(nt_h, kc_q, h->sm_count);
   c.splits_down = pick_splits(nt_h, kc_i, h->sm_count);
+  const int rs_cap = tp == 1 ? 8 : (tp == 2 ? 4 : 2);       // rows_norm keeps tp * splits slices in flight
+  c.splits_o = std::min(c.splits_o, rs_cap);
+  c.splits_down = std::min(c.splits_down, rs_cap);
+  c.tp_rank = tpr; c.tp_size = tp;
   h->max_splits = std::max(c.splits_qkv, std::max(c.splits_o, c.splits_down));
 
   int rc = JF_OK;
@@ -212,7 +226,7 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   auto layout = [&]() -> int {
   // ---- weights
   __nv_bfloat16 *embed, *lm_head, *final_norm, *cosb, *sinb;
-  ALLOC(embed, (size_t)md.vocab * md.h, h->bytes_weights);
+  ALLOC(embed, (size_t)md.vocab_embed * md.h, h->bytes_weights);
   ALLOC(lm_head, (size_t)nt_v * kc_h * 8192, h->bytes_weights);
   ALLOC(final_norm, md.h, h->bytes_weights);
   ALLOC(cosb, (size_t)md.max_pos * (md.d / 2), h->bytes_weights);
@@ -248,7 +262,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.qbuf, (size_t)c.T_cap * md.q_dim, h->bytes_act);
   c.attn_slots_cap = rt.attn_slots; c.attn_chunk = rt.attn_chunk;
   c.attn_hsplit = md.n_rep >= 4 ? 2 : 1;
-  ALLOC(c.argmax_keys, c.T_cap, h->bytes_act);
+  ALLOC(c.argmax_keys, (size_t)2 * c.T_cap, h->bytes_act);
+  ALLOC(c.xflag, kMaxTP, h->bytes_act);
   ALLOC(c.row_ss, (size_t)c.T_cap * 8, h->bytes_act);
   ALLOC(c.hdr, 1, h->bytes_act);
   ALLOC(c.tok, c.T_cap, h->bytes_act);
@@ -278,14 +293,16 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.bar_counter, 4, h->bytes_act);
   ALLOC(h->dctx, 1, h->bytes_act);
   // large, sparsely touched buffers last: the small hot ones above share the arena's first pages
-  c.part_splits = h->max_splits; c.part_n = std::max(md.qkv_dim, md.h);
+  c.part_splits = h->max_splits; c.part_n = md.qkv_dim;
   ALLOC(c.part, (size_t)c.T_cap * c.part_splits * c.part_n, h->bytes_act);
+  ALLOC(c.part_rs[0], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
+  ALLOC(c.part_rs[1], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.attn_ml, (size_t)c.attn_slots_cap * md.n_q * 2, h->bytes_act);
   ALLOC(c.attn_o, (size_t)c.attn_slots_cap * md.n_q * md.d, h->bytes_act);
   ALLOC(c.xact, (size_t)kc_i * c.xrows_cap * 64, h->bytes_act);
   ALLOC(c.kv_scratch, (size_t)md.layers * 2 * rt.max_rows * md.n_kv * md.d, h->bytes_act);
   // staging: the largest single HF tensor (embedding / lm_head or gate/up/down)
-  h->stage_elems = std::max((size_t)md.vocab * md.h, (size_t)md.inter * md.h);
+  h->stage_elems = std::max((size_t)md.vocab_embed * md.h, (size_t)md.inter * md.h);
     return JF_OK;
   };
   h->arena_mode = 1;
@@ -302,6 +319,10 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   h->arena_mode = 2;
   if ((rc = layout()) != JF_OK) return fail(rc, h->err);
   h->arena_mode = 0;
+  for (int r2 = 0; r2 < kMaxTP; ++r2) {            // until jf_tp_import: every 'peer' is this rank itself
+    c.peer_part_rs[r2][0] = c.part_rs[0]; c.peer_part_rs[r2][1] = c.part_rs[1];
+    c.peer_keys[r2] = c.argmax_keys; c.peer_xflag[r2] = c.xflag;
+  }
   if ((rc = dev_alloc(h, &h->stage, h->stage_elems, (int64_t*)nullptr)) != JF_OK) return fail(rc, h->err);
   if ((rc = dev_alloc(h, &h->bias_stage, (size_t)md.qkv_dim + 128, (int64_t*)nullptr)) != JF_OK) return fail(rc, h->err);
 #undef ALLOC
@@ -337,6 +358,40 @@ extern "C" int jf_device_info(jf_handle h, int32_t* sm_count, int64_t* bw, int64
 }
 
 extern "C" int64_t jf_launch_count(jf_handle h) { return h ? h->launches : 0; }
+
+extern "C" int jf_tp_export(jf_handle h, void* handle64) {
+  if (!h || !handle64) return JF_ERR_INVALID;
+  cudaSetDevice(h->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t ipc;
+  JF_CUDA(h, cudaIpcGetMemHandle(&ipc, h->arena_base[2]));
+  memcpy(handle64, &ipc, 64);
+  return JF_OK;
+}
+
+extern "C" int jf_tp_import(jf_handle h, const void* handles) {
+  if (!h || !handles) return JF_ERR_INVALID;
+  cudaSetDevice(h->device);
+  DevCtx& c = h->hctx;
+  const uint8_t* mine = h->arena_base[2];
+  for (int r = 0; r < c.tp_size; ++r) {
+    uint8_t* base = h->arena_base[2];
+    if (r != c.tp_rank) {
+      cudaIpcMemHandle_t ipc;
+      memcpy(&ipc, reinterpret_cast<const uint8_t*>(handles) + (size_t)r * 64, 64);
+      void* p = nullptr;
+      JF_CUDA(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+      base = reinterpret_cast<uint8_t*>(p);
+    }
+    // every rank lays its arena out identically, so a peer's buffer sits at the same offset
+    c.peer_part_rs[r][0] = reinterpret_cast<const float*>(base + (reinterpret_cast<const uint8_t*>(c.part_rs[0]) - mine));
+    c.peer_part_rs[r][1] = reinterpret_cast<const float*>(base + (reinterpret_cast<const uint8_t*>(c.part_rs[1]) - mine));
+    c.peer_keys[r] = reinterpret_cast<const unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.argmax_keys) - mine));
+    c.peer_xflag[r] = reinterpret_cast<unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.xflag) - mine));
+  }
+  if (h->finalized) JF_CUDA(h, cudaMemcpy(h->dctx, &h->hctx, sizeof(DevCtx), cudaMemcpyHostToDevice));
+  return JF_OK;
+}
 
 extern "C" int jf_profile_enable(jf_handle h, int32_t forward_index) {
   if (!h) return JF_ERR_INVALID;
@@ -422,6 +477,12 @@ static int stage_tensor(jf_engine* h, const void* data, size_t n, int dtype) {
   return JF_OK;
 }
 
+static int pack_staged_from(jf_engine* h, __nv_bfloat16* dst, int R, int K, int dest_row0, size_t stage_off) {
+  pack_rows_into_tiles_kernel<<<2048, 256, 0, h->stream>>>(h->stage + stage_off, dst, R, K, K / 64, dest_row0);
+  ++h->launches;
+  JF_CUDA(h, cudaStreamSynchronize(h->stream));
+  return JF_OK;
+}
 static int pack_staged(jf_engine* h, __nv_bfloat16* dst, int R, int K, int dest_row0) {
   pack_rows_into_tiles_kernel<<<2048, 256, 0, h->stream>>>(h->stage, dst, R, K, K / 64, dest_row0);
   ++h->launches;
@@ -450,12 +511,12 @@ extern "C" int jf_load_tensor(jf_handle h, const char* name, const void* data, c
   int rc;
   std::string s(name);
   if (s == "model.embed_tokens.weight") {
-    if (!want(md.vocab, md.h)) return JF_ERR_INVALID;
+    if (!want(md.vocab_embed, md.h)) return JF_ERR_INVALID;
     if ((rc = stage_tensor(h, data, n, dtype)) != JF_OK) return rc;
     JF_CUDA(h, cudaMemcpyAsync(const_cast<__nv_bfloat16*>(c.embed), h->stage, n * 2, cudaMemcpyDeviceToDevice, h->stream));
     h->seen_global |= G_EMBED;
     if (md.tie) {
-      if ((rc = pack_staged(h, const_cast<__nv_bfloat16*>(c.lm_head), md.vocab, md.h, 0)) != JF_OK) return rc;
+      if ((rc = pack_staged_from(h, const_cast<__nv_bfloat16*>(c.lm_head), md.vocab, md.h, 0, (size_t)md.vocab_offset * md.h)) != JF_OK) return rc;
       h->seen_global |= G_HEAD;
     }
     JF_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -564,6 +625,9 @@ extern "C" int jf_set_rope_tables(jf_handle h, const float* cosv, const float* s
 static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float* elapsed_ms) {
   JF_CUDA(h, cudaMemsetAsync(h->hctx.bar_counter, 0, 16, h->stream));
   h->hctx.launch_id = (h->hctx.launch_id + 1u) & 0xffu;
+  h->hctx.xflag_base += (1ull << 32);
+  JF_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->dctx) + offsetof(DevCtx, xflag_base), &h->hctx.xflag_base, 8,
+                             cudaMemcpyHostToDevice, h->stream));
   JF_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->dctx) + offsetof(DevCtx, launch_id), &h->hctx.launch_id, 4,
                              cudaMemcpyHostToDevice, h->stream));
   const DevCtx* dctx = h->dctx;

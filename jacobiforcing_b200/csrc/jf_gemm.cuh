@@ -54,6 +54,7 @@ struct GemmTask {
   int out_split_stride;      // PARTIAL: floats between the k-split slices of one row
   int epilogue;
   int out_rows_cap;          // SWIGLU: xrows_cap of the destination packed buffer
+  int index_offset;          // ARGMAX: added to the local feature index (vocabulary slice of this rank)
 };
 
 struct GemmSmem {
@@ -331,7 +332,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
           unsigned long long mine = 0ull;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            unsigned long long key = valid ? argmax_key(bf16_round(__uint_as_float(v[j])), n) : 0ull;
+            unsigned long long key = valid ? argmax_key(bf16_round(__uint_as_float(v[j])), n + t.index_offset) : 0ull;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
               const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);

@@ -26,17 +26,42 @@ __device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned
 // Grid barrier of the worker warps.  Writer side: every worker's global stores are ordered before the CTA barrier,
 // and thread 0's release-add after it is cumulative over them (the cooperative-groups grid.sync pattern); the
 // per-thread proxy fence makes those stores visible to bulk-copy (async proxy) reads issued by other CTAs.
-__device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w, unsigned int& epoch,
-                                             int* prof_slot = nullptr, bool tma_consumer = true) {
+// Barrier k is complete when counter >= k * nctas + (cross-GPU barriers so far): a cross-GPU barrier adds ONE extra
+// arrival, made by CTA 0 after it has exchanged flags with every tensor-parallel peer through NVLink peer memory.
+struct BarState {
+  unsigned int epoch = 0;      // barriers passed
+  unsigned int xcount = 0;     // of which cross-GPU
+  __device__ __forceinline__ unsigned int target(unsigned int nctas) const { return epoch * nctas + xcount; }
+};
+
+__device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w, BarState& bs,
+                                             int* prof_slot = nullptr, bool tma_consumer = true, bool xgpu = false) {
   if (tma_consumer) fence_proxy_async_all();   // only stages whose output a bulk copy (async proxy) will read need it
   workers_sync();
-  epoch += 1;
+  const unsigned int local_target = (bs.epoch + 1) * (unsigned int)w.nctas + bs.xcount;
+  bs.epoch += 1;
+  if (xgpu) bs.xcount += 1;
   if (w.wtid == 0) {
     long long t_arrive = 0;
     if (prof_slot) t_arrive = clock64();
     prof_mark(c, w, 900);
     red_release_gpu_add_u32(c.bar_counter, 1u);
-    wait_epoch<false>(c.bar_counter, epoch * (unsigned int)w.nctas);   // critical path: spin, do not sleep
+    if (xgpu && w.cta == 0) {
+      wait_epoch<false>(c.bar_counter, local_target);          // every CTA of this GPU has arrived
+      fence_acq_rel_sys();
+      const unsigned long long val = c.xflag_base + bs.xcount;
+      for (int r = 0; r < c.tp_size; ++r)
+        if (r != c.tp_rank) st_relaxed_sys_u64(c.peer_xflag[r] + c.tp_rank, val);
+      const long long t0 = clock64();
+      for (int r = 0; r < c.tp_size; ++r) {
+        if (r == c.tp_rank) continue;
+        while (ld_relaxed_sys_u64(c.xflag + r) < val)
+          if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+      }
+      fence_acq_rel_sys();
+      red_release_gpu_add_u32(c.bar_counter, 1u);              // the extra arrival releases this GPU's CTAs
+    }
+    wait_epoch<false>(c.bar_counter, bs.target(w.nctas));      // critical path: spin, do not sleep
     if (prof_slot && *prof_slot + 2 <= c.prof_cap) {      // (arrival of CTA 0, release of the barrier)
       c.prof[*prof_slot] = t_arrive;
       c.prof[*prof_slot + 1] = clock64();
@@ -50,15 +75,27 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
 // ---------------------------------------------------------------------------------------------------------------
 // policy stages (CTA 0, worker warps)
 // ---------------------------------------------------------------------------------------------------------------
+// best key over the tensor-parallel ranks (each holds the argmax of its vocabulary slice; the packed key orders by
+// value, then by LOWEST global index, so the merge keeps torch.argmax's first-maximum rule)
+__device__ __forceinline__ unsigned long long merged_key(const DevCtx& c, int kbuf, int t) {
+  const size_t off = (size_t)kbuf * c.T_cap + t;
+  if (c.tp_size == 1) return ld_weak(&c.argmax_keys[off]);
+  unsigned long long best = 0ull;
+  for (int r = 0; r < c.tp_size; ++r) {
+    const unsigned long long k = (r == c.tp_rank) ? ld_weak(&c.argmax_keys[off]) : ld_relaxed_sys_u64(c.peer_keys[r] + off);
+    best = k > best ? k : best;
+  }
+  return best;
+}
+
 __device__ __noinline__ void policy_stage_plan(const DevCtx& c, const WorkerCtx& w) {
   PlanHdr* hdr = c.hdr;
+  const int kbuf = ld_weak(&hdr->iter) & 1;
   const int n_lm = ld_weak(&hdr->n_lm_tasks);
   for (int i = 0; i < n_lm; ++i) {
     const int r0 = ld_weak(&hdr->lm_row0[i]), rn = ld_weak(&hdr->lm_rows[i]);
     for (int t = r0 + w.wtid; t < r0 + rn; t += kWorkerThreads) {
-      const unsigned long long key = ld_weak(&c.argmax_keys[t]);
-      c.greedy[t] = argmax_key_index(key);
-      c.argmax_keys[t] = 0ull;
+      c.greedy[t] = argmax_key_index(merged_key(c, kbuf, t));
     }
   }
   if (w.wtid == 0) {
@@ -72,10 +109,12 @@ __device__ __noinline__ void policy_stage_plan(const DevCtx& c, const WorkerCtx&
 __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerCtx& w, bool first, int max_forwards) {
   PlanHdr* hdr = c.hdr;
   const int Tprev = first ? 0 : ld_weak(&hdr->T);
-  for (int t = w.wtid; t < Tprev; t += kWorkerThreads) {
-    const unsigned long long key = ld_weak(&c.argmax_keys[t]);
-    c.greedy[t] = argmax_key_index(key);
-    c.argmax_keys[t] = 0ull;
+  const int kbuf = first ? 0 : (ld_weak(&hdr->iter) & 1);
+  if (!first) {
+    for (int t = w.wtid; t < Tprev; t += kWorkerThreads) c.greedy[t] = argmax_key_index(merged_key(c, kbuf, t));
+    // the OTHER buffer is cleared for the next forward; its last readers (the previous policy stage of every rank)
+    // are separated from this point by that forward's cross-GPU barriers
+    for (int t = w.wtid; t < c.T_cap; t += kWorkerThreads) c.argmax_keys[(size_t)(kbuf ^ 1) * c.T_cap + t] = 0ull;
   }
   __threadfence_block();
   workers_sync();
@@ -198,24 +237,26 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
                          int run_mode, int max_forwards) {
   WorkerCtx w = w_in;
   const int cta = blockIdx.x, nctas = gridDim.x;
-  unsigned int epoch = 0;
+  BarState bs;
   PipeState pipe;
   AccState acc;
   const ModelDims& md = c.md;
   const int kc_h = md.h >> 6, kc_q = md.q_dim >> 6, kc_i = md.inter >> 6;
   const int nt_qkv = (md.qkv_dim + 127) >> 7, nt_h = (md.h + 127) >> 7, nt_i = (md.inter + 127) >> 7;
   const int nt_v = (md.vocab + 127) >> 7;
+  const bool tp = c.tp_size > 1;
   int nstages = 1, slot_bytes = 0;
   int prof_n = 0;
   int* prof_slot = nullptr;
 
-  auto gemm_stage = [&](const GemmTask& t, bool barrier_after, const GemmTask* next = nullptr) {
+  auto skip_barrier = [&](bool xgpu) { bs.epoch += 1; if (xgpu) bs.xcount += 1; };
+  auto gemm_stage = [&](const GemmTask& t, bool barrier_after, const GemmTask* next = nullptr, bool xgpu = false) {
     if (ROLE == ROLE_W) {
-      if (c.debug_skip & 16) wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);   // experiment: no run-ahead
+      if (c.debug_skip & 16) wait_epoch(c.bar_counter, bs.target(nctas));   // experiment: no run-ahead
       gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
       if (next != nullptr) gemm_prefetch_l2(*next, cta, nctas, c.prefetch_tiles);
     } else if (ROLE == ROLE_X) {
-      wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);
+      wait_epoch(c.bar_counter, bs.target(nctas));
       fence_proxy_async_all();
       gemm_produce_x(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
     } else if (ROLE == ROLE_MMA) {
@@ -224,12 +265,12 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       gemm_epilogue(t, gs, cta, nctas, acc);
     }
     if (barrier_after) {
-      if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch, prof_slot, t.epilogue == EPI_SWIGLU_BF16); else epoch += 1;
+      if (ROLE == ROLE_WORKER) grid_barrier(c, w, bs, prof_slot, t.epilogue == EPI_SWIGLU_BF16, xgpu); else skip_barrier(xgpu);
     }
   };
 #define JF_SIMT_STAGE_X(tma_out, body)                         \
   do {                                                        \
-    if (ROLE == ROLE_WORKER) { w.tag = (c.launch_id << 24) ^ (epoch + 1u); body; grid_barrier(c, w, epoch, prof_slot, tma_out); } else { epoch += 1; } \
+    if (ROLE == ROLE_WORKER) { w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); body; grid_barrier(c, w, bs, prof_slot, tma_out); } else { skip_barrier(false); } \
   } while (0)
 
 #define JF_SIMT_STAGE(body) JF_SIMT_STAGE_X(true, body)
@@ -238,7 +279,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   }
 
   for (;;) {
-    if (ROLE != ROLE_WORKER) wait_epoch(c.bar_counter, epoch * (unsigned int)nctas);
+    if (ROLE != ROLE_WORKER) wait_epoch(c.bar_counter, bs.target(nctas));
     const PlanHdr* hdr = c.hdr;
     IterPlan ip;
     ip.T = ld_weak(&hdr->T); ip.G = ld_weak(&hdr->G); ip.done = ld_weak(&hdr->done);
@@ -247,6 +288,9 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     if (ip.done) {
       if (ROLE == ROLE_WORKER) {
         if (prof_slot != nullptr && w.wtid == 0) *c.prof_count = prof_n;
+        if (tp) grid_barrier(c, w, bs, nullptr, false, true);      // every rank has read every rank's keys
+        if (cta == 0)
+          for (int t = w.wtid; t < 2 * c.T_cap; t += kWorkerThreads) c.argmax_keys[t] = 0ull;   // clean for the next launch
         stage_commit(c, w, ip.n_commit);
       }
       break;
@@ -268,11 +312,11 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     nstages = min(kMaxStages, ring_bytes / slot_bytes);
     pipe.stage = 0;
 
-    JF_SIMT_STAGE(stage_commit(c, w, ip.n_commit); stage_rows_norm(c, w, T, true, 0, c.layer[0].ln1));
+    JF_SIMT_STAGE(stage_commit(c, w, ip.n_commit); stage_rows_norm(c, w, T, true, 0, c.layer[0].ln1, 0));
 
     auto base_task = [&]() {
       GemmTask t;
-      t.M = T; t.x_row0 = 0; t.xrows_cap = c.xrows_cap; t.out_rows_cap = c.xrows_cap;
+      t.M = T; t.x_row0 = 0; t.xrows_cap = c.xrows_cap; t.out_rows_cap = c.xrows_cap; t.index_offset = 0;
       t.out_row_stride = c.part_splits * c.part_n; t.out_split_stride = c.part_n;
       return t;
     };
@@ -284,8 +328,8 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     };
     auto task_o = [&](int l) {
       GemmTask t = base_task();
-      t.W = c.layer[l].wo; t.X = c.xa; t.out = c.part; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
-      t.N = md.h; t.epilogue = EPI_PARTIAL_F32;
+      t.W = c.layer[l].wo; t.X = c.xa; t.out = c.part_rs[0]; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
+      t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
       return t;
     };
     auto task_gu = [&](int l) {       // gate/up projection with the SwiGLU epilogue
@@ -296,13 +340,14 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     };
     auto task_down = [&](int l) {
       GemmTask t = base_task();
-      t.W = c.layer[l].wd; t.X = c.xact; t.out = c.part; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
-      t.N = md.h; t.epilogue = EPI_PARTIAL_F32;
+      t.W = c.layer[l].wd; t.X = c.xact; t.out = c.part_rs[1]; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
+      t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
       return t;
     };
     auto task_lm = [&](int i) {
       GemmTask t = base_task();
-      t.W = c.lm_head; t.X = c.xn; t.out = c.argmax_keys; t.n_tiles = nt_v; t.k_chunks = kc_h; t.splits = 1;
+      t.W = c.lm_head; t.X = c.xn; t.out = c.argmax_keys + (size_t)(ld_weak(&hdr->iter) & 1) * c.T_cap;
+      t.n_tiles = nt_v; t.k_chunks = kc_h; t.splits = 1; t.index_offset = md.vocab_offset;
       t.M = ld_weak(&hdr->lm_rows[i]); t.x_row0 = ld_weak(&hdr->lm_row0[i]);
       t.N = md.vocab; t.epilogue = EPI_ARGMAX;
       return t;
@@ -315,20 +360,20 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       JF_SIMT_STAGE_X(false, if (!(c.debug_skip & 1)) stage_qkv_rope(c, w, T, l));
       JF_SIMT_STAGE_X(false, if (!(c.debug_skip & 2)) stage_attention(c, w, l, ip.G, ip.attn_units));
       JF_SIMT_STAGE(if (!(c.debug_skip & 4)) stage_attn_combine(c, w, T));
-      gemm_stage(to, true, &tg);
-      JF_SIMT_STAGE(if (!(c.debug_skip & 8)) stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2));
+      gemm_stage(to, true, &tg, tp);
+      JF_SIMT_STAGE(if (!(c.debug_skip & 8)) stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2, 0));
       gemm_stage(tg, true, &td);
       if (l + 1 < md.layers) {
         const GemmTask tn = task_qkv(l + 1);
-        gemm_stage(td, true, &tn);
+        gemm_stage(td, true, &tn, tp);
       } else if (ip.n_lm > 0) {
         const GemmTask tn = task_lm(0);
-        gemm_stage(td, true, &tn);
+        gemm_stage(td, true, &tn, tp);
       } else {
-        gemm_stage(td, true);
+        gemm_stage(td, true, nullptr, tp);
       }
       JF_SIMT_STAGE(stage_rows_norm(c, w, T, false, c.splits_down,
-                                    (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm));
+                                    (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm, 1));
     }
 
     // LM head: fused bf16-rounded argmax (no logits in HBM); optional fp32 logits for the tolerance checks
@@ -342,7 +387,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         gemm_stage(t, false);
       }
     }
-    if (ROLE == ROLE_WORKER) grid_barrier(c, w, epoch, prof_slot); else epoch += 1;
+    if (ROLE == ROLE_WORKER) grid_barrier(c, w, bs, prof_slot, true, tp); else skip_barrier(tp);
 
     JF_SIMT_STAGE(if (cta == 0) {
       if (run_mode == RUN_JACOBI) policy_stage_jacobi(c, w, false, max_forwards); else policy_stage_plan(c, w);

@@ -69,8 +69,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // once); each slice publishes its sum of squares, and the CTA that arrives last for a row adds the slice sums in slice
 // order (deterministic, independent of who is last) and normalises the whole row.
 // ---------------------------------------------------------------------------------------------------------------
-template <int SPLITS>     // SPLITS == 0: embedding lookup instead of a split-K reduce
-__device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx& w, int T, const __nv_bfloat16* normw) {
+// SPLITS == 0: embedding lookup instead of a reduce.  TP = tensor-parallel ranks whose partial sums are added (rank order,
+// then split order, identical on every rank): rank r's slices live in peer memory reached through c.peer_part_rs.
+template <int SPLITS, int TP>
+__device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx& w, int T, const __nv_bfloat16* normw,
+                                               int which) {
   const int h = c.md.h;
   const int nvec = h >> 3;
   const int NS = (nvec + kWorkerThreads - 1) / kWorkerThreads;     // slices per row (<= 8), one CTA each
@@ -86,19 +89,27 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
       const uint4 wraw = __ldg(reinterpret_cast<const uint4*>(normw) + v);       // needed last: fetch first
       if (SPLITS == 0) {
         int tk = ld_weak(&c.tok[t]);
-        tk = tk < 0 ? 0 : (tk >= c.md.vocab ? c.md.vocab - 1 : tk);
+        tk = tk < 0 ? 0 : (tk >= c.md.vocab_embed ? c.md.vocab_embed - 1 : tk);
         unpack8(__ldg(reinterpret_cast<const uint4*>(c.embed + (size_t)tk * h) + v), x);
       } else {
-        // every split-K slice of this 8-column group is in flight before the first add; the sum runs in slice order
+        // every slice of this 8-column group is in flight before the first add; the sum runs in (rank, split) order
         const uint4 rr = ld_weak(reinterpret_cast<const uint4*>(hrow) + v);
-        const float4* p = reinterpret_cast<const float4*>(c.part + (size_t)t * c.part_splits * c.part_n) + v * 2;
-        const size_t sstride4 = (size_t)c.part_n >> 2;
-        float4 pa[SPLITS > 0 ? SPLITS : 1], pb[SPLITS > 0 ? SPLITS : 1];
+        const size_t roff = (size_t)t * c.part_splits * h;
+        const size_t sstride4 = (size_t)h >> 2;
+        float4 pa[(SPLITS > 0 ? SPLITS : 1) * TP], pb[(SPLITS > 0 ? SPLITS : 1) * TP];
 #pragma unroll
-        for (int s2 = 0; s2 < SPLITS; ++s2) { pa[s2] = ld_weak(p + s2 * sstride4); pb[s2] = ld_weak(p + s2 * sstride4 + 1); }
+        for (int r = 0; r < TP; ++r) {
+          const float* src = (TP == 1) ? c.part_rs[which] : c.peer_part_rs[r][which];
+          const float4* p = reinterpret_cast<const float4*>(src + roff) + v * 2;
+#pragma unroll
+          for (int s2 = 0; s2 < SPLITS; ++s2) {
+            pa[r * SPLITS + s2] = ld_weak(p + s2 * sstride4);
+            pb[r * SPLITS + s2] = ld_weak(p + s2 * sstride4 + 1);
+          }
+        }
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int s2 = 0; s2 < SPLITS; ++s2) {
+        for (int s2 = 0; s2 < SPLITS * TP; ++s2) {
           acc[0] += pa[s2].x; acc[1] += pa[s2].y; acc[2] += pa[s2].z; acc[3] += pa[s2].w;
           acc[4] += pb[s2].x; acc[5] += pb[s2].y; acc[6] += pb[s2].z; acc[7] += pb[s2].w;
         }
@@ -150,19 +161,29 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
   }
 }
 
+// which: 0 = after the O projection, 1 = after the down projection (selects the row-split partial buffer)
 __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w, int T, bool embed, int splits,
-                                             const __nv_bfloat16* normw) {
-  if (embed) { rows_norm_impl<0>(c, w, T, normw); return; }
-  switch (splits) {
-    case 1: rows_norm_impl<1>(c, w, T, normw); break;
-    case 2: rows_norm_impl<2>(c, w, T, normw); break;
-    case 3: rows_norm_impl<3>(c, w, T, normw); break;
-    case 4: rows_norm_impl<4>(c, w, T, normw); break;
-    case 5: rows_norm_impl<5>(c, w, T, normw); break;
-    case 6: rows_norm_impl<6>(c, w, T, normw); break;
-    case 7: rows_norm_impl<7>(c, w, T, normw); break;
-    default: rows_norm_impl<8>(c, w, T, normw); break;
+                                             const __nv_bfloat16* normw, int which) {
+  if (embed) { rows_norm_impl<0, 1>(c, w, T, normw, which); return; }
+#define JF_NORM_CASE(S, TPN) case S: rows_norm_impl<S, TPN>(c, w, T, normw, which); break;
+  if (c.tp_size == 1) {
+    switch (splits) {
+      JF_NORM_CASE(1, 1) JF_NORM_CASE(2, 1) JF_NORM_CASE(3, 1) JF_NORM_CASE(4, 1) JF_NORM_CASE(5, 1) JF_NORM_CASE(6, 1)
+      JF_NORM_CASE(7, 1)
+      default: rows_norm_impl<8, 1>(c, w, T, normw, which); break;
+    }
+  } else if (c.tp_size == 2) {
+    switch (splits) {
+      JF_NORM_CASE(1, 2) JF_NORM_CASE(2, 2) JF_NORM_CASE(3, 2)
+      default: rows_norm_impl<4, 2>(c, w, T, normw, which); break;
+    }
+  } else {                       // tp_size == 4 (creation rejects other sizes; splits are capped at 2 for tp 4)
+    switch (splits) {
+      JF_NORM_CASE(1, 4)
+      default: rows_norm_impl<2, 4>(c, w, T, normw, which); break;
+    }
   }
+#undef JF_NORM_CASE
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@ constexpr int kMaxLayers   = 64;     // the per-layer weight table lives in shar
 constexpr int kAttnSub     = 64;     // keys per mma.sync sub-tile
 constexpr int kMaxLmTasks  = 16;     // LM-head row tiles of kArgmaxRows per forward
 constexpr int kQTokPerUnit = 64;     // query tokens one attention unit covers
+constexpr int kMaxTP       = 8;      // tensor-parallel ranks whose buffers one kernel may address (NVLink peers)
 
 struct ModelDims {
   int h, layers, n_q, n_kv, d, inter, vocab;
@@ -20,6 +21,8 @@ struct ModelDims {
   float eps;
   float rope_theta;
   int max_pos;               // rows of the rope tables
+  int vocab_embed;           // rows of the (replicated) embedding table; `vocab` is the LM-head slice of this rank
+  int vocab_offset;          // first vocabulary id of this rank's LM-head slice
 };
 
 struct LayerW {
@@ -95,13 +98,15 @@ struct alignas(16) DevCtx {
   float* part;                       // [T_cap][part_splits][part_n] split-K partial sums, row-major by ROW so the live
                                      // rows of a forward share a few 2 MB pages (TLB reach matters: see DESIGN.md)
   int part_splits, part_n;
+  float* part_rs[2];                 // [T_cap][part_splits][h]: partials of the row-split GEMMs (0 = O, 1 = down); with
+                                     // tensor parallelism the peers read them over NVLink, hence double-buffered
   __nv_bfloat16* qbuf;               // [T_cap][q_dim] rotated queries
   float* attn_o;                     // [attn_slots_cap][n_q][d] unnormalised partial outputs
   float* attn_ml;                    // [attn_slots_cap][n_q][2] (running max, running sum)
   int attn_slots_cap;
   int attn_chunk;                    // keys per attention unit (multiple of kAttnSub)
   int attn_hsplit;                   // attention units per kv head along its q heads (2 when n_rep >= 4)
-  unsigned long long* argmax_keys;   // [T_cap]
+  unsigned long long* argmax_keys;   // [2][T_cap] packed (value, ~index) keys, double-buffered by forward parity
   unsigned long long* row_ss;        // [T_cap][8] per-slice {stage tag, sum of squares} words of the row being normalised
   unsigned int launch_id;            // makes the stage tags unique across launches
   int splits_qkv, splits_o, splits_down;
@@ -128,6 +133,14 @@ struct alignas(16) DevCtx {
   int* trace;                        // optional forward trace: {iter, seq, ctx, B, L, tokens...}*
   int trace_cap;
   int* trace_len;
+  // ---- tensor parallelism: every rank runs the same kernel on its shard; row-split partial sums and argmax keys are
+  // read straight out of the peers' memory (CUDA IPC mappings), cross-GPU barriers are flags in peer memory
+  int tp_rank, tp_size;
+  const float* peer_part_rs[kMaxTP][2];
+  const unsigned long long* peer_keys[kMaxTP];
+  unsigned long long* peer_xflag[kMaxTP];     // rank r's flag array (this rank writes element [tp_rank])
+  unsigned long long* xflag;                  // own flag array [kMaxTP]
+  unsigned long long xflag_base;              // launch sequence << 32 (flags are monotonic, never reset)
   // ---- sync
   unsigned int* bar_counter;
   // ---- optional stage profile: SM-clock stamps taken by CTA 0 after every grid barrier of forward `prof_forward`

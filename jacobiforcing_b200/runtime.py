@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _cabi
 from .policy import MODES, POLICY_ERRORS, STOP_REASONS, PolicyKnobs, draw_choice_indices, draw_prefill_draft
+from .tp import check_divisibility, shard_tensor
 
 PAGE = 256
 
@@ -51,7 +52,8 @@ class JacobiResult:
 class JacobiRuntime:
     def __init__(self, hf_config, *, device: int = 0, max_rows: int = 1024, max_seqs: int = 8,
                  num_kv_pages: int = 64, max_pages_per_seq: int = 8, attn_chunk: int = 64, attn_slots: int = 0,
-                 gen_capacity: int = 4096, max_calls: int = 256, trace_capacity: int = 0):
+                 gen_capacity: int = 4096, max_calls: int = 256, trace_capacity: int = 0,
+                 tp_rank: int = 0, tp_size: int = 1, tp_group=None):
         self.lib = _cabi.load()
         g = (lambda k, d=None: hf_config[k] if isinstance(hf_config, dict) else getattr(hf_config, k, d))
         heads = int(g("num_attention_heads"))
@@ -65,9 +67,12 @@ class JacobiRuntime:
             hidden, int(g("num_hidden_layers")), heads, int(g("num_key_value_heads")), int(head_dim),
             int(g("intermediate_size")), int(g("vocab_size")), int(bool(g("tie_word_embeddings", False))),
             int(g("max_position_embeddings")), float(g("rms_norm_eps", 1e-6)), float(theta))
+        check_divisibility(hf_config, tp_size)
+        self.tp_rank, self.tp_size = tp_rank, tp_size
         self.runtime_cfg = _cabi.RuntimeCfg(device, max_rows, max_seqs, num_kv_pages, max_pages_per_seq, attn_chunk,
-                                            attn_slots, gen_capacity, max_calls, trace_capacity)
+                                            attn_slots, gen_capacity, max_calls, trace_capacity, tp_rank, tp_size)
         self.vocab = int(g("vocab_size"))
+        self.vocab_local = self.vocab // tp_size
         self.hidden = hidden
         self.max_rows = (max(max_rows, 16) + 15) & ~15
         self.max_seqs = max_seqs
@@ -80,6 +85,20 @@ class JacobiRuntime:
         self.free_pages = list(range(num_kv_pages - 1, -1, -1))
         self._next_seq = 0
         self.stats = {"forwards": 0, "device_ms": 0.0, "rows": 0}
+        if tp_size > 1:
+            self._connect_peers(tp_group)
+
+    def _connect_peers(self, group) -> None:
+        """Exchange the CUDA IPC handles of the activation arenas (torch.distributed is only the transport) so the
+        kernel can read peers' partial sums / argmax keys and signal barriers over NVLink."""
+        import torch.distributed as dist
+        mine = (C.c_ubyte * 64)()
+        _cabi.check(self.lib.jf_tp_export(self.h, mine), self.h)
+        gathered = [None] * self.tp_size
+        dist.all_gather_object(gathered, bytes(mine), group=group)
+        blob = (C.c_ubyte * (64 * self.tp_size))(*b"".join(gathered))
+        _cabi.check(self.lib.jf_tp_import(self.h, blob), self.h)
+        dist.barrier(group=group)
 
     # ---- lifecycle -----------------------------------------------------------------------------------------------
     def close(self):
@@ -134,7 +153,7 @@ class JacobiRuntime:
         import torch
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t)
-        t = t.detach().contiguous()
+        t = shard_tensor(name, t.detach(), self.tp_rank, self.tp_size).contiguous()
         if t.is_cuda:
             # the library copies on its own stream: the producer kernels on torch's stream must have finished
             torch.cuda.current_stream(t.device).synchronize()
@@ -198,7 +217,7 @@ class JacobiRuntime:
         commits = _i32(commits).reshape(-1, 3)
         bt = self._block_tables(seqs)
         greedy = np.zeros(T, np.int32)
-        logits = np.zeros((lm_rows, self.vocab), np.float32) if want_logits else None
+        logits = np.zeros((lm_rows, self.vocab_local), np.float32) if want_logits else None   # this rank's vocabulary slice
         hidden = np.zeros((T, self.hidden), np.uint16) if want_hidden else None
         ms = C.c_float()
         _cabi.check(self.lib.jf_forward(self.h, T, _ptr(tokens), groups.shape[0], _ptr(groups), len(seqs), _ptr(bt),

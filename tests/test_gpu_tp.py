@@ -1,0 +1,118 @@
+"""Tensor parallelism on real GPUs (needs >= 2 B200 with NVLink peer access; skipped otherwise): one process per GPU,
+the persistent kernel on every rank reading the peers' row-split partial sums and argmax keys over NVLink.
+Checks: both ranks return identical ids / iteration counts; the gathered logits match the single-GPU engine and the HF
+fp32 oracle within the bf16 tolerance; Jacobi == AR on the sharded engine; ids equal the single-GPU ids up to near-ties
+(the cross-rank sum changes the fp32 summation order)."""
+import os
+import random
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(rank)
+        from jacobiforcing_b200.runtime import JacobiRuntime, hf_generate
+        from oracle.hf_model import build_model, rope_tables, state_dict_bf16, teacher_forced_logits
+        model = build_model("tiny", seed=0, dtype=torch.float32)
+        sd = state_dict_bf16(model)
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(v.to(torch.bfloat16).to(torch.float32))
+        cfg = model.config
+        cos, sin = rope_tables(float(cfg.rope_theta), cfg.hidden_size // cfg.num_attention_heads,
+                               cfg.max_position_embeddings)
+        kw = dict(device=rank, max_rows=256, max_seqs=4, num_kv_pages=16, max_pages_per_seq=4)
+        rt = JacobiRuntime(cfg, tp_rank=rank, tp_size=world, **kw)
+        rt.load_state_dict(sd)
+        rt.set_rope_tables(cos.numpy(), sin.numpy())
+        g = torch.Generator().manual_seed(1)
+        ids = torch.randint(0, cfg.vocab_size, (72,), generator=g).tolist()
+        seq = rt.new_sequence(); rt.ensure_capacity(seq, len(ids))
+        res = rt.forward(ids, [(0, len(ids), 0, 0)], [seq], 0, len(ids), want_logits=True)
+        parts = [None] * world
+        dist.all_gather_object(parts, res["logits"])
+        logits = np.concatenate(parts, axis=1)
+        greedy_all = [None] * world
+        dist.all_gather_object(greedy_all, res["greedy"].tolist())
+        ref = teacher_forced_logits(model, ids).numpy()
+        err = np.abs(logits - ref)
+        out = {"max_err": float(err.max()), "mean_err": float(err.mean()),
+               "greedy_same_on_ranks": all(g2 == greedy_all[0] for g2 in greedy_all),
+               "fused_argmax_ok": bool((np.array(greedy_all[0]) ==
+                                        torch.from_numpy(logits).to(torch.bfloat16).float().argmax(-1).numpy()).all())}
+        rt.release(seq)
+        prompt = torch.randint(0, cfg.vocab_size, (24,), generator=g).tolist()
+        runs = {}
+        for mode, n in (("single", 1), ("single", 8), ("multiblock", 8)):
+            seqs, results, run = hf_generate(rt, [prompt], n=n, max_new_tokens=40, mode=mode, pad=0,
+                                             rngs=[random.Random(2)])
+            runs[(mode, n)] = (results[0].tokens[:40], results[0].iters, run["forwards"])
+            for s in seqs:
+                rt.release(s)
+        out["jacobi_equals_ar"] = runs[("single", 1)][0] == runs[("single", 8)][0] == runs[("multiblock", 8)][0]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, runs)
+        out["runs_same_on_ranks"] = all(r2 == gathered[0] for r2 in gathered)
+        out["tokens"] = runs[("multiblock", 8)][0]
+        out["iters"] = runs[("multiblock", 8)][1]
+        dist.barrier()
+        rt.close()
+        if rank == 0:                                   # the single-GPU engine on the same weights
+            rt1 = JacobiRuntime(cfg, **kw)
+            rt1.load_state_dict(sd)
+            rt1.set_rope_tables(cos.numpy(), sin.numpy())
+            seqs, results, _ = hf_generate(rt1, [prompt], n=8, max_new_tokens=40, mode="multiblock", pad=0,
+                                           rngs=[random.Random(2)])
+            out["tokens_tp1"] = results[0].tokens[:40]
+            same = next((i for i, (a, b) in enumerate(zip(out["tokens"], out["tokens_tp1"])) if a != b), 40)
+            out["common_prefix_vs_tp1"] = same
+            if same < 40:
+                lg = teacher_forced_logits(model, prompt + out["tokens_tp1"][:same])[-1]
+                t2 = lg.topk(2).values
+                out["margin_at_divergence"] = float(t2[0] - t2[1])
+            rt1.close()
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_tp2_matches_single_gpu_and_oracle():
+    import torch.multiprocessing as mp
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0, "a tensor-parallel rank failed"
+    r0, r1 = ret[0], ret[1]
+    print("TP2 rank0:", {k: v for k, v in r0.items() if k not in ("tokens", "tokens_tp1")})
+    assert r0["max_err"] <= 2.5e-2 and r0["mean_err"] <= 4e-3
+    assert r0["greedy_same_on_ranks"] and r0["fused_argmax_ok"]
+    assert r0["runs_same_on_ranks"] and r1["runs_same_on_ranks"]
+    assert r0["jacobi_equals_ar"] and r1["jacobi_equals_ar"]
+    assert r0["tokens"] == r1["tokens"] and r0["iters"] == r1["iters"]
+    if r0["common_prefix_vs_tp1"] < 40:
+        assert r0["margin_at_divergence"] < 3e-2
