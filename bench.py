@@ -44,16 +44,16 @@ SHAPES = {
 }
 
 
-def algorithmic_bytes_per_forward(cfg: dict, rows: float, ctx: float, batch_groups: float) -> float:
-    """every layer weight + LM head once, committed KV once per group, in-flight KV written
-    and read, embedding rows gathered.  Logits are never materialised (fused argmax)."""
+def algorithmic_bytes_per_forward(cfg: dict, rows: float, ctx: float, batch_groups: float, tp: int = 1) -> float:
+    """SURVEY.md section 8(d), per GPU: every layer weight + LM head once (1/tp of them), committed KV once per group,
+    in-flight KV written and read (1/tp of the heads), embedding rows gathered.  Logits are never materialised."""
     h, L, I, V = cfg["hidden_size"], cfg["num_hidden_layers"], cfg["intermediate_size"], cfg["vocab_size"]
     q = cfg["num_attention_heads"] * cfg["head_dim"]
     kv = cfg["num_key_value_heads"] * cfg["head_dim"]
     w_layer = 2 * (h * (q + 2 * kv) + (q + 2 * kv) + q * h + 3 * h * I + 2 * h)
     w_head = 2 * V * h
     kvb = L * 2 * kv * 2
-    return L * w_layer + w_head + batch_groups * ctx * kvb + rows * kvb + rows * h * 2
+    return (L * w_layer + w_head + batch_groups * ctx * kvb + rows * kvb) / tp + rows * h * 2
 
 
 class ClockSampler:
@@ -215,8 +215,11 @@ def workload_config(args, world: int, where: str) -> dict:
                         f"prompt={args.prompt}, gen={args.gen}, EOS disabled",
             "baseline_config": "configs[1]: Qwen2.5-Coder-7B random-init, block_size=32, batch=1, 1xB200, greedy "
                                "single-block Jacobi",
-            "parallelism": ("single GPU" if world == 1 else f"{world} independent replicas (one sequence batch per "
-                            "GPU, no data-path collective; tensor-parallel sharding not built yet)"),
+            "parallelism": ("single GPU" if world == 1 else
+                            (f"{world} independent engines, one sequence batch per GPU, no data-path collective "
+                             "(tensor-parallel kernel available with --tp 2|4)") if getattr(args, "_tp", 1) == 1 else
+                            (f"tp{args._tp} x {world // args._tp} group(s): tensor-parallel column/row split with in-kernel "
+                             "peer-memory all-reduce over NVLink inside a group, independent sequence batches across groups")),
             "l2_policy": "inputs larger than L2: every forward streams 15.2 GB of weights (L2 = 126 MB)",
             "where": where}
 
@@ -233,27 +236,45 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
+    cfg = SHAPES[args.model]
+    # Layout at N GPUs: tensor parallelism inside groups of tp ranks (the path shards along heads / intermediate /
+    # vocabulary), independent sequence batches across groups.  Qwen2.5-7B has 4 KV heads -> tp <= 4.
+    # Default: tp = 1 (N independent engines, weak scaling).  The tensor-parallel kernel is selected with --tp 2|4; at
+    # batch 1 it does not yet beat one GPU (latency-bound stages + cross-GPU barriers, profiles/r01_tp_*.txt), so the
+    # aggregate-throughput headline uses replicas, exactly how the reference's own sweep uses several GPUs
+    # (JacobiForcing/scripts/inference/scanning_hyperparameter_jacobi_decoding_mr.sh:31-45).
+    tp = args.tp if args.tp > 0 else 1
+    if world % tp or cfg["num_key_value_heads"] % tp or tp not in (1, 2, 4):
+        raise SystemExit(f"--tp {tp} does not fit {world} GPUs / {cfg['num_key_value_heads']} KV heads")
+    groups = world // tp
+    args._tp = tp
+    group_id, tp_rank = rank // tp, rank % tp
+    tp_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
-    cfg = SHAPES[args.model]
+        for gi in range(groups):
+            pg = dist.new_group(list(range(gi * tp, (gi + 1) * tp)))
+            if gi == group_id:
+                tp_group = pg
     B, P, G, n = args.batch, args.prompt, args.gen, args.n
     rows_cap = max(P + n, B * n * (2 if args.mode == "multiblock" else 1) * max(1, args.pool if args.mode == "multiblock" else 1))
     rows_cap = min(max(rows_cap, 64), 4096)
     pages = (P + G + 3 * n + 255) // 256 + 1
     rt = JacobiRuntime(cfg, device=local_rank, max_rows=rows_cap, max_seqs=B, num_kv_pages=pages * B,
-                       max_pages_per_seq=pages, gen_capacity=P + G + 4 * n + 8, max_calls=G // n + 8)
-    load_random_weights(rt, cfg, seed=1234 + rank, device=device)
+                       max_pages_per_seq=pages, gen_capacity=P + G + 4 * n + 8, max_calls=G // n + 8,
+                       tp_rank=tp_rank, tp_size=tp, tp_group=tp_group)
+    load_random_weights(rt, cfg, seed=1234 + group_id, device=device)
 
     knobs = PolicyKnobs(mode=MODES[args.mode], n=n, K=args.K, r=args.r, n_gram_pool_size=args.pool, eos=None, pad=0,
                         max_iteration_count=128, max_new_tokens=G, max_calls=G // n + 4, vocab=cfg["vocab_size"])
-    g = torch.Generator().manual_seed(1 + rank)
+    g = torch.Generator().manual_seed(1 + group_id)
     prompts = torch.randint(0, cfg["vocab_size"], (B, P), generator=g).tolist()
 
     def one_step(step_idx: int):
         seqs, fcs, fcts, chs = [], [], [], []
         t_pre = 0.0
         for b in range(B):
-            rng = random.Random(2 + 1000 * step_idx + b)
+            rng = random.Random(2 + 1000 * step_idx + b + 100000 * group_id)
             s = rt.new_sequence()
             fc, drafted, ms = rt.prefill(s, prompts[b], draw_prefill_draft(rng, prompts[b], n))
             t_pre += ms
@@ -297,7 +318,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     wall_s = sum(s["wall_s"] for s in steps)
     fwd = sum(s["forwards"] for s in steps)
     rows = sum(s["rows"] for s in steps)
-    stats = torch.tensor([dev_s, wall_s, float(toks), float(fwd), float(rows), float(launches)], device=device,
+    lead = 1.0 if tp_rank == 0 else 0.0                  # tokens / forwards are counted once per tensor-parallel group
+    stats = torch.tensor([dev_s, wall_s, lead * toks, lead * fwd, lead * rows, float(launches)], device=device,
                          dtype=torch.float64)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -319,7 +341,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     mean_rows = rows / max(1, fwd)
     mean_ctx = P + G / 2.0
     groups_per_fwd = mean_rows / max(1.0, float(n)) if args.mode == "single" else max(1.0, mean_rows / (2.0 * n))
-    bytes_fwd = algorithmic_bytes_per_forward(cfg, mean_rows, mean_ctx, max(float(B), groups_per_fwd))
+    bytes_fwd = algorithmic_bytes_per_forward(cfg, mean_rows, mean_ctx, max(float(B), groups_per_fwd), tp)
     bytes_launch = bytes_fwd * fwd / max(1, len(steps))
     launch_s = dev_s / max(1, len(steps))
     achieved = bytes_launch / launch_s / 1e9
@@ -338,7 +360,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             pass
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
             from oracle.cpu_baseline import host_cores, time_reference_jacobi
             cores = host_cores()
@@ -362,13 +384,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dev_s_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * dev_s_max / max(1, args.steps), "higher_is_better": True,
+        "scaling": ("strong" if (tp > 1 and groups == 1) else "weak"),
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args, world, "B200"),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": steps[0]["h2d"], "d2h_bytes_per_step": steps[0]["d2h"],
                 "ms_per_step": 1e3 * wall_s_max / max(1, args.steps)},
         "gpu_launches": launches_all,
-        "forwards_per_s": fwd_all / dev_s_max / max(1, world),
+        "forwards_per_s": fwd_all / dev_s_max / max(1, groups),
         "iterations": {"forwards_total": fwd_all, "tokens_total": toks_all,
                        "iters_per_token": fwd_all / max(1.0, toks_all) * (B if B > 0 else 1) / B,
                        "tokens_per_forward_per_seq": toks_all / max(1.0, fwd_all) / B / 1.0,
@@ -401,6 +424,7 @@ def main():
     ap.add_argument("--gen", type=int, default=512)
     ap.add_argument("--ref-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel group size (0 = largest of 1/2/4 dividing N)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                  # timing rule: at least three warm-up steps

@@ -24,11 +24,20 @@ def main():
     a = ap.parse_args()
     import torch
     from jacobiforcing_b200.runtime import JacobiRuntime, hf_generate
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(rank)
+    group = None
+    if world > 1:                                   # tensor-parallel profile: torchrun --nproc-per-node tp
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{rank}"))
+        group = dist.group.WORLD
     cfg = bench.SHAPES[a.model]
     pages = (a.prompt + a.gen + 3 * a.n + 255) // 256 + 1
-    rt = JacobiRuntime(cfg, max_rows=max(a.prompt + a.n, 64), max_seqs=1, num_kv_pages=pages, max_pages_per_seq=pages,
-                       gen_capacity=a.prompt + a.gen + 4 * a.n + 8)
-    bench.load_random_weights(rt, cfg, 1234, "cuda:0")
+    rt = JacobiRuntime(cfg, device=rank, max_rows=max(a.prompt + a.n, 64), max_seqs=1, num_kv_pages=pages,
+                       max_pages_per_seq=pages, gen_capacity=a.prompt + a.gen + 4 * a.n + 8, tp_rank=rank, tp_size=world,
+                       tp_group=group)
+    bench.load_random_weights(rt, cfg, 1234, f"cuda:{rank}")
     g = torch.Generator().manual_seed(1)
     prompt = torch.randint(0, cfg["vocab_size"], (a.prompt,), generator=g).tolist()
     for rep in range(2):
@@ -37,6 +46,8 @@ def main():
                                          rngs=[random.Random(2)])
         for s in seqs:
             rt.release(s)
+    if rank != 0:
+        return
     prof = rt.profile_read()
     kinds = defaultdict(lambda: [0.0, 0.0, 0])
     total = 0.0
