@@ -46,12 +46,21 @@ def load_model(runner: "ModelRunner", path: str) -> None:
 
 class ModelRunner:
     def __init__(self, config: Config, rank: int = 0, event=None):
-        if config.tensor_parallel_size != 1:
-            raise NotImplementedError("tensor_parallel_size > 1: the sharded persistent kernel is not built yet "
-                                      "(DESIGN.md, multi-GPU); run one engine per GPU")
         self.config = config
         self.rank = rank
-        self.world_size = 1
+        self.world_size = config.tensor_parallel_size
+        tp_group = None
+        if config.tensor_parallel_size > 1:
+            # SPMD instead of the reference's spawned workers + SHM RPC (engine/llm_engine.py:31-44, model_runner.py:
+            # 423-458): every rank is started by the launcher (torchrun, one process per GPU), builds the same engine
+            # and makes the same calls; the ranks only meet inside the kernel, over NVLink peer memory.
+            import torch.distributed as dist
+            if not dist.is_initialized() or dist.get_world_size() != config.tensor_parallel_size:
+                raise RuntimeError("tensor_parallel_size > 1 needs torch.distributed initialised with one process per "
+                                   "GPU (world_size == tensor_parallel_size); launch with torchrun")
+            self.rank = dist.get_rank()
+            config.device = self.rank
+            tp_group = dist.group.WORLD
         hf = config.hf_config
         self.block_size = config.kvcache_block_size
         assert self.block_size == PAGE, "the device KV cache uses 256-token pages"
@@ -64,7 +73,8 @@ class ModelRunner:
         self.rt = JacobiRuntime(hf, device=config.device, max_rows=rows, max_seqs=max_seqs,
                                 num_kv_pages=config.num_kvcache_blocks, max_pages_per_seq=self.max_pages_per_seq,
                                 gen_capacity=config.max_model_len + 1024 + 64, max_calls=1024,
-                                trace_capacity=1 << 20)
+                                trace_capacity=1 << 20, tp_rank=(self.rank if self.world_size > 1 else 0),
+                                tp_size=self.world_size, tp_group=tp_group)
         self.rt.free_pages = []                            # pages are owned by the scheduler's BlockManager
         if config.state_dict is not None:
             self.rt.load_state_dict(config.state_dict)

@@ -116,3 +116,50 @@ def test_tp2_matches_single_gpu_and_oracle():
     assert r0["tokens"] == r1["tokens"] and r0["iters"] == r1["iters"]
     if r0["common_prefix_vs_tp1"] < 40:
         assert r0["margin_at_divergence"] < 3e-2
+
+
+def _llm_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(rank)
+        from jacobiforcing_b200 import LLM, SamplingParams
+        from oracle.hf_model import build_model, state_dict_bf16
+        model = build_model("tiny", seed=0, dtype=torch.float32)
+        llm = LLM(None, hf_config=model.config, state_dict=state_dict_bf16(model), max_model_len=2048,
+                  num_kvcache_blocks=64, max_num_seqs=8, max_num_batched_tokens=2048, draft_seed=7,
+                  tensor_parallel_size=world)
+        llm.config.eos, llm.config.pad = -1, 0
+        llm.scheduler.eos = -1
+        g = torch.Generator().manual_seed(0)
+        prompts = [torch.randint(0, 1000, (16 + 5 * i,), generator=g).tolist() for i in range(3)]
+        ar = llm.generate(prompts, SamplingParams(temperature=0.0, max_tokens=48, decode_strategy="autoregressive"),
+                          use_tqdm=False)
+        jc = llm.generate(prompts, SamplingParams(temperature=0.0, max_tokens=48, decode_strategy="jacobi",
+                                                  jacobi_block_len=8), use_tqdm=False)
+        ret[rank] = ([a["token_ids"][:48] for a in ar], [j["token_ids"][:48] for j in jc])
+        dist.barrier()
+        llm.exit()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_llm_api_tensor_parallel():
+    """LLM(..., tensor_parallel_size=2).generate on two ranks: Jacobi == AR, identical on both ranks."""
+    import torch.multiprocessing as mp
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_llm_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    assert ret[0] == ret[1]
+    ar, jc = ret[0]
+    assert ar == jc
