@@ -108,7 +108,7 @@ int jf_commit_rows(jf_handle h, int32_t n_seqs, const int32_t* block_tables, int
  *   pad_stream[s][pad_stream_len]                 engine: the random padding tokens, consumed in order
  *   block_tables[s][max_pages_per_seq]
  * Outputs: out_tokens[s][out_capacity] generated ids, out_summary[s][8] = {n_generated, calls, stop_reason,
- * total_new_tokens, policy_error, total_iterations, ctx_len, reserved}, iters_log[s][max_calls] (may be NULL),
+ * total_new_tokens, policy_error, total_iterations, ctx_len, next_token (first_correct_token for a following call)}, iters_log[s][max_calls] (may be NULL),
  * run_stats[4] = {forwards, elapsed_ms (device), rows_total, reserved}, trace (may be NULL) int32[trace_capacity]
  * with trace_len words used: {iter, seq, ctx, B, L, B*L tokens}*. */
 int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs* knobs, const int32_t* prompts,

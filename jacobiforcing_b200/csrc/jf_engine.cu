@@ -850,7 +850,7 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
     memcpy(out_tokens + (size_t)s * out_capacity, &hgen[(size_t)s * c.gen_cap + st.prompt_len0], (size_t)ncopy * 4);
     int32_t* sm = out_summary + (size_t)s * 8;
     sm[0] = ngen; sm[1] = st.calls; sm[2] = st.stop_reason; sm[3] = st.total_new; sm[4] = st.error;
-    sm[5] = st.total_iters; sm[6] = st.ctx; sm[7] = 0;
+    sm[5] = st.total_iters; sm[6] = st.ctx; sm[7] = st.first_correct;
     if (st.error) policy_err = st.error;
   }
   if (iters_log) TRYC(cudaMemcpy(iters_log, c.iters_log, (size_t)n_seqs * c.iters_cap * 4, cudaMemcpyDeviceToHost));

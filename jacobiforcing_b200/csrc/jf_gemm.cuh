@@ -135,7 +135,13 @@ __device__ __forceinline__ UnitRange unit_range(const GemmTask& t, int u) {
   r.k1 = (int)(((long long)(r.split + 1) * t.k_chunks) / t.splits);
   return r;
 }
-__device__ __forceinline__ int task_rows_mma(const GemmTask& t) { return t.epilogue == EPI_SWIGLU_BF16 ? 128 : kMaxRowsMMA; }
+// Rows one accumulator use covers.  SwiGLU needs two accumulators (gate, up): up to 128 rows they share one 256-column
+// TMEM buffer (double-buffered across units); 129..256 rows take the whole TMEM (gate in columns [0,256), up in
+// [256,512)) so the weight tiles are still streamed once - at the price of no overlap between units.
+__device__ __forceinline__ bool task_wide_dual(const GemmTask& t) { return t.epilogue == EPI_SWIGLU_BF16 && t.M > 128; }
+__device__ __forceinline__ int task_rows_mma(const GemmTask& t) {
+  return t.epilogue == EPI_SWIGLU_BF16 ? (t.M > 128 ? 256 : 128) : kMaxRowsMMA;
+}
 
 // ---- warp 0, lane 0 ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gemm_produce_w(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
@@ -217,6 +223,7 @@ __device__ __forceinline__ void gemm_produce_x(const GemmTask& t, GemmSmem* gs, 
 __device__ __forceinline__ void gemm_issue_mma(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
                                                int slot_bytes, int cta, int nctas, PipeState& pipe, AccState& acc) {
   const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
+  const bool wide = task_wide_dual(t);
   const int units = t.n_tiles * t.splits;
   const int rows_mma = task_rows_mma(t);
   const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
@@ -228,8 +235,11 @@ __device__ __forceinline__ void gemm_issue_mma(const GemmTask& t, GemmSmem* gs, 
       const int mpad = round_up16(min(t.M - m0, rows_mma));
       const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)mpad);
       mbar_wait(&gs->acc_empty[acc.buf], acc.phase ^ 1);
+      AccState acc2 = acc;
+      if (wide) { acc2.advance(); mbar_wait(&gs->acc_empty[acc2.buf], acc2.phase ^ 1); }   // both buffers must be free
       tc_fence_after();
-      const uint32_t d0 = tmem + acc.buf * 256u;     // buffer b = columns [b*256, b*256+256); dual: gate | up halves
+      const uint32_t d0 = wide ? tmem : tmem + acc.buf * 256u;   // buffer b = columns [b*256, b*256+256); dual: gate | up
+      const uint32_t up_off = wide ? 256u : 128u;
       for (int k = r.k0; k < r.k1; ++k) {
         mbar_wait(&gs->full[pipe.stage], pipe.phase());
         const uint32_t sa = smem_u32(tiles + (size_t)pipe.stage * slot_bytes);
@@ -250,13 +260,14 @@ __device__ __forceinline__ void gemm_issue_mma(const GemmTask& t, GemmSmem* gs, 
         for (int kk = 0; kk < 4; ++kk) {   // 4 x UMMA_K(16) = one 64-wide k-chunk; +32 B inside the swizzle atom
           const uint64_t db = umma_desc_sw128(xbase + kk * 32);
           umma_bf16(d0, umma_desc_sw128(sa + kk * 32), db, idesc, (accum0 | (kk > 0)) ? 1u : 0u);
-          if (dual) umma_bf16(d0 + 128u, umma_desc_sw128(sb + kk * 32), db, idesc, (accum0 | (kk > 0)) ? 1u : 0u);
+          if (dual) umma_bf16(d0 + up_off, umma_desc_sw128(sb + kk * 32), db, idesc, (accum0 | (kk > 0)) ? 1u : 0u);
         }
         umma_commit(empty_a);               // frees the slot(s) when these MMAs retire
         if (dual) umma_commit(empty_b);
       }
       umma_commit(&gs->acc_full[acc.buf]);
       acc.advance();
+      if (wide) { umma_commit(&gs->acc_full[acc.buf]); acc.advance(); }
     }
   }
 }
@@ -268,6 +279,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
   const int q = warp & 3;                       // TMEM lane quarter this warp may access (warp id % 4)
   const int feat_in_tile = q * 32 + lane;
   const int units = t.n_tiles * t.splits;
+  const bool wide = task_wide_dual(t);
   const int rows_mma = task_rows_mma(t);
   const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
   if (t.epilogue == EPI_ARGMAX) {
@@ -282,8 +294,11 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
       const int mlive = min(t.M - m0, rows_mma);
       const int mpad = round_up16(mlive);
       mbar_wait(&gs->acc_full[acc.buf], acc.phase);
+      AccState acc2 = acc;
+      if (wide) { acc2.advance(); mbar_wait(&gs->acc_full[acc2.buf], acc2.phase); }
       tc_fence_after();
-      const uint32_t taddr = gs->tmem_base + acc.buf * 256u + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = gs->tmem_base + (wide ? 0u : acc.buf * 256u) + ((uint32_t)(q * 32) << 16);
+      const uint32_t up_off = wide ? 256u : 128u;
       if (t.epilogue == EPI_PARTIAL_F32) {
         float* out = reinterpret_cast<float*>(t.out) + (size_t)r.split * t.out_split_stride;
         const bool nvalid = n < t.N;
@@ -307,7 +322,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
         for (int c0 = 0; c0 < mpad; c0 += 16) {
           uint32_t g[16], up[16];
           tmem_ld16(taddr + c0, g);
-          tmem_ld16(taddr + 128u + c0, up);
+          tmem_ld16(taddr + up_off + c0, up);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -348,6 +363,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
       tc_fence_before();
       mbar_arrive(&gs->acc_empty[acc.buf]);
       acc.advance();
+      if (wide) { mbar_arrive(&gs->acc_empty[acc.buf]); acc.advance(); }
     }
   }
   if (t.epilogue == EPI_ARGMAX) {

@@ -182,7 +182,7 @@ class ModelRunner:
             seq.extend_tokens(res.tokens)
             seq.num_cached_tokens = len(seq)                                  # invariant at jacobi_decoding.py:404-407
             seq._kv_ctx = res.ctx
-            seq._first_correct = seq.token_ids[-1]
+            seq._first_correct = res.next_token
             out.append(list(res.tokens))
             st["num_chunk_calls"] += 1
             st["num_jacobi_iterations"] += res.total_iterations

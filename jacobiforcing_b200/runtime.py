@@ -47,6 +47,7 @@ class JacobiResult:
     total_iterations: int
     iters: List[int]
     ctx: int
+    next_token: int = -1          # first_correct_token a following call starts from (HF convention)
 
 
 class JacobiRuntime:
@@ -319,12 +320,12 @@ class JacobiRuntime:
         _cabi.check(rc, self.h)
         results = []
         for i, s in enumerate(seqs):
-            ngen, calls, stop, total_new, _err, total_iters, ctx, _ = [int(x) for x in summ[i]]
+            ngen, calls, stop, total_new, _err, total_iters, ctx, nxt = [int(x) for x in summ[i]]
             toks = out[i, :ngen].tolist()
             s.tokens = s.tokens + toks
             s.ctx = ctx
             results.append(JacobiResult(toks, calls, STOP_REASONS.get(stop, str(stop)), total_new, total_iters,
-                                        iters[i, :calls].tolist(), ctx))
+                                        iters[i, :calls].tolist(), ctx, nxt))
         self.stats["forwards"] += int(stats[0])
         self.stats["device_ms"] += float(stats[1])
         self.stats["rows"] += int(stats[2])

@@ -141,3 +141,26 @@ def test_engine_policy_device_loop_bit_exact(L, max_tokens, max_iters):
     assert res[0].total_iterations == iters == run["forwards"]
     assert res[0].stop_reason == ("max_iterations" if iters >= max_iters and len(acc) < max_tokens else "max_new_tokens")
     rt.close()
+
+
+def test_streaming_and_profile_drivers():
+    """Block-by-block streaming (applications/jacobi_streaming_driver.py) and the CSV profile rows
+    (MR_humaneval.py:259-273) produce the same ids as the one-launch generation."""
+    from jacobiforcing_b200.drivers import CSV_COLUMNS, jacobi_stream, profile_rows
+    from jacobiforcing_b200.runtime import hf_generate
+    from tests.gpu_helpers import make_pair
+    model, rt = make_pair("tiny")
+    g = torch.Generator().manual_seed(21)
+    prompt = torch.randint(0, model.config.vocab_size, (20,), generator=g).tolist()
+    seqs, res, _ = hf_generate(rt, [prompt], n=8, max_new_tokens=40, mode="multiblock", K=2, r=0.8, pad=0,
+                               rngs=[random.Random(0)])
+    for s in seqs:
+        rt.release(s)
+    blocks = list(jacobi_stream(rt, prompt, n=8, max_new_tokens=40, K=2, r=0.8, pad=0, rng=random.Random(0)))
+    assert all(len(b) == 8 for b in blocks) and len(blocks) == 5
+    assert [t for b in blocks for t in b] == res[0].tokens[:40]
+    rows = profile_rows(rt, [prompt], n=8, max_new_tokens=40, K=2, r=0.8, pad=0, seed=0)
+    assert set(CSV_COLUMNS) <= set(rows[0])
+    assert rows[0]["token_ids"][:40] == res[0].tokens[:40]
+    assert rows[0]["calls"] == res[0].calls and rows[0]["total_iterations"] == res[0].total_iterations
+    rt.close()

@@ -35,10 +35,11 @@ def _prompt(model, P, seed=1):
     return torch.randint(0, model.config.vocab_size, (P,), generator=g).tolist()
 
 
-def test_forward_logits_within_tolerance(pair):
+@pytest.mark.parametrize("rows", [72, 200, 256])      # 200 / 256 rows: the wide (whole-TMEM) SwiGLU accumulator mode
+def test_forward_logits_within_tolerance(pair, rows):
     from oracle.hf_model import teacher_forced_logits
     name, model, rt = pair
-    ids = _prompt(model, 72)
+    ids = _prompt(model, rows)
     seq = rt.new_sequence()
     rt.ensure_capacity(seq, len(ids))
     res = rt.forward(ids, [(0, len(ids), 0, 0)], [seq], 0, len(ids), want_logits=True)
