@@ -231,7 +231,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from jacobiforcing_b200.policy import MODES, PolicyKnobs, draw_choice_indices, draw_prefill_draft
+    from jacobiforcing_b200.policy import MODES, PolicyKnobs, draw_prefill_draft, mt_state_words
     from jacobiforcing_b200.runtime import JacobiRuntime
 
     torch.cuda.set_device(local_rank)
@@ -279,14 +279,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             fc, drafted, ms = rt.prefill(s, prompts[b], draw_prefill_draft(rng, prompts[b], n))
             t_pre += ms
             seqs.append(s); fcs.append(fc); fcts.append(drafted)
-            chs.append(draw_choice_indices(rng, P, n, G // n + 5))
+            chs.append(mt_state_words(rng))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        results, run = rt.jacobi_run(seqs, knobs, fcs, fcts, choice_idx=chs)     # host buffers in, host ids out
+        results, run = rt.jacobi_run(seqs, knobs, fcs, fcts, rng_states=chs)     # host buffers in, host ids out
         wall = time.perf_counter() - t0
         toks = sum(len(r.tokens) for r in results)
         iters = run["forwards"]
-        h2d = 4 * (B * P + B * n + B * len(chs[0]) * (n - 1) + B * pages + 3 * B) + 64 * B
+        h2d = 4 * (B * P + B * n + B * 625 + B * pages + 3 * B) + 64 * B
         d2h = 4 * (B * (G + 3 * n + 1) + 8 * B + B * rt.max_calls) + 16
         for s in seqs:
             rt.release(s)

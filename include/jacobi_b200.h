@@ -104,7 +104,9 @@ int jf_commit_rows(jf_handle h, int32_t n_seqs, const int32_t* block_tables, int
  *   prompts (concatenated) / prompt_lens[s]      tokens already committed to the KV cache (ctx_lens[s] of them)
  *   first_correct[s]                              HF: first_correct_token of the prefill; engine: unused
  *   first_call_tokens[s][n]                       HF: prefill_drafted_n_gram; engine: the prefill draft (n-1 used)
- *   choice_idx[s][choice_rows][n-1]               HF: per-call indices into [prompt|generated] (random.choice), rows >= 2
+ *   rng_state[s][rng_words]                       HF: state of the random.Random (MT19937: 624 words + index = 625)
+ *                                                 whose random.choice(generated_ids) calls seed every later call's
+ *                                                 draft; the device continues that exact stream
  *   pad_stream[s][pad_stream_len]                 engine: the random padding tokens, consumed in order
  *   block_tables[s][max_pages_per_seq]
  * Outputs: out_tokens[s][out_capacity] generated ids, out_summary[s][8] = {n_generated, calls, stop_reason,
@@ -113,7 +115,7 @@ int jf_commit_rows(jf_handle h, int32_t n_seqs, const int32_t* block_tables, int
  * with trace_len words used: {iter, seq, ctx, B, L, B*L tokens}*. */
 int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs* knobs, const int32_t* prompts,
                   const int32_t* prompt_lens, const int32_t* ctx_lens, const int32_t* first_correct,
-                  const int32_t* first_call_tokens, const int32_t* choice_idx, int32_t choice_rows,
+                  const int32_t* first_call_tokens, const uint32_t* rng_state, int32_t rng_words,
                   const int32_t* pad_stream, int32_t pad_stream_len, const int32_t* block_tables,
                   int32_t max_forwards, int32_t* out_tokens, int32_t out_capacity, int32_t* out_summary,
                   int32_t* iters_log, float* run_stats, int32_t* trace, int32_t* trace_len);

@@ -750,7 +750,7 @@ extern "C" int jf_commit_rows(jf_handle h, int32_t n_seqs, const int32_t* block_
 
 extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs* knobs, const int32_t* prompts,
                              const int32_t* prompt_lens, const int32_t* ctx_lens, const int32_t* first_correct,
-                             const int32_t* first_call_tokens, const int32_t* choice_idx, int32_t choice_rows,
+                             const int32_t* first_call_tokens, const uint32_t* rng_state, int32_t rng_words,
                              const int32_t* pad_stream, int32_t pad_stream_len, const int32_t* block_tables,
                              int32_t max_forwards, int32_t* out_tokens, int32_t out_capacity, int32_t* out_summary,
                              int32_t* iters_log, float* run_stats, int32_t* trace, int32_t* trace_len) {
@@ -770,7 +770,7 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
   if (kn.max_calls > c.iters_cap) kn.max_calls = c.iters_cap;
   kn.vocab = h->md.vocab;
   const int n = kn.n;
-  const int cr = choice_idx ? choice_rows : 0;
+  const int cr = (rng_state && rng_words >= 625) ? rng_words : 0;
   // device copies of the draft sources
   int *d_first = nullptr, *d_choice = nullptr, *d_pad = nullptr;
   std::vector<void*> tmp_allocs;
@@ -790,9 +790,9 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
     TRY(tmp_alloc(&d_first, (size_t)n_seqs * n));
     TRYC(cudaMemcpyAsync(d_first, first_call_tokens, (size_t)n_seqs * n * 4, cudaMemcpyHostToDevice, h->stream));
   }
-  if (cr > 0 && n > 1) {
-    TRY(tmp_alloc(&d_choice, (size_t)n_seqs * cr * (n - 1)));
-    TRYC(cudaMemcpyAsync(d_choice, choice_idx, (size_t)n_seqs * cr * (n - 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (cr > 0) {
+    TRY(tmp_alloc(&d_choice, (size_t)n_seqs * cr));
+    TRYC(cudaMemcpyAsync(d_choice, rng_state, (size_t)n_seqs * cr * 4, cudaMemcpyHostToDevice, h->stream));
   }
   if (pad_stream && pad_stream_len > 0) {
     TRY(tmp_alloc(&d_pad, (size_t)n_seqs * pad_stream_len));
@@ -815,8 +815,8 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
     memset(&st, 0, offsetof(SeqState, ret));
     seq_state_init(st, pl, ctx_lens[s], first_correct ? first_correct[s] : 0);
     hs[s].first_call_tokens = d_first ? d_first + (size_t)s * n : nullptr;
-    hs[s].choice_idx = d_choice ? d_choice + (size_t)s * cr * (n - 1) : nullptr;
-    hs[s].choice_rows = d_choice ? cr : 0;
+    hs[s].mt = d_choice ? reinterpret_cast<unsigned int*>(d_choice) + (size_t)s * cr : nullptr;
+    hs[s].mt_words = d_choice ? cr : 0;
     hs[s].pad_stream = d_pad ? d_pad + (size_t)s * pad_stream_len : nullptr;
     hs[s].pad_stream_len = d_pad ? pad_stream_len : 0;
   }

@@ -30,7 +30,7 @@ constexpr int kOutColsMax   = kBlocksMax * kNMax;
 
 enum PolicyMode : int { MODE_HF_SINGLE = 0, MODE_HF_MULTI = 1, MODE_ENGINE = 2 };
 enum StopReason : int { STOP_NONE = 0, STOP_EOS = 1, STOP_MAX_NEW = 2, STOP_MAX_CALLS = 3, STOP_MAX_ITERS = 4,
-                        STOP_ERROR = 5, STOP_SHORT_CALL = 6 };
+                        STOP_ERROR = 5 };
 enum PolicyError : int { PERR_NONE = 0, PERR_BROADCAST = 1, PERR_NO_PAD = 2, PERR_BLOCKS = 3, PERR_PROMOTE_LEN = 4,
                          PERR_CAPACITY = 5, PERR_DRAFT_SOURCE = 6 };
 
@@ -96,15 +96,43 @@ struct SeqState {
   MBlock blk[kBlocksMax];
 };
 
-// Where a call's first draft comes from: explicit tokens (call 1 = prefill_drafted_n_gram), then per call n-1 indices
-// into the generated buffer (random.choice(generated_ids), precomputed by the host from an explicit seed).
+// Where a call's first draft comes from: explicit tokens for the first call (prefill_drafted_n_gram), then
+// random.choice(generated_ids) for the n-1 guesses of every later call (MR_humaneval.py:209-215).  The reference uses
+// Python's `random` (MT19937); the host hands over the generator's state (random.Random.getstate()[1]: 624 words + index)
+// and the device continues the very same stream, so drafts are reproducible whatever number of tokens a call returns.
 struct DraftSource {
   const int* first_call_tokens;   // [n]
-  const int* choice_idx;          // [max_calls][n-1], row c used by call c (c >= 2); may be null when max_calls <= 2
-  int choice_rows;
+  unsigned int* mt;               // [625] MT19937 state + index, advanced in place; null when only one call can happen
+  int mt_words;
   const int* pad_stream;          // engine mode: torch.randint stand-in, consumed in order
   int pad_stream_len;
 };
+
+JF_HD inline unsigned int mt_u32(unsigned int* mt) {                    // CPython _randommodule.c genrand_uint32
+  unsigned int idx = mt[624];
+  if (idx >= 624) {
+    for (int k = 0; k < 624; ++k) {
+      const unsigned int y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+      mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    idx = 0;
+  }
+  unsigned int y = mt[idx];
+  mt[624] = idx + 1;
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+// random.Random._randbelow_with_getrandbits(n) for 1 <= n < 2^32: k = n.bit_length(); r = getrandbits(k) until r < n
+JF_HD inline int mt_randbelow(unsigned int* mt, int n) {
+  int k = 0;
+  for (unsigned int v = (unsigned int)n; v; v >>= 1) ++k;
+  unsigned int r = mt_u32(mt) >> (32 - k);
+  while (r >= (unsigned int)n) r = mt_u32(mt) >> (32 - k);
+  return (int)r;
+}
 
 JF_HD inline int leading_matches(const int* draft_tail, const int* greedy_head, int count) {
   int k = 0;
@@ -514,12 +542,7 @@ JF_HD inline bool hf_advance(SeqState& s, const PolicyKnobs& kn, const DraftSour
         ended = multi ? mb_pre_forward(s, kn) : sb_pre_forward(s, kn);
         if (!ended) { s.commit_row = saved_commit_row; s.commit_n = saved_commit_n; return true; }
       }
-      const int expected = kn.n;
-      const int got = s.ret_n;
       driver_finish_call(s, kn, gen, gen_cap, iters_log, iters_cap);
-      if (!s.finished && got != expected && !s.eos_seen) {        // precomputed choice indices assume n tokens / call
-        s.finished = 1; s.stop_reason = STOP_SHORT_CALL;
-      }
       continue;
     }
     // ---- loop head of the driver (:152-170)
@@ -530,17 +553,11 @@ JF_HD inline bool hf_advance(SeqState& s, const PolicyKnobs& kn, const DraftSour
     if (s.calls == 1) {                                             // :206-208
       for (int j = 0; j < kn.n; ++j) input_ids[j] = src.first_call_tokens[j];
     } else {                                                        // :209-215
-      if (kn.n > 1 && (src.choice_idx == nullptr || s.calls >= src.choice_rows)) {
+      if (kn.n > 1 && (src.mt == nullptr || src.mt_words < 625)) {
         s.error = PERR_DRAFT_SOURCE; s.finished = 1; s.stop_reason = STOP_ERROR; break;
       }
       input_ids[0] = s.first_correct;
-      const int* idx = src.choice_idx + (size_t)s.calls * (kn.n - 1);
-      for (int j = 0; j < kn.n - 1; ++j) {
-        int ix = idx[j];
-        if (ix < 0) ix = 0;
-        if (ix >= s.gen_len) ix = s.gen_len - 1;
-        input_ids[1 + j] = gen[ix];
-      }
+      for (int j = 0; j < kn.n - 1; ++j) input_ids[1 + j] = gen[mt_randbelow(src.mt, s.gen_len)];
     }
     if (multi) mb_begin_call(s, kn, input_ids); else sb_begin_call(s, kn, input_ids);
   }

@@ -14,7 +14,7 @@ import random
 import time
 from typing import Callable, Dict, Iterator, List, Optional, Sequence
 
-from .policy import MODES, PolicyKnobs, draw_choice_indices, draw_prefill_draft
+from .policy import MODES, PolicyKnobs, draw_prefill_draft
 from .runtime import JacobiRuntime, hf_generate
 
 CSV_COLUMNS = ["index", "task_id", "prompt_tokens", "new_tokens", "calls", "total_iterations", "avg_iter_per_call",

@@ -12,7 +12,7 @@ import random
 from typing import Dict, List, Optional
 
 from ..config import Config
-from ..policy import MODES, PolicyKnobs, draw_choice_indices
+from ..policy import MODES, PolicyKnobs, mt_state_words
 from ..runtime import PAGE, JacobiRuntime, SeqHandle
 from .sequence import Sequence
 
@@ -169,9 +169,9 @@ class ModelRunner:
                 else:                                                         # resumed: [first_correct, random...]
                     fcs.append(int(seq._first_correct))
                     fcts.append([int(seq._first_correct)] + [self._rng.choice(seq.token_ids) for _ in range(L - 1)])
-                chs.append(draw_choice_indices(self._rng, S, L, knobs.max_calls + 1))
+                chs.append(mt_state_words(random.Random(self._rng.getrandbits(64))))
             seq._prefill_draft = None
-        results, run = self.rt.jacobi_run(handles, knobs, fcs, fcts, choice_idx=(chs or None),
+        results, run = self.rt.jacobi_run(handles, knobs, fcs, fcts, rng_states=(chs or None),
                                           pad_stream=(pads or None), want_trace=True)
         out = []
         st = self.jacobi_decoder.stats

@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 MODE_HF_SINGLE, MODE_HF_MULTI, MODE_ENGINE = 0, 1, 2
 MODES = {"single": MODE_HF_SINGLE, "multiblock": MODE_HF_MULTI, "engine": MODE_ENGINE}
 STOP_REASONS = {0: "", 1: "eos", 2: "max_new_tokens", 3: "max_calls", 4: "max_iterations", 5: "error",
-                6: "short_call"}
+                }
 POLICY_ERRORS = {0: "", 1: "reference would fail to broadcast draft rows against greedy rows",
                  2: "pad_token_id must be provided when spawning pseudo-active blocks.",
                  3: "block list capacity exceeded (K >= 3 bookkeeping drift is not supported on device)",
@@ -59,15 +59,13 @@ class PolicyKnobs:
                 self.max_iteration_count, self.max_new_tokens, self.max_calls, lsr_min, self.vocab]
 
 
-def draw_choice_indices(rng, prompt_len: int, n: int, max_calls: int) -> List[List[int]]:
-    """Row c = the n-1 indices random.choice(generated_ids) would pick at call c (c >= 2), valid while every call
-    returns exactly n tokens (always true for K <= 2 without EOS; with EOS the run ends at the short call).
-    `rng.choice(range(m))` consumes the RNG exactly like `rng.choice(list_of_len_m)`."""
-    rows = [[0] * (n - 1), [0] * (n - 1)]
-    for c in range(2, max_calls):
-        m = prompt_len + (c - 1) * n
-        rows.append([rng.choice(range(m)) for _ in range(n - 1)])
-    return rows
+def mt_state_words(rng) -> List[int]:
+    """The 625 words (624 of MT19937 state + position) of a random.Random: handed to the device, which continues the
+    generator exactly where the host left it (csrc/jf_policy.h mt_randbelow == random.Random._randbelow)."""
+    version, internal, _gauss = rng.getstate()
+    if version != 3 or len(internal) != 625:
+        raise ValueError("unsupported random.Random state layout")
+    return [int(x) for x in internal]
 
 
 def draw_prefill_draft(rng, prompt: Sequence[int], n: int) -> List[int]:

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _cabi
-from .policy import MODES, POLICY_ERRORS, STOP_REASONS, PolicyKnobs, draw_choice_indices, draw_prefill_draft
+from .policy import MODES, POLICY_ERRORS, STOP_REASONS, PolicyKnobs, draw_prefill_draft, mt_state_words
 from .tp import check_divisibility, shard_tensor
 
 PAGE = 256
@@ -280,7 +280,7 @@ class JacobiRuntime:
 
     # ---- the device-resident Jacobi loop -----------------------------------------------------------------------------
     def jacobi_run(self, seqs: Sequence[SeqHandle], knobs: PolicyKnobs, first_correct: Sequence[int],
-                   first_call_tokens: Optional[Sequence[Sequence[int]]], choice_idx=None, pad_stream=None,
+                   first_call_tokens: Optional[Sequence[Sequence[int]]], rng_states=None, pad_stream=None,
                    max_forwards: int = 0, want_trace: bool = False):
         knobs.validate()
         B = len(seqs)
@@ -296,9 +296,9 @@ class JacobiRuntime:
         fc = _i32(first_correct) if first_correct is not None else None
         fct = _i32(first_call_tokens).reshape(B, n) if first_call_tokens is not None else None
         ch, ch_rows = None, 0
-        if choice_idx is not None and n > 1:
-            ch = _i32(choice_idx).reshape(B, -1, n - 1)
-            ch_rows = ch.shape[1]
+        if rng_states is not None:                       # [B][625] MT19937 words (mt_state_words)
+            ch = np.ascontiguousarray(np.asarray(rng_states, dtype=np.uint32)).reshape(B, 625)
+            ch_rows = 625
         pad, pad_len = None, 0
         if pad_stream is not None:
             pad = _i32(pad_stream).reshape(B, -1)
@@ -357,7 +357,6 @@ def hf_generate(rt: JacobiRuntime, prompts: Sequence[Sequence[int]], *, n: int, 
     B = len(prompts)
     rngs = rngs or [random.Random(2 + i) for i in range(B)]
     seqs, fcs, fcts, chs = [], [], [], []
-    n_calls = min(max_calls, (max_new_tokens + n - 1) // n + 2)
     prefill_ms = 0.0
     for p, rng in zip(prompts, rngs):
         s = rt.new_sequence()
@@ -365,10 +364,10 @@ def hf_generate(rt: JacobiRuntime, prompts: Sequence[Sequence[int]], *, n: int, 
         fc, drafted, ms = rt.prefill(s, p, draft)
         prefill_ms += ms
         seqs.append(s); fcs.append(fc); fcts.append(drafted)
-        chs.append(draw_choice_indices(rng, len(p), n, n_calls + 1))
+        chs.append(mt_state_words(rng))      # the device continues this generator for the later calls' drafts
     knobs = PolicyKnobs(mode=MODES[mode], n=n, K=K, r=r, lookahead_start_ratio=lookahead_start_ratio,
                         n_gram_pool_size=n_gram_pool_size, eos=eos, pad=pad, max_iteration_count=max_iteration_count,
                         max_new_tokens=max_new_tokens, max_calls=min(max_calls, rt.max_calls), vocab=rt.vocab)
-    results, run = rt.jacobi_run(seqs, knobs, fcs, fcts, choice_idx=chs, want_trace=want_trace)
+    results, run = rt.jacobi_run(seqs, knobs, fcs, fcts, rng_states=chs, want_trace=want_trace)
     run["prefill_ms"] = prefill_ms
     return seqs, results, run

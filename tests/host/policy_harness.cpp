@@ -14,7 +14,7 @@ extern "C" {
 // Returns 0 on success, otherwise 100 + index of the first forward whose (kv, rows) differ from the table,
 // or 1 when the policy asks for more forwards than recorded.
 int jf_policy_replay(const int* knobs_i /*12 ints in PolicyKnobs order*/, const int* prompt, int prompt_len, int ctx0,
-                     int first_correct, const int* first_call_tokens, const int* choice_idx, int choice_rows,
+                     int first_correct, const int* first_call_tokens, unsigned int* mt_state, int mt_words,
                      const int* pad_stream, int pad_stream_len, int nfw, const int* kv_before, const int* fB,
                      const int* fL, const long long* rows_off, const int* rows_flat, const int* greedy_flat,
                      int* gen_out, int gen_cap, int* iters_log, int iters_cap, int* result /*[8]*/) {
@@ -23,7 +23,7 @@ int jf_policy_replay(const int* knobs_i /*12 ints in PolicyKnobs order*/, const 
   SeqState* s = (SeqState*)std::calloc(1, sizeof(SeqState));
   seq_state_init(*s, prompt_len, ctx0, first_correct);
   for (int i = 0; i < prompt_len && i < gen_cap; ++i) gen_out[i] = prompt[i];
-  DraftSource src{first_call_tokens, choice_idx, choice_rows, pad_stream, pad_stream_len};
+  DraftSource src{first_call_tokens, mt_state, mt_words, pad_stream, pad_stream_len};
   int f = 0, rc = 0;
   const int* greedy = nullptr;
   int gstride = 0;

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from jacobiforcing_b200.policy import MODES, PolicyKnobs, STOP_REASONS, draw_choice_indices
+from jacobiforcing_b200.policy import MODES, PolicyKnobs, STOP_REASONS, mt_state_words
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.json")))
@@ -47,7 +47,7 @@ def replay(g, lib):
     _ = [rng.choice(prompt) for _ in range(g["n"])]              # the prefill draft draws come first
     prefill = g["call_log"][0]
     n_calls = g["calls"] + 2
-    choice = draw_choice_indices(rng, len(prompt), g["n"], n_calls)
+    mt = _arr(mt_state_words(rng), np.uint32)
     fws = g["forwards"][1:]                                      # forward 0 is the prefill
     kv = _arr([f["kv_before"] for f in fws]); fB = _arr([len(f["rows"]) for f in fws])
     fL = _arr([len(f["rows"][0]) for f in fws])
@@ -60,9 +60,9 @@ def replay(g, lib):
     offs = _arr(offs, np.int64); rows = _arr(rows); greedy = _arr(greedy)
     gen_cap = len(prompt) + g["max_new_tokens"] + 4 * g["n"]
     gen = np.zeros(gen_cap, np.int32); iters = np.zeros(n_calls + 4, np.int32); res = np.zeros(8, np.int32)
-    knobs = _arr(kn.as_ints()); pr = _arr(prompt); fct = _arr(prefill["prefill_drafted"]); ch = _arr(choice)
+    knobs = _arr(kn.as_ints()); pr = _arr(prompt); fct = _arr(prefill["prefill_drafted"])
     rc = lib.jf_policy_replay(_p(knobs), _p(pr), len(prompt), prefill["kv_after"], prefill["first_correct"], _p(fct),
-                              _p(ch), len(choice), None, 0, len(fws), _p(kv), _p(fB), _p(fL), _p(offs), _p(rows),
+                              _p(mt), 625, None, 0, len(fws), _p(kv), _p(fB), _p(fL), _p(offs), _p(rows),
                               _p(greedy), _p(gen), gen_cap, _p(iters), len(iters), _p(res))
     return rc, gen, iters, res, len(fws)
 
