@@ -30,6 +30,7 @@ struct jf_engine {
   DevCtx hctx{};
   DevCtx* dctx = nullptr;
   std::vector<void*> allocs;
+  std::vector<void*> ipc_maps;       // peer arenas opened with cudaIpcOpenMemHandle
   std::string err;
   int64_t bytes_weights = 0, bytes_kv = 0, bytes_act = 0;
   // arenas: one cudaMalloc per class (weights / KV cache / activations+state) so each class sits in few, densely
@@ -340,6 +341,7 @@ extern "C" int jf_destroy(jf_handle h) {
   if (!h) return JF_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  for (void* p : h->ipc_maps) cudaIpcCloseMemHandle(p);
   for (void* p : h->allocs) cudaFree(p);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
@@ -381,6 +383,7 @@ extern "C" int jf_tp_import(jf_handle h, const void* handles) {
       memcpy(&ipc, reinterpret_cast<const uint8_t*>(handles) + (size_t)r * 64, 64);
       void* p = nullptr;
       JF_CUDA(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->ipc_maps.push_back(p);
       base = reinterpret_cast<uint8_t*>(p);
     }
     // every rank lays its arena out identically, so a peer's buffer sits at the same offset
