@@ -278,6 +278,10 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   {
     const char* e1 = getenv("JF_DEBUG_SKIP");
     c.debug_skip = e1 ? atoi(e1) : 0;
+    const char* e3 = getenv("JF_ATTN_PREFETCH");
+    c.attn_prefetch = e3 ? atoi(e3) : 1;
+    const char* e4 = getenv("JF_W_EVICT_FIRST");
+    c.w_evict_first = e4 ? atoi(e4) : 1;
     const char* e2 = getenv("JF_PREFETCH_TILES");
     c.prefetch_tiles = e2 ? atoi(e2) : 0;   // measured: no gain from L2 prefetch on B200 (profiles/r01_stage_experiments.txt)
   }

@@ -145,26 +145,29 @@ __device__ __forceinline__ int task_rows_mma(const GemmTask& t) {
 
 // ---- warp 0, lane 0 ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gemm_produce_w(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
-                                               int slot_bytes, int cta, int nctas, PipeState& pipe) {
+                                               int slot_bytes, int cta, int nctas, PipeState& pipe, bool hint,
+                                               uint64_t policy) {
   const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
   const int units = t.n_tiles * t.splits;
   const int rows_mma = task_rows_mma(t);
   const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
+  auto copy_w = [&](void* dst, const void* src, uint64_t* bar) {
+    if (hint) bulk_g2s_hint(dst, src, kWTileBytes, bar, policy); else bulk_g2s(dst, src, kWTileBytes, bar);
+  };
   for (int u = cta; u < units; u += nctas) {
     const UnitRange r = unit_range(t, u);
     for (int mt = 0; mt < m_tiles; ++mt) {
       for (int k = r.k0; k < r.k1; ++k) {
         mbar_wait(&gs->empty[pipe.stage], pipe.phase() ^ 1);
         mbar_expect_tx(&gs->full[pipe.stage], kWTileBytes);
-        bulk_g2s(tiles + (size_t)pipe.stage * slot_bytes,
-                 t.W + ((size_t)r.n_tile * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes, &gs->full[pipe.stage]);
+        copy_w(tiles + (size_t)pipe.stage * slot_bytes,
+               t.W + ((size_t)r.n_tile * t.k_chunks + k) * (kTileN * kTileK), &gs->full[pipe.stage]);
         pipe.advance(nstages);
         if (dual) {
           mbar_wait(&gs->empty[pipe.stage], pipe.phase() ^ 1);
           mbar_expect_tx(&gs->full[pipe.stage], kWTileBytes);
-          bulk_g2s(tiles + (size_t)pipe.stage * slot_bytes,
-                   t.W + ((size_t)(r.n_tile + t.n_tiles) * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes,
-                   &gs->full[pipe.stage]);
+          copy_w(tiles + (size_t)pipe.stage * slot_bytes,
+                 t.W + ((size_t)(r.n_tile + t.n_tiles) * t.k_chunks + k) * (kTileN * kTileK), &gs->full[pipe.stage]);
           pipe.advance(nstages);
         }
       }

@@ -248,12 +248,13 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   int nstages = 1, slot_bytes = 0;
   int prof_n = 0;
   int* prof_slot = nullptr;
+  const uint64_t w_policy = (ROLE == ROLE_W) ? l2_policy_evict_first() : 0ull;
 
   auto skip_barrier = [&](bool xgpu) { bs.epoch += 1; if (xgpu) bs.xcount += 1; };
   auto gemm_stage = [&](const GemmTask& t, bool barrier_after, const GemmTask* next = nullptr, bool xgpu = false) {
     if (ROLE == ROLE_W) {
       if (c.debug_skip & 16) wait_epoch(c.bar_counter, bs.target(nctas));   // experiment: no run-ahead
-      gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
+      gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, c.w_evict_first != 0, w_policy);
       if (next != nullptr) gemm_prefetch_l2(*next, cta, nctas, c.prefetch_tiles);
     } else if (ROLE == ROLE_X) {
       wait_epoch(c.bar_counter, bs.target(nctas));
@@ -356,6 +357,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     for (int l = 0; l < md.layers; ++l) {
       const LayerW& lw = c.layer[l];
       const GemmTask tq = task_qkv(l), to = task_o(l), tg = task_gu(l), td = task_down(l);
+      if (ROLE == ROLE_WORKER) attention_prefetch(c, w, l, ip.G, ip.attn_units);
       gemm_stage(tq, true, &to);
       JF_SIMT_STAGE_X(false, if (!(c.debug_skip & 1)) stage_qkv_rope(c, w, T, l));
       JF_SIMT_STAGE_X(false, if (!(c.debug_skip & 2)) stage_attention(c, w, l, ip.G, ip.attn_units));

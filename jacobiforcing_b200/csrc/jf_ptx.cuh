@@ -74,6 +74,25 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// The same copy with an L2 eviction-priority hint.  The weight stream (15 GB per forward on a 126 MB L2) is marked
+// evict_first so that it does not push out what IS reused between stages and forwards: the kernel's own code (instruction
+// fetches are served by L2), the activations / split-K partials, and the paged KV cache.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
 // L2 prefetch of a contiguous global range (no shared-memory destination, no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");

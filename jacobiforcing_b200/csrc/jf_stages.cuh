@@ -301,7 +301,7 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
 // ---------------------------------------------------------------------------------------------------------------
 template <int D>
 __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, const Group& grp, int g_kvh, int chunk,
-                               int qs, int hs) {
+                               int qs, int hs, bool prefetched) {
   constexpr int LDS = D + 8;                  // padded smem row (bf16 elements) -> conflict-free fragment loads
   constexpr int VPR = D / 8;                  // 16-byte chunks per row
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem);
@@ -324,9 +324,11 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
   const int r0 = w.lane >> 2, c2 = (w.lane & 3) * 2;
 
   // K/V sub-tile fill: asynchronous 16-byte copies, one page-table lookup per 64-key sub-tile (kPage % kAttnSub == 0)
-  auto fill_issue = [&](int k0) {
+  // skip_committed: the committed keys of this sub-tile are already in flight / in place (attention_prefetch)
+  auto fill_issue = [&](int k0, bool skip_committed) {
+    if (skip_committed && k0 + kAttnSub <= ctx) return;
     const __nv_bfloat16* cbase[2] = {nullptr, nullptr};
-    if (k0 < ctx) {
+    if (k0 < ctx && !skip_committed) {
       const int page = ld_weak(bt + (k0 / kPage));
       cbase[0] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 0, page, g_kvh, k0 % kPage);
       cbase[1] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 1, page, g_kvh, k0 % kPage);
@@ -342,8 +344,10 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
       const int pos = k0 + jr;
       const __nv_bfloat16* src = sbase[kv];
       uint32_t nbytes = 0;
-      if (pos < ctx) { src = cbase[kv] + (size_t)jr * D + v * 8; nbytes = 16; }
-      else if (pos < nkeys) { src = sbase[kv] + (size_t)(pos - ctx) * srow + v * 8; nbytes = 16; }
+      if (pos < ctx) {
+        if (skip_committed) continue;
+        src = cbase[kv] + (size_t)jr * D + v * 8; nbytes = 16;
+      } else if (pos < nkeys) { src = sbase[kv] + (size_t)(pos - ctx) * srow + v * 8; nbytes = 16; }
       cp_async_16((kv ? Vs : Ks) + jr * LDS + v * 8, src, nbytes);
     }
     cp_async_commit();
@@ -352,9 +356,27 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
   if (tiles <= 0) return;
   prof_mark(c, w, 400);
   if (nsub == 1) {                                         // the common case: issue the fill first, overlap it with Q loads
-    workers_sync();                                        // previous readers of Ks / Vs are done
-    fill_issue(key_lo);
+    if (!prefetched) workers_sync();                       // previous readers of Ks / Vs are done
+    fill_issue(key_lo, prefetched);
   }
+  // Q fragments of one tile (head j, 16 tokens): straight from qbuf (written by the rope stage, L2-resident)
+  auto load_q = [&](int tile, uint32_t (&q)[D / 16][4]) {
+    if (tile >= tiles) return;
+    const int j = j_lo + tile / ntt;
+    const int i0 = q0 + (tile % ntt) * 16;
+    if (key_lo > ctx + min(i0 + 15, len - 1)) return;      // inactive tile (no visible key in this chunk)
+    const int head = g_kvh * md.n_rep + j;
+    const __nv_bfloat16* qa = c.qbuf + (size_t)(row0 + min(i0 + r0, len - 1)) * md.q_dim + head * D;
+    const __nv_bfloat16* qb = c.qbuf + (size_t)(row0 + min(i0 + r0 + 8, len - 1)) * md.q_dim + head * D;
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      q[ks][0] = ld_weak(reinterpret_cast<const unsigned int*>(qa + ks * 16 + c2));
+      q[ks][1] = ld_weak(reinterpret_cast<const unsigned int*>(qb + ks * 16 + c2));
+      q[ks][2] = ld_weak(reinterpret_cast<const unsigned int*>(qa + ks * 16 + 8 + c2));
+      q[ks][3] = ld_weak(reinterpret_cast<const unsigned int*>(qb + ks * 16 + 8 + c2));
+    }
+  };
+  uint32_t qnx[D / 16][4];
   for (int tb = 0; tb * 4 < tiles; ++tb) {
     const int tile = tb * 4 + w.wwarp;
     const bool tvalid = tile < tiles;
@@ -367,17 +389,12 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
     const bool tactive = tvalid && (key_lo <= ctx + min(i0 + 15, len - 1));
 
     uint32_t qf[D / 16][4];
-    if (tactive) {
-      const __nv_bfloat16* qa = c.qbuf + (size_t)(row0 + min(ia, len - 1)) * md.q_dim + head * D;
-      const __nv_bfloat16* qb = c.qbuf + (size_t)(row0 + min(ib, len - 1)) * md.q_dim + head * D;
+    if (tb == 0) load_q(tile, qf);
+    else {
 #pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks) {
-        qf[ks][0] = ld_weak(reinterpret_cast<const unsigned int*>(qa + ks * 16 + c2));
-        qf[ks][1] = ld_weak(reinterpret_cast<const unsigned int*>(qb + ks * 16 + c2));
-        qf[ks][2] = ld_weak(reinterpret_cast<const unsigned int*>(qa + ks * 16 + 8 + c2));
-        qf[ks][3] = ld_weak(reinterpret_cast<const unsigned int*>(qb + ks * 16 + 8 + c2));
-      }
+      for (int ks = 0; ks < D / 16; ++ks) { qf[ks][0] = qnx[ks][0]; qf[ks][1] = qnx[ks][1]; qf[ks][2] = qnx[ks][2]; qf[ks][3] = qnx[ks][3]; }
     }
+    if ((tb + 1) * 4 < tiles) load_q(tile + 4, qnx);       // next round's queries are in flight while this round computes
     if (nsub == 1 && tb == 0) {
       cp_async_wait_all();
       workers_sync();
@@ -392,7 +409,7 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
       const int k0 = key_lo + sub * kAttnSub;
       if (nsub > 1) {
         workers_sync();
-        fill_issue(k0);
+        fill_issue(k0, prefetched && sub == 0 && tb == 0);
         cp_async_wait_all();
         workers_sync();
       }
@@ -402,16 +419,20 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
       // K fragments with ldmatrix: matrix m of one x4 = keys nt*8..+7 (rows) x dims (ks2*32 + m*8)..+7, i.e. (b0, b1) of
       // k-steps 2*ks2 and 2*ks2+1 for n-tile nt
       const uint32_t k_lane = ks_addr + (uint32_t)(((w.lane & 7) * LDS + (w.lane >> 3) * 8) * 2);
+      // k-step outer, key tile inner: eight independent accumulator chains in flight (the mma latency, not its
+      // issue rate, bounds a lone warp per scheduler)
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
 #pragma unroll
-        for (int ks2 = 0; ks2 < D / 32; ++ks2) {
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(k_lane + (uint32_t)((nt * 8 * LDS + ks2 * 32) * 2), b0, b1, b2, b3);
-          mma_bf16_16816(s[nt], qf[2 * ks2], b0, b1);
-          mma_bf16_16816(s[nt], qf[2 * ks2 + 1], b2, b3);
-        }
+      for (int ks2 = 0; ks2 < D / 32; ++ks2) {
+        uint32_t kb[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          ldmatrix_x4(k_lane + (uint32_t)((nt * 8 * LDS + ks2 * 32) * 2), kb[nt][0], kb[nt][1], kb[nt][2], kb[nt][3]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(s[nt], qf[2 * ks2], kb[nt][0], kb[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(s[nt], qf[2 * ks2 + 1], kb[nt][2], kb[nt][3]);
       }
       prof_mark(c, w, 402);
       // scale, causal mask, running max
@@ -461,12 +482,14 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
         // transposed on load -> (b0, b1) of dim tiles 2*nd2 and 2*nd2+1 for key step kk
         const uint32_t v_lane = vs_addr + (uint32_t)((((kk * 16 + (w.lane & 7) + ((w.lane >> 3) & 1) * 8) * LDS) +
                                                      (w.lane >> 4) * 8) * 2);
+        uint32_t vb[D / 16][4];
+#pragma unroll
+        for (int nd2 = 0; nd2 < D / 16; ++nd2)
+          ldmatrix_x4_trans(v_lane + (uint32_t)(nd2 * 16 * 2), vb[nd2][0], vb[nd2][1], vb[nd2][2], vb[nd2][3]);
 #pragma unroll
         for (int nd2 = 0; nd2 < D / 16; ++nd2) {
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4_trans(v_lane + (uint32_t)(nd2 * 16 * 2), b0, b1, b2, b3);
-          mma_bf16_16816(o[2 * nd2], pa, b0, b1);
-          mma_bf16_16816(o[2 * nd2 + 1], pa, b2, b3);
+          mma_bf16_16816(o[2 * nd2], pa, vb[nd2][0], vb[nd2][1]);
+          mma_bf16_16816(o[2 * nd2 + 1], pa, vb[nd2][2], vb[nd2][3]);
         }
       }
     }
@@ -504,24 +527,61 @@ __device__ __forceinline__ Group load_group(const DevCtx& c, int g) {
   return grp;
 }
 
-__device__ __noinline__ void stage_attention(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
+struct AttnUnitId { Group grp; int kvh, hs, chunk, qs; };
+__device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, int u, int G) {
+  AttnUnitId id;
   const int hsplit = c.attn_hsplit;
+  int g = 0;
+  id.grp = load_group(c, 0);
+  while (g + 1 < G) {                                   // groups are few; linear scan over unit ranges
+    const int per = c.md.n_kv * id.grp.nchunks * id.grp.qsplit * hsplit;
+    if (u < id.grp.unit0 + per) break;
+    ++g;
+    id.grp = load_group(c, g);
+  }
+  int local = u - id.grp.unit0;
+  id.kvh = local % c.md.n_kv; local /= c.md.n_kv;
+  id.hs = local % hsplit; local /= hsplit;
+  id.chunk = local % id.grp.nchunks;
+  id.qs = local / id.grp.nchunks;
+  return id;
+}
+
+// Issued by the workers at the START of the layer's QKV GEMM stage: the committed K/V rows of the first 64-key
+// sub-tile of the unit this CTA will run in the attention stage do not depend on this layer's projections, so their
+// HBM latency hides behind the QKV GEMM and the rope stage.  attention_unit(prefetched = true) then only adds the
+// in-flight rows.  (The tile buffer is free: the previous attention stage and LM head ended grid barriers ago.)
+__device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
+  if (w.cta >= units || !c.attn_prefetch) return;
+  const AttnUnitId id = decode_attn_unit(c, w.cta, G);
+  const ModelDims& md = c.md;
+  const int D = md.d, LDS = D + 8, VPR = D >> 3;
+  const int ctx = id.grp.ctx;
+  const int k0 = id.chunk * c.attn_chunk;
+  if (k0 >= ctx) return;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem);
+  __nv_bfloat16* Vs = Ks + kAttnSub * LDS;
+  const int page = ld_weak(c.block_tables + (size_t)id.grp.seq * c.max_pages_per_seq + (k0 / kPage));
+  const __nv_bfloat16* cbase[2] = {c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 0, page, id.kvh, k0 % kPage),
+                                   c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 1, page, id.kvh, k0 % kPage)};
+  const int nrow = min(kAttnSub, ctx - k0);
+  for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
+    const int kv = idx / (kAttnSub * VPR);
+    const int rem = idx - kv * (kAttnSub * VPR);
+    const int jr = rem / VPR, v = rem - jr * VPR;
+    if (jr < nrow) cp_async_16((kv ? Vs : Ks) + jr * LDS + v * 8, cbase[kv] + (size_t)jr * D + v * 8, 16);
+  }
+  cp_async_commit();
+}
+
+__device__ __noinline__ void stage_attention(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
   for (int u = w.cta; u < units; u += w.nctas) {
-    int g = 0;
-    Group grp = load_group(c, 0);
-    while (g + 1 < G) {                                   // groups are few; linear scan over unit ranges
-      const int per = c.md.n_kv * grp.nchunks * grp.qsplit * hsplit;
-      if (u < grp.unit0 + per) break;
-      ++g;
-      grp = load_group(c, g);
-    }
-    int local = u - grp.unit0;
-    const int kvh = local % c.md.n_kv; local /= c.md.n_kv;
-    const int hs = local % hsplit; local /= hsplit;
-    const int chunk = local % grp.nchunks;
-    const int qs = local / grp.nchunks;
-    if (c.md.d == 128) attention_unit<128>(c, w, layer, grp, kvh, chunk, qs, hs);
-    else attention_unit<64>(c, w, layer, grp, kvh, chunk, qs, hs);
+    prof_mark(c, w, 398);
+    const AttnUnitId id = decode_attn_unit(c, u, G);
+    const bool pf = c.attn_prefetch && u == w.cta;
+    prof_mark(c, w, 399);
+    if (c.md.d == 128) attention_unit<128>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf);
+    else attention_unit<64>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf);
   }
 }
 
