@@ -265,7 +265,7 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   c.attn_hsplit = md.n_rep >= 4 ? 2 : 1;
   ALLOC(c.argmax_keys, (size_t)2 * c.T_cap, h->bytes_act);
   ALLOC(c.xflag, kMaxTP, h->bytes_act);
-  ALLOC(c.row_ss, (size_t)c.T_cap * 8, h->bytes_act);
+  ALLOC(c.row_ss, (size_t)c.T_cap * kMaxHTiles, h->bytes_act);
   ALLOC(c.hdr, 1, h->bytes_act);
   ALLOC(c.tok, c.T_cap, h->bytes_act);
   ALLOC(c.row_group, c.T_cap, h->bytes_act);
@@ -282,6 +282,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     c.attn_prefetch = e3 ? atoi(e3) : 1;
     const char* e4 = getenv("JF_W_EVICT_FIRST");
     c.w_evict_first = e4 ? atoi(e4) : 1;
+    const char* e5 = getenv("JF_FUSE_NORM");
+    c.fuse_norm = e5 ? atoi(e5) : 1;
     const char* e2 = getenv("JF_PREFETCH_TILES");
     c.prefetch_tiles = e2 ? atoi(e2) : 0;   // measured: no gain from L2 prefetch on B200 (profiles/r01_stage_experiments.txt)
   }
@@ -295,7 +297,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   c.trace_cap = rt.trace_capacity > 0 ? rt.trace_capacity : 0;
   if (c.trace_cap > 0) { ALLOC(c.trace, c.trace_cap, h->bytes_act); } else c.trace = nullptr;
   ALLOC(c.trace_len, 4, h->bytes_act);
-  ALLOC(c.bar_counter, 4, h->bytes_act);
+  ALLOC(c.bar_counter, 4 + 3 * kMaxTilesPerKind, h->bytes_act);
+  c.tile_ctr = c.bar_counter + 4;
   ALLOC(h->dctx, 1, h->bytes_act);
   // large, sparsely touched buffers last: the small hot ones above share the arena's first pages
   c.part_splits = h->max_splits; c.part_n = md.qkv_dim;
@@ -630,7 +633,7 @@ extern "C" int jf_set_rope_tables(jf_handle h, const float* cosv, const float* s
 // launch
 // ---------------------------------------------------------------------------------------------------------------
 static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float* elapsed_ms) {
-  JF_CUDA(h, cudaMemsetAsync(h->hctx.bar_counter, 0, 16, h->stream));
+  JF_CUDA(h, cudaMemsetAsync(h->hctx.bar_counter, 0, (4 + 3 * kMaxTilesPerKind) * sizeof(unsigned int), h->stream));
   h->hctx.launch_id = (h->hctx.launch_id + 1u) & 0xffu;
   h->hctx.xflag_base += (1ull << 32);
   JF_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->dctx) + offsetof(DevCtx, xflag_base), &h->hctx.xflag_base, 8,

@@ -35,7 +35,8 @@ struct BarState {
 };
 
 __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w, BarState& bs,
-                                             int* prof_slot = nullptr, bool tma_consumer = true, bool xgpu = false) {
+                                             int* prof_slot = nullptr, bool tma_consumer = true, bool xgpu = false,
+                                             int stage_id = 0) {
   if (tma_consumer) fence_proxy_async_all();   // only stages whose output a bulk copy (async proxy) will read need it
   workers_sync();
   const unsigned int local_target = (bs.epoch + 1) * (unsigned int)w.nctas + bs.xcount;
@@ -62,10 +63,11 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
       red_release_gpu_add_u32(c.bar_counter, 1u);              // the extra arrival releases this GPU's CTAs
     }
     wait_epoch<false>(c.bar_counter, bs.target(w.nctas));      // critical path: spin, do not sleep
-    if (prof_slot && *prof_slot + 2 <= c.prof_cap) {      // (arrival of CTA 0, release of the barrier)
-      c.prof[*prof_slot] = t_arrive;
-      c.prof[*prof_slot + 1] = clock64();
-      *prof_slot += 2;
+    if (prof_slot && *prof_slot + 3 <= c.prof_cap) {      // (stage id, arrival of CTA 0, release of the barrier)
+      c.prof[*prof_slot] = stage_id;
+      c.prof[*prof_slot + 1] = t_arrive;
+      c.prof[*prof_slot + 2] = clock64();
+      *prof_slot += 3;
     }
     prof_mark(c, w, 901);
   }
@@ -226,6 +228,10 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerCt
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
 enum Role : int { ROLE_W = 0, ROLE_MMA = 1, ROLE_WORKER = 2, ROLE_X = 3 };
+// stage ids recorded with every profiled grid barrier (jacobiforcing_b200/runtime.py maps them to names)
+enum StageId : int { SID_NONE = 0, SID_EMBED = 1, SID_QKV = 2, SID_ROPE = 3, SID_ATTN = 4, SID_COMBINE = 5, SID_O = 6,
+                     SID_O_NORM = 7, SID_GU = 8, SID_DOWN = 9, SID_DOWN_NORM = 10, SID_LM = 11, SID_POLICY = 12,
+                     SID_O_FUSED = 13, SID_DOWN_FUSED = 14, SID_QKV_FUSED = 15 };
 constexpr int kPrefetchTiles = 24;    // 384 KiB per SM, 57 MB chip-wide: well inside the 126 MB L2
 
 struct IterPlan {
@@ -249,9 +255,14 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   int prof_n = 0;
   int* prof_slot = nullptr;
   const uint64_t w_policy = (ROLE == ROLE_W) ? l2_policy_evict_first() : 0ull;
+  unsigned int fuse_seq[3] = {0u, 0u, 0u};     // fused GEMM stages of each kind executed so far in this launch
 
   auto skip_barrier = [&](bool xgpu) { bs.epoch += 1; if (xgpu) bs.xcount += 1; };
-  auto gemm_stage = [&](const GemmTask& t, bool barrier_after, const GemmTask* next = nullptr, bool xgpu = false) {
+  // fuse_kind: 0 = plain GEMM stage; 1 / 2 = O / down projection whose split-K reduce + residual + RMSNorm runs as the
+  // tail of the epilogue: the CTAs of an n-tile's k-splits wait for each other on the tile's arrival counter and then
+  // share its rows (needs one unit per CTA at most: no CTA may owe a second unit while it waits)
+  auto gemm_stage = [&](const GemmTask& t, bool barrier_after, int stage_id, const GemmTask* next = nullptr,
+                        bool xgpu = false, int fuse_kind = 0, const __nv_bfloat16* normw = nullptr) {
     if (ROLE == ROLE_W) {
       if (c.debug_skip & 16) wait_epoch(c.bar_counter, bs.target(nctas));   // experiment: no run-ahead
       gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, c.w_evict_first != 0, w_policy);
@@ -263,20 +274,37 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     } else if (ROLE == ROLE_MMA) {
       gemm_issue_mma(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, acc);
     } else {
+      w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u);
       gemm_epilogue(t, gs, cta, nctas, acc);
+      if (fuse_kind != 0) {
+        fuse_seq[fuse_kind - 1] += 1u;
+        if (cta < t.n_tiles * t.splits) {
+          const int n_tile = cta / t.splits, split = cta - n_tile * t.splits;
+          workers_sync();                                 // every worker's partial sums are stored
+          if (w.wtid == 0) {
+            unsigned int* ctr = c.tile_ctr + (fuse_kind - 1) * kMaxTilesPerKind + n_tile;
+            red_release_gpu_add_u32(ctr, 1u);
+            wait_epoch<false>(ctr, fuse_seq[fuse_kind - 1] * (unsigned int)t.splits);   // all k-splits of the tile
+          }
+          workers_sync();
+          gemm_norm_tail(c, w, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
+        }
+      }
     }
     if (barrier_after) {
-      if (ROLE == ROLE_WORKER) grid_barrier(c, w, bs, prof_slot, t.epilogue == EPI_SWIGLU_BF16, xgpu); else skip_barrier(xgpu);
+      if (ROLE == ROLE_WORKER)
+        grid_barrier(c, w, bs, prof_slot, t.epilogue == EPI_SWIGLU_BF16 || fuse_kind != 0, xgpu, stage_id);
+      else skip_barrier(xgpu);
     }
   };
-#define JF_SIMT_STAGE_X(tma_out, body)                         \
+#define JF_SIMT_STAGE_X(tma_out, sid, body)                    \
   do {                                                        \
-    if (ROLE == ROLE_WORKER) { w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); body; grid_barrier(c, w, bs, prof_slot, tma_out); } else { skip_barrier(false); } \
+    if (ROLE == ROLE_WORKER) { w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); body; grid_barrier(c, w, bs, prof_slot, tma_out, false, sid); } else { skip_barrier(false); } \
   } while (0)
 
-#define JF_SIMT_STAGE(body) JF_SIMT_STAGE_X(true, body)
+#define JF_SIMT_STAGE(sid, body) JF_SIMT_STAGE_X(true, sid, body)
   if (run_mode == RUN_JACOBI) {
-    JF_SIMT_STAGE(if (cta == 0) policy_stage_jacobi(c, w, true, max_forwards));
+    JF_SIMT_STAGE(SID_POLICY, if (cta == 0) policy_stage_jacobi(c, w, true, max_forwards));
   }
 
   for (;;) {
@@ -306,14 +334,18 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         prof_slot = &prof_n;
         w.prof_on = 1;
         if (w.wtid == 0 && c.prof_marks_n) *c.prof_marks_n = 0;
-        if (w.wtid == 0 && c.prof_cap >= 2) { c.prof[0] = clock64(); c.prof[1] = c.prof[0]; prof_n = 2; }
+        if (w.wtid == 0 && c.prof_cap >= 3) { c.prof[0] = 0; c.prof[1] = clock64(); c.prof[2] = c.prof[1]; prof_n = 3; }
       }
     }
     slot_bytes = gemm_slot_bytes(min(kMaxRowsMMA, round_up16(T)));
     nstages = min(kMaxStages, ring_bytes / slot_bytes);
     pipe.stage = 0;
 
-    JF_SIMT_STAGE(stage_commit(c, w, ip.n_commit); stage_rows_norm(c, w, T, true, 0, c.layer[0].ln1, 0));
+    JF_SIMT_STAGE(SID_EMBED, stage_commit(c, w, ip.n_commit); stage_rows_norm(c, w, T, true, 0, c.layer[0].ln1, 0));
+    // the fused tails apply to Jacobi-sized forwards on one GPU (see gemm_stage); prefill-sized ones keep the stages
+    const bool fuse_ok = c.fuse_norm != 0 && !tp && T <= kFuseMaxRows;
+    const bool fuse_o = fuse_ok && nt_h * c.splits_o <= nctas;
+    const bool fuse_d = fuse_ok && nt_h * c.splits_down <= nctas;
 
     auto base_task = [&]() {
       GemmTask t;
@@ -357,41 +389,45 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     for (int l = 0; l < md.layers; ++l) {
       const LayerW& lw = c.layer[l];
       const GemmTask tq = task_qkv(l), to = task_o(l), tg = task_gu(l), td = task_down(l);
+      const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
       if (ROLE == ROLE_WORKER) attention_prefetch(c, w, l, ip.G, ip.attn_units);
-      gemm_stage(tq, true, &to);
-      JF_SIMT_STAGE_X(false, if (!(c.debug_skip & 1)) stage_qkv_rope(c, w, T, l));
-      JF_SIMT_STAGE_X(false, if (!(c.debug_skip & 2)) stage_attention(c, w, l, ip.G, ip.attn_units));
-      JF_SIMT_STAGE(if (!(c.debug_skip & 4)) stage_attn_combine(c, w, T));
-      gemm_stage(to, true, &tg, tp);
-      JF_SIMT_STAGE(if (!(c.debug_skip & 8)) stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2, 0));
-      gemm_stage(tg, true, &td);
-      if (l + 1 < md.layers) {
-        const GemmTask tn = task_qkv(l + 1);
-        gemm_stage(td, true, &tn, tp);
-      } else if (ip.n_lm > 0) {
-        const GemmTask tn = task_lm(0);
-        gemm_stage(td, true, &tn, tp);
+      gemm_stage(tq, true, SID_QKV, &to);
+      JF_SIMT_STAGE_X(false, SID_ROPE, if (!(c.debug_skip & 1)) stage_qkv_rope(c, w, T, l));
+      JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) stage_attention(c, w, l, ip.G, ip.attn_units));
+      JF_SIMT_STAGE(SID_COMBINE, if (!(c.debug_skip & 4)) stage_attn_combine(c, w, T));
+      if (fuse_o) {
+        gemm_stage(to, true, SID_O_FUSED, &tg, false, 1, lw.ln2);
       } else {
-        gemm_stage(td, true, nullptr, tp);
+        gemm_stage(to, true, SID_O, &tg, tp);
+        JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2, 0));
       }
-      JF_SIMT_STAGE(stage_rows_norm(c, w, T, false, c.splits_down,
-                                    (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm, 1));
+      gemm_stage(tg, true, SID_GU, &td);
+      GemmTask tn;
+      const GemmTask* tnp = nullptr;
+      if (l + 1 < md.layers) { tn = task_qkv(l + 1); tnp = &tn; }
+      else if (ip.n_lm > 0) { tn = task_lm(0); tnp = &tn; }
+      if (fuse_d) {
+        gemm_stage(td, true, SID_DOWN_FUSED, tnp, false, 2, next_norm);
+      } else {
+        gemm_stage(td, true, SID_DOWN, tnp, tp);
+        JF_SIMT_STAGE(SID_DOWN_NORM, stage_rows_norm(c, w, T, false, c.splits_down, next_norm, 1));
+      }
     }
 
     // LM head: fused bf16-rounded argmax (no logits in HBM); optional fp32 logits for the tolerance checks
     for (int i = 0; i < ip.n_lm; ++i) {
       GemmTask t = task_lm(i);
       const GemmTask tn = task_qkv(0);               // the next forward's first weights (harmless if there is none)
-      gemm_stage(t, false, (i + 1 == ip.n_lm) ? &tn : nullptr);
+      gemm_stage(t, false, SID_LM, (i + 1 == ip.n_lm) ? &tn : nullptr);
       if (i == 0 && ip.want_logits) {
         t.out = c.logits - (size_t)t.x_row0 * md.vocab;
         t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = md.vocab; t.out_split_stride = 0;
-        gemm_stage(t, false);
+        gemm_stage(t, false, SID_LM);
       }
     }
-    if (ROLE == ROLE_WORKER) grid_barrier(c, w, bs, prof_slot, true, tp); else skip_barrier(tp);
+    if (ROLE == ROLE_WORKER) grid_barrier(c, w, bs, prof_slot, true, tp, SID_LM); else skip_barrier(tp);
 
-    JF_SIMT_STAGE(if (cta == 0) {
+    JF_SIMT_STAGE(SID_POLICY, if (cta == 0) {
       if (run_mode == RUN_JACOBI) policy_stage_jacobi(c, w, false, max_forwards); else policy_stage_plan(c, w);
     });
   }

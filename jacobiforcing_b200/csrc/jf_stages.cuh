@@ -38,16 +38,6 @@ constexpr uint32_t kBarReduce  = 2;
 
 __device__ __forceinline__ void workers_sync() { named_bar_sync(kBarWorkers, kWorkerThreads); }
 
-__device__ __forceinline__ float block_sum_128(float v, const WorkerCtx& w) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (w.lane == 0) w.red[w.wwarp] = v;
-  named_bar_sync(kBarReduce, kWorkerThreads);
-  const float r = (w.red[0] + w.red[1]) + (w.red[2] + w.red[3]);
-  named_bar_sync(kBarReduce, kWorkerThreads);
-  return r;
-}
-
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -65,10 +55,50 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // rows: (embedding | split-K reduce + residual add) -> hidden, then RMSNorm -> packed X operand of the next GEMM.
-// A row is cut into slices of 1024 columns (one CTA each, one 8-column group per thread, every load in flight at
-// once); each slice publishes its sum of squares, and the CTA that arrives last for a row adds the slice sums in slice
-// order (deterministic, independent of who is last) and normalises the whole row.
+// Stand-alone stage: a row is cut into slices of 1024 columns (one CTA each, one 8-column group per thread, every
+// load in flight at once); every slice publishes the sums of squares of its 128-column tiles, polls the row's other
+// tiles and normalises its own columns.
 // ---------------------------------------------------------------------------------------------------------------
+// Canonical row statistic (identical in the stand-alone stage and in the fused GEMM tail, so a row's RMSNorm does not
+// depend on which of the two produced it): every 128-column tile publishes its sum of squares - 8 columns per lane
+// added in column order, then a 16-lane xor tree - as one tagged 64-bit word {stage tag, value}; a single relaxed
+// store / polling load carries flag and payload together, so no fences, atomics or resets are needed.  The row total
+// is formed by 16 lanes: lane l adds tiles l, l+16, l+32, ... in order, then the same xor tree.
+__device__ __forceinline__ float halfwarp_tree(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+__device__ __forceinline__ float sumsq8(const float (&x)[8]) {
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ss += x[j] * x[j];
+  return ss;
+}
+__device__ __forceinline__ void publish_tile_ss(const DevCtx& c, int t, int tile, unsigned int tag, float ss) {
+  st_relaxed_gpu_u64(c.row_ss + (size_t)t * kMaxHTiles + tile,
+                     ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(ss));
+}
+// called by whole warps; each 16-lane half works on its own row (valid = the half has a row)
+__device__ __forceinline__ float row_total_canonical(const DevCtx& c, int t, int nt_h, unsigned int tag, int l16, bool valid) {
+  float p = 0.f;
+  if (valid) {
+    const unsigned long long* slots = c.row_ss + (size_t)t * kMaxHTiles;
+    for (int s2 = l16; s2 < nt_h; s2 += 16) {
+      unsigned long long word = ld_relaxed_gpu_u64(slots + s2);
+      const long long t0 = clock64();
+      while ((unsigned int)(word >> 32) != tag) {
+        word = ld_relaxed_gpu_u64(slots + s2);
+        if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+      }
+      p += __uint_as_float((unsigned int)(word & 0xffffffffull));
+    }
+  }
+  return halfwarp_tree(p);
+}
+
 // SPLITS == 0: embedding lookup instead of a reduce.  TP = tensor-parallel ranks whose partial sums are added (rank order,
 // then split order, identical on every rank): rank r's slices live in peer memory reached through c.peer_part_rs.
 template <int SPLITS, int TP>
@@ -76,15 +106,16 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
                                                int which) {
   const int h = c.md.h;
   const int nvec = h >> 3;
+  const int nt_h = (h + 127) >> 7;
   const int NS = (nvec + kWorkerThreads - 1) / kWorkerThreads;     // slices per row (<= 8), one CTA each
   const int items = T * NS;
+  const int l16 = w.lane & 15;
   prof_mark(c, w, 200);
   for (int item = w.cta; item < items; item += w.nctas) {
     const int t = item / NS, sl = item - t * NS;
     const int v = sl * kWorkerThreads + w.wtid;
     __nv_bfloat16* hrow = c.hidden + (size_t)t * h;
-    float ss = 0.f;
-    float x[8], wt[8];
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, wt[8];
     if (v < nvec) {
       const uint4 wraw = __ldg(reinterpret_cast<const uint4*>(normw) + v);       // needed last: fetch first
       if (SPLITS == 0) {
@@ -120,33 +151,12 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
       }
       unpack8(wraw, wt);
       reinterpret_cast<uint4*>(hrow)[v] = pack8(x);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ss += x[j] * x[j];
     }
     prof_mark(c, w, 201);
-    ss = block_sum_128(ss, w);
+    const float tile_ss = halfwarp_tree(sumsq8(x));                 // lanes past the row end contribute zeros
+    if (l16 == 0 && (v >> 4) < nt_h) publish_tile_ss(c, t, v >> 4, w.tag, tile_ss);
     prof_mark(c, w, 202);
-    // The slices of a row exchange their sums of squares through one 64-bit word each, {stage tag, value}: a single
-    // relaxed store / polling load carries flag and payload together, so no fences, atomics or resets are needed.
-    float total = ss;
-    if (NS > 1) {
-      unsigned long long* slots = c.row_ss + (size_t)t * 8;
-      if (w.wtid == 0)
-        st_relaxed_gpu_u64(slots + sl, ((unsigned long long)w.tag << 32) | (unsigned long long)__float_as_uint(ss));
-      if (w.wtid < NS) {
-        unsigned long long word = ld_relaxed_gpu_u64(slots + w.wtid);
-        const long long t0 = clock64();
-        while ((unsigned int)(word >> 32) != w.tag) {
-          word = ld_relaxed_gpu_u64(slots + w.wtid);
-          if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
-        }
-        w.red[8 + w.wtid] = __uint_as_float((unsigned int)(word & 0xffffffffull));
-      }
-      named_bar_sync(kBarReduce, kWorkerThreads);
-      total = 0.f;
-      for (int s2 = 0; s2 < NS; ++s2) total += w.red[8 + s2];            // slice order: the same on every CTA
-      named_bar_sync(kBarReduce, kWorkerThreads);
-    }
+    const float total = row_total_canonical(c, t, nt_h, w.tag, l16, true);
     prof_mark(c, w, 203);
     if (v < nvec) {
       const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
@@ -159,6 +169,95 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
     }
     prof_mark(c, w, 204);
   }
+}
+
+// The same reduce + residual + RMSNorm executed as the TAIL of a row-split GEMM (O / down projection): once every
+// k-split of n-tile `n_tile` has stored its partial sums, the CTAs of those splits share the tile's rows - row step
+// `it` (8 rows: one per half-warp) belongs to split it % SPLITS - and each owns the tile's 128 columns of its rows
+// (8 columns per lane).  The arithmetic (split order, rounding points, the canonical row statistic) is that of
+// rows_norm_impl, bit for bit.
+constexpr int kFuseMaxRows = 64;
+template <int SPLITS>
+__device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerCtx& w, int T, int n_tile, int split,
+                                                 const __nv_bfloat16* normw, int which) {
+  constexpr int MAXJ = (kFuseMaxRows / 8 + SPLITS - 1) / SPLITS;     // row steps one split may own
+  const int h = c.md.h;
+  const int nt_h = (h + 127) >> 7;
+  const int l16 = w.lane & 15, hw = w.lane >> 4;
+  const int v = n_tile * 16 + l16;                       // 16-byte chunk of the row
+  const bool cvalid = v < (h >> 3);
+  const int nit = (T + 7) >> 3;
+  if (split >= nit) return;
+  const size_t sstride4 = (size_t)h >> 2;
+  const float* src = c.part_rs[which];
+  uint4 xs[MAXJ];
+  uint4 wraw = make_uint4(0u, 0u, 0u, 0u);
+  if (cvalid) wraw = __ldg(reinterpret_cast<const uint4*>(normw) + v);
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    const int it = split + j * SPLITS;
+    xs[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (it < nit) {
+      const int t = it * 8 + w.wwarp * 2 + hw;
+      uint4 rr = make_uint4(0u, 0u, 0u, 0u);
+      float4 pa[SPLITS], pb[SPLITS];
+#pragma unroll
+      for (int s2 = 0; s2 < SPLITS; ++s2) { pa[s2] = make_float4(0.f, 0.f, 0.f, 0.f); pb[s2] = pa[s2]; }
+      if (t < T && cvalid) {
+        rr = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
+        const float4* p = reinterpret_cast<const float4*>(src + (size_t)t * c.part_splits * h) + v * 2;
+#pragma unroll
+        for (int s2 = 0; s2 < SPLITS; ++s2) {
+          pa[s2] = ld_weak(p + s2 * sstride4);
+          pb[s2] = ld_weak(p + s2 * sstride4 + 1);
+        }
+      }
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s2 = 0; s2 < SPLITS; ++s2) {
+        acc[0] += pa[s2].x; acc[1] += pa[s2].y; acc[2] += pa[s2].z; acc[3] += pa[s2].w;
+        acc[4] += pb[s2].x; acc[5] += pb[s2].y; acc[6] += pb[s2].z; acc[7] += pb[s2].w;
+      }
+      float r[8], x[8];
+      unpack8(rr, r);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = bf16_round(r[q] + bf16_round(acc[q]));
+      xs[j] = pack8(x);
+      if (t < T && cvalid) reinterpret_cast<uint4*>(c.hidden + (size_t)t * h)[v] = xs[j];
+      const float tile_ss = halfwarp_tree(sumsq8(x));
+      if (l16 == 0 && t < T) publish_tile_ss(c, t, n_tile, w.tag, tile_ss);
+    }
+  }
+  float wt[8];
+  unpack8(wraw, wt);
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    const int it = split + j * SPLITS;
+    if (it < nit) {
+      const int t = it * 8 + w.wwarp * 2 + hw;
+      const float total = row_total_canonical(c, t, nt_h, w.tag, l16, t < T);
+      if (t < T && cvalid) {
+        const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
+        float x[8], o[8];
+        unpack8(xs[j], x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = wt[q] * bf16_round(x[q] * rstd);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(v >> 3) * c.xrows_cap + t) * 128 +
+                       (((v & 7) ^ (t & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = pack8(o);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void gemm_norm_tail(const DevCtx& c, const WorkerCtx& w, int T, int n_tile, int split,
+                                            int splits, const __nv_bfloat16* normw, int which) {
+#define JF_TAIL_CASE(S) case S: gemm_norm_tail_impl<S>(c, w, T, n_tile, split, normw, which); break;
+  switch (splits) {
+    JF_TAIL_CASE(1) JF_TAIL_CASE(2) JF_TAIL_CASE(3) JF_TAIL_CASE(4) JF_TAIL_CASE(5) JF_TAIL_CASE(6) JF_TAIL_CASE(7)
+    default: gemm_norm_tail_impl<8>(c, w, T, n_tile, split, normw, which); break;
+  }
+#undef JF_TAIL_CASE
 }
 
 // which: 0 = after the O projection, 1 = after the down projection (selects the row-split partial buffer)

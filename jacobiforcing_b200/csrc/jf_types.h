@@ -11,6 +11,8 @@ constexpr int kMaxLayers   = 64;     // the per-layer weight table lives in shar
 constexpr int kAttnSub     = 64;     // keys per mma.sync sub-tile
 constexpr int kMaxLmTasks  = 16;     // LM-head row tiles of kArgmaxRows per forward
 constexpr int kQTokPerUnit = 64;     // query tokens one attention unit covers
+constexpr int kMaxHTiles   = 64;     // 128-column tiles of a hidden row (h <= 8192)
+constexpr int kMaxTilesPerKind = 128; // arrival counters per fused GEMM kind (O, down, QKV)
 constexpr int kMaxTP       = 8;      // tensor-parallel ranks whose buffers one kernel may address (NVLink peers)
 
 struct ModelDims {
@@ -107,7 +109,7 @@ struct alignas(16) DevCtx {
   int attn_chunk;                    // keys per attention unit (multiple of kAttnSub)
   int attn_hsplit;                   // attention units per kv head along its q heads (2 when n_rep >= 4)
   unsigned long long* argmax_keys;   // [2][T_cap] packed (value, ~index) keys, double-buffered by forward parity
-  unsigned long long* row_ss;        // [T_cap][8] per-slice {stage tag, sum of squares} words of the row being normalised
+  unsigned long long* row_ss;        // [T_cap][kMaxHTiles] per-tile {stage tag, sum of squares} words of the row being normalised
   unsigned int launch_id;            // makes the stage tags unique across launches
   int splits_qkv, splits_o, splits_down;
   // ---- plan (written by the host in plan mode, by the policy stage in Jacobi mode)
@@ -143,6 +145,8 @@ struct alignas(16) DevCtx {
   unsigned long long xflag_base;              // launch sequence << 32 (flags are monotonic, never reset)
   // ---- sync
   unsigned int* bar_counter;
+  unsigned int* tile_ctr;            // [3][kMaxTilesPerKind] k-split arrivals per n-tile of the fused GEMM stages (zeroed per launch)
+  int fuse_norm;                     // 1: O / down projections run reduce + residual + RMSNorm as their epilogue tail
   // ---- optional stage profile: SM-clock stamps taken by CTA 0 after every grid barrier of forward `prof_forward`
   long long* prof;
   int prof_cap;

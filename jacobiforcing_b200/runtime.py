@@ -135,18 +135,21 @@ class JacobiRuntime:
         _cabi.check(self.lib.jf_profile_read(self.h, stamps.ctypes.data_as(C.POINTER(C.c_int64)), 4096, C.byref(n),
                                              C.byref(khz)), self.h)
         st = stamps[:n.value].astype(np.float64) / (khz.value / 1e3)       # microseconds
-        names = ["start", "embed+norm"]
-        per_layer = ["qkv_gemm", "qkv_rope", "attention", "attn_combine", "o_gemm", "o_reduce_norm", "gate_up_gemm",
-                     "down_gemm", "down_reduce_norm"]
-        for l in range(self.model_cfg.num_hidden_layers):
-            names += [f"L{l}.{s}" for s in per_layer]
-        names += ["lm_head_argmax", "policy"]
+        kinds = {1: "embed+norm", 2: "qkv_gemm", 3: "qkv_rope", 4: "attention", 5: "attn_combine", 6: "o_gemm",
+                 7: "o_reduce_norm", 8: "gate_up_gemm", 9: "down_gemm", 10: "down_reduce_norm", 11: "lm_head_argmax",
+                 12: "policy", 13: "o_gemm+norm", 14: "down_gemm+norm", 15: "qkv_gemm+rope"}
         rows = []
-        for i in range(1, n.value // 2):
-            arrive, release = st[2 * i], st[2 * i + 1]
-            prev_release = st[2 * i - 1]
-            rows.append({"stage": names[i] if i < len(names) else f"#{i}", "work_us": arrive - prev_release,
-                         "wait_us": release - arrive})
+        layer, seen_qkv = -1, False
+        for i in range(1, n.value // 3):                    # triples (stage id, arrival of CTA 0, release)
+            sid = int(stamps[3 * i])
+            arrive, release = st[3 * i + 1], st[3 * i + 2]
+            prev_release = st[3 * i - 1]
+            if sid in (2, 15):
+                layer += 1
+            name = kinds.get(sid, f"#{sid}")
+            if 2 <= sid <= 10 or sid >= 13:
+                name = f"L{layer}.{name}"
+            rows.append({"stage": name, "work_us": arrive - prev_release, "wait_us": release - arrive})
         return {"sm_clock_khz": khz.value, "stages": rows}
 
     # ---- weights (loader.py:27-47 loop stays with the caller; this is the per-tensor weight_loader) ---------------
