@@ -413,10 +413,12 @@ extern "C" int jf_profile_enable(jf_handle h, int32_t forward_index) {
     if (rc != JF_OK) return rc;
     rc = dev_alloc(h, &c.prof_count, 4, &h->bytes_act);
     if (rc != JF_OK) return rc;
-    rc = dev_alloc(h, &c.prof_marks, 8192, &h->bytes_act);
-    if (rc != JF_OK) return rc;
-    rc = dev_alloc(h, &c.prof_marks_n, 4, &h->bytes_act);
-    if (rc != JF_OK) return rc;
+    if (getenv("JF_PROF_MARKS")) {                       // fine-grained marks only on request: they perturb the stages
+      rc = dev_alloc(h, &c.prof_marks, 8192, &h->bytes_act);
+      if (rc != JF_OK) return rc;
+      rc = dev_alloc(h, &c.prof_marks_n, 4, &h->bytes_act);
+      if (rc != JF_OK) return rc;
+    }
   }
   c.prof_forward = forward_index;
   long long* keep = c.prof;
@@ -437,7 +439,7 @@ extern "C" int jf_profile_read(jf_handle h, int64_t* stamps, int32_t capacity, i
   if (n > capacity) n = capacity;
   if (n > 0) JF_CUDA(h, cudaMemcpy(stamps, c.prof, (size_t)n * 8, cudaMemcpyDeviceToHost));
   *n_stamps = n;
-  if (const char* path = getenv("JF_PROF_MARKS")) {          // developer aid: dump the fine-grained marks as text
+  if (const char* path = c.prof_marks_n ? getenv("JF_PROF_MARKS") : nullptr) {          // developer aid: dump the fine-grained marks as text
     int nm = 0;
     cudaMemcpy(&nm, c.prof_marks_n, 4, cudaMemcpyDeviceToHost);
     std::vector<long long> mk(nm > 0 ? nm : 1);

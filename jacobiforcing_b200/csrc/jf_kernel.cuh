@@ -90,7 +90,8 @@ __device__ __forceinline__ unsigned long long merged_key(const DevCtx& c, int kb
   return best;
 }
 
-__device__ __noinline__ void policy_stage_plan(const DevCtx& c, const WorkerCtx& w) {
+__device__ __noinline__ void policy_stage_plan(const DevCtx& c, const WorkerShared* ws) {
+  const WorkerCtx w = load_wctx(ws);
   PlanHdr* hdr = c.hdr;
   const int kbuf = ld_weak(&hdr->iter) & 1;
   const int n_lm = ld_weak(&hdr->n_lm_tasks);
@@ -108,7 +109,8 @@ __device__ __noinline__ void policy_stage_plan(const DevCtx& c, const WorkerCtx&
   }
 }
 
-__device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerCtx& w, bool first, int max_forwards) {
+__device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerShared* ws, bool first, int max_forwards) {
+  const WorkerCtx w = load_wctx(ws);
   PlanHdr* hdr = c.hdr;
   const int Tprev = first ? 0 : ld_weak(&hdr->T);
   const int kbuf = first ? 0 : (ld_weak(&hdr->iter) & 1);
@@ -239,9 +241,9 @@ struct IterPlan {
 };
 
 template <int ROLE>
-__device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring_bytes, const WorkerCtx& w_in,
+__device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring_bytes, WorkerShared* ws,
                          int run_mode, int max_forwards) {
-  WorkerCtx w = w_in;
+  WorkerCtx w = load_wctx(ws);
   const int cta = blockIdx.x, nctas = gridDim.x;
   BarState bs;
   PipeState pipe;
@@ -275,6 +277,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       gemm_issue_mma(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, acc);
     } else {
       w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u);
+      ws->tag = w.tag;
       gemm_epilogue(t, gs, cta, nctas, acc);
       if (fuse_kind != 0) {
         fuse_seq[fuse_kind - 1] += 1u;
@@ -287,7 +290,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
             wait_epoch<false>(ctr, fuse_seq[fuse_kind - 1] * (unsigned int)t.splits);   // all k-splits of the tile
           }
           workers_sync();
-          gemm_norm_tail(c, w, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
+          gemm_norm_tail(c, ws, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
         }
       }
     }
@@ -299,12 +302,12 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   };
 #define JF_SIMT_STAGE_X(tma_out, sid, body)                    \
   do {                                                        \
-    if (ROLE == ROLE_WORKER) { w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); body; grid_barrier(c, w, bs, prof_slot, tma_out, false, sid); } else { skip_barrier(false); } \
+    if (ROLE == ROLE_WORKER) { w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); ws->tag = w.tag; body; grid_barrier(c, w, bs, prof_slot, tma_out, false, sid); } else { skip_barrier(false); } \
   } while (0)
 
 #define JF_SIMT_STAGE(sid, body) JF_SIMT_STAGE_X(true, sid, body)
   if (run_mode == RUN_JACOBI) {
-    JF_SIMT_STAGE(SID_POLICY, if (cta == 0) policy_stage_jacobi(c, w, true, max_forwards));
+    JF_SIMT_STAGE(SID_POLICY, if (cta == 0) policy_stage_jacobi(c, ws, true, max_forwards));
   }
 
   for (;;) {
@@ -316,24 +319,32 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     ip.n_lm = ld_weak(&hdr->n_lm_tasks); ip.want_logits = ld_weak(&hdr->want_logits);
     if (ip.done) {
       if (ROLE == ROLE_WORKER) {
-        if (prof_slot != nullptr && w.wtid == 0) *c.prof_count = prof_n;
+        if (prof_slot != nullptr && w.wtid == 0) {
+          *c.prof_count = prof_n;
+          if (c.prof_marks_n) *c.prof_marks_n = reinterpret_cast<int*>(w.red)[4];
+        }
         if (tp) grid_barrier(c, w, bs, nullptr, false, true);      // every rank has read every rank's keys
         if (cta == 0)
           for (int t = w.wtid; t < 2 * c.T_cap; t += kWorkerThreads) c.argmax_keys[t] = 0ull;   // clean for the next launch
-        stage_commit(c, w, ip.n_commit);
+        stage_commit(c, ws, ip.n_commit);
       }
       break;
     }
     const int T = ip.T;
     if (ROLE == ROLE_WORKER) {
-      if (prof_slot != nullptr && w.wtid == 0) *c.prof_count = prof_n;     // forward profiled: publish and stop
+      if (prof_slot != nullptr && w.wtid == 0) {                           // forward profiled: publish and stop
+        *c.prof_count = prof_n;
+        if (c.prof_marks_n) *c.prof_marks_n = reinterpret_cast<int*>(w.red)[4];
+      }
       prof_slot = nullptr;
       w.prof_on = 0;
+      ws->prof_on = 0;
       if (cta == 0 && c.prof != nullptr && ld_weak(&hdr->iter) == c.prof_forward) {
         prof_n = 0;
         prof_slot = &prof_n;
         w.prof_on = 1;
-        if (w.wtid == 0 && c.prof_marks_n) *c.prof_marks_n = 0;
+        ws->prof_on = 1;
+        if (w.wtid == 0) reinterpret_cast<int*>(w.red)[4] = 0;
         if (w.wtid == 0 && c.prof_cap >= 3) { c.prof[0] = 0; c.prof[1] = clock64(); c.prof[2] = c.prof[1]; prof_n = 3; }
       }
     }
@@ -341,7 +352,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     nstages = min(kMaxStages, ring_bytes / slot_bytes);
     pipe.stage = 0;
 
-    JF_SIMT_STAGE(SID_EMBED, stage_commit(c, w, ip.n_commit); stage_rows_norm(c, w, T, true, 0, c.layer[0].ln1, 0));
+    JF_SIMT_STAGE(SID_EMBED, stage_commit(c, ws, ip.n_commit); stage_rows_norm(c, ws, T, true, 0, c.layer[0].ln1, 0));
     // the fused tails apply to Jacobi-sized forwards on one GPU (see gemm_stage); prefill-sized ones keep the stages
     const bool fuse_ok = c.fuse_norm != 0 && !tp && T <= kFuseMaxRows;
     const bool fuse_o = fuse_ok && nt_h * c.splits_o <= nctas;
@@ -390,16 +401,23 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       const LayerW& lw = c.layer[l];
       const GemmTask tq = task_qkv(l), to = task_o(l), tg = task_gu(l), td = task_down(l);
       const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
-      if (ROLE == ROLE_WORKER) attention_prefetch(c, w, l, ip.G, ip.attn_units);
+      if (ROLE == ROLE_WORKER) attention_prefetch(c, ws, l, ip.G, ip.attn_units);
       gemm_stage(tq, true, SID_QKV, &to);
-      JF_SIMT_STAGE_X(false, SID_ROPE, if (!(c.debug_skip & 1)) stage_qkv_rope(c, w, T, l));
-      JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) stage_attention(c, w, l, ip.G, ip.attn_units));
-      JF_SIMT_STAGE(SID_COMBINE, if (!(c.debug_skip & 4)) stage_attn_combine(c, w, T));
+      JF_SIMT_STAGE_X(false, SID_ROPE, if (!(c.debug_skip & 1)) stage_qkv_rope(c, ws, T, l));
+      JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) {
+        stage_attention(c, ws, l, ip.G, ip.attn_units);
+        if (c.debug_skip & 512) {                          // timing experiment: the same stage again, code and data warm
+          workers_sync(); prof_mark(c, w, 396);
+          stage_attention(c, ws, l, ip.G, ip.attn_units);
+          workers_sync(); prof_mark(c, w, 397);
+        }
+      });
+      JF_SIMT_STAGE(SID_COMBINE, if (!(c.debug_skip & 4)) stage_attn_combine(c, ws, T));
       if (fuse_o) {
         gemm_stage(to, true, SID_O_FUSED, &tg, false, 1, lw.ln2);
       } else {
         gemm_stage(to, true, SID_O, &tg, tp);
-        JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, w, T, false, c.splits_o, lw.ln2, 0));
+        JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, ws, T, false, c.splits_o, lw.ln2, 0));
       }
       gemm_stage(tg, true, SID_GU, &td);
       GemmTask tn;
@@ -410,7 +428,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         gemm_stage(td, true, SID_DOWN_FUSED, tnp, false, 2, next_norm);
       } else {
         gemm_stage(td, true, SID_DOWN, tnp, tp);
-        JF_SIMT_STAGE(SID_DOWN_NORM, stage_rows_norm(c, w, T, false, c.splits_down, next_norm, 1));
+        JF_SIMT_STAGE(SID_DOWN_NORM, stage_rows_norm(c, ws, T, false, c.splits_down, next_norm, 1));
       }
     }
 
@@ -428,7 +446,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     if (ROLE == ROLE_WORKER) grid_barrier(c, w, bs, prof_slot, true, tp, SID_LM); else skip_barrier(tp);
 
     JF_SIMT_STAGE(SID_POLICY, if (cta == 0) {
-      if (run_mode == RUN_JACOBI) policy_stage_jacobi(c, w, false, max_forwards); else policy_stage_plan(c, w);
+      if (run_mode == RUN_JACOBI) policy_stage_jacobi(c, ws, false, max_forwards); else policy_stage_plan(c, ws);
     });
   }
 #undef JF_SIMT_STAGE
@@ -464,18 +482,18 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
   gemm_setup(gs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WorkerCtx w;
-  w.cta = blockIdx.x; w.nctas = gridDim.x; w.lane = lane; w.red = red; w.attn_smem = attn; w.prof_on = 0;
-  w.wwarp = warp - kWarpWorker0; w.wtid = (int)threadIdx.x - kWarpWorker0 * 32;
+  WorkerShared* ws = reinterpret_cast<WorkerShared*>(red + 8);      // red[8..15]
+  if (threadIdx.x == 0) { ws->red = red; ws->attn_smem = attn; ws->prof_on = 0; ws->tag = 0u; }
+  __syncthreads();
 
   if (warp == kWarpW) {
-    if (lane == 0) run_role<ROLE_W>(c, gs, tiles, ring_bytes, w, run_mode, max_forwards);
+    if (lane == 0) run_role<ROLE_W>(c, gs, tiles, ring_bytes, ws, run_mode, max_forwards);
   } else if (warp == kWarpMMA) {
-    if (lane == 0) run_role<ROLE_MMA>(c, gs, tiles, ring_bytes, w, run_mode, max_forwards);
+    if (lane == 0) run_role<ROLE_MMA>(c, gs, tiles, ring_bytes, ws, run_mode, max_forwards);
   } else if (warp == kWarpX) {
-    if (lane == 0) run_role<ROLE_X>(c, gs, tiles, ring_bytes, w, run_mode, max_forwards);
+    if (lane == 0) run_role<ROLE_X>(c, gs, tiles, ring_bytes, ws, run_mode, max_forwards);
   } else {
-    run_role<ROLE_WORKER>(c, gs, tiles, ring_bytes, w, run_mode, max_forwards);
+    run_role<ROLE_WORKER>(c, gs, tiles, ring_bytes, ws, run_mode, max_forwards);
   }
   __syncwarp();
   gemm_teardown(gs);

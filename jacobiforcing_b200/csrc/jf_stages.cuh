@@ -20,16 +20,38 @@ struct WorkerCtx {
   int wtid;        // 0..127 among the worker warps
   int wwarp;       // 0..3
   int lane;
-  float* red;      // [8] block-reduction scratch
+  float* red;      // [16] scratch words
   uint8_t* attn_smem;
   int prof_on;     // CTA 0, forward being profiled
   unsigned int tag; // unique id of the stage instance being executed (launch id, barrier count)
 };
+// The part of the worker context that is not derivable from special registers lives in shared memory.  Non-inlined
+// stage functions receive a pointer to it and rebuild their WorkerCtx in registers: a struct passed by reference to a
+// non-inlined function lives on the caller's stack, and every field access becomes a local-memory load that misses L1
+// after each grid barrier (ncu: long-scoreboard stalls on w.lane / grp.slot0 inside the attention stage).
+struct WorkerShared {
+  float* red;
+  uint8_t* attn_smem;
+  int prof_on;
+  unsigned int tag;
+};
+__device__ __forceinline__ WorkerCtx load_wctx(const WorkerShared* ws) {
+  WorkerCtx w;
+  w.cta = blockIdx.x; w.nctas = gridDim.x;
+  w.lane = threadIdx.x & 31;
+  w.wwarp = (int)(threadIdx.x >> 5) - 2;          // kWarpWorker0
+  w.wtid = (int)threadIdx.x - 2 * 32;
+  w.red = ws->red; w.attn_smem = ws->attn_smem; w.prof_on = ws->prof_on; w.tag = ws->tag;
+  return w;
+}
 
 __device__ __forceinline__ void prof_mark(const DevCtx& c, const WorkerCtx& w, int id) {
   if (w.prof_on && w.wtid == 0 && c.prof_marks != nullptr) {
-    const int n = *c.prof_marks_n;
-    if (n + 2 <= 8192) { c.prof_marks[n] = id; c.prof_marks[n + 1] = clock64(); *c.prof_marks_n = n + 2; }
+    // the running count lives in shared memory (a global counter costs an L2 round trip per mark: ~0.45 us measured);
+    // it is published with the stage stamps when the profiled forward ends
+    int* cnt = reinterpret_cast<int*>(w.red) + 4;
+    const int n = *cnt;
+    if (n + 2 <= 8192) { c.prof_marks[n] = id; c.prof_marks[n + 1] = clock64(); *cnt = n + 2; }
   }
 }
 
@@ -178,8 +200,9 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
 // rows_norm_impl, bit for bit.
 constexpr int kFuseMaxRows = 64;
 template <int SPLITS>
-__device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerCtx& w, int T, int n_tile, int split,
+__device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerShared* ws, int T, int n_tile, int split,
                                                  const __nv_bfloat16* normw, int which) {
+  const WorkerCtx w = load_wctx(ws);
   constexpr int MAXJ = (kFuseMaxRows / 8 + SPLITS - 1) / SPLITS;     // row steps one split may own
   const int h = c.md.h;
   const int nt_h = (h + 127) >> 7;
@@ -250,7 +273,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerCt
   }
 }
 
-__device__ __forceinline__ void gemm_norm_tail(const DevCtx& c, const WorkerCtx& w, int T, int n_tile, int split,
+__device__ __forceinline__ void gemm_norm_tail(const DevCtx& c, const WorkerShared* w, int T, int n_tile, int split,
                                             int splits, const __nv_bfloat16* normw, int which) {
 #define JF_TAIL_CASE(S) case S: gemm_norm_tail_impl<S>(c, w, T, n_tile, split, normw, which); break;
   switch (splits) {
@@ -261,8 +284,9 @@ __device__ __forceinline__ void gemm_norm_tail(const DevCtx& c, const WorkerCtx&
 }
 
 // which: 0 = after the O projection, 1 = after the down projection (selects the row-split partial buffer)
-__device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerCtx& w, int T, bool embed, int splits,
+__device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerShared* ws, int T, bool embed, int splits,
                                              const __nv_bfloat16* normw, int which) {
+  const WorkerCtx w = load_wctx(ws);
   if (embed) { rows_norm_impl<0, 1>(c, w, T, normw, which); return; }
 #define JF_NORM_CASE(S, TPN) case S: rows_norm_impl<S, TPN>(c, w, T, normw, which); break;
   if (c.tp_size == 1) {
@@ -378,7 +402,8 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
   prof_mark(c, w, 102);
 }
 
-__device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w, int T, int layer) {
+__device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerShared* ws, int T, int layer) {
+  const WorkerCtx w = load_wctx(ws);
   const int splits = c.splits_qkv;
 #define JF_ROPE_CASE(S)                                                                   \
   case S:                                                                                 \
@@ -399,7 +424,7 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerCtx& w,
 // committed pages and in-flight scratch rows (AR decoding and Jacobi decoding of the same prefix agree bit for bit).
 // ---------------------------------------------------------------------------------------------------------------
 template <int D>
-__device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, const Group& grp, int g_kvh, int chunk,
+__device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, const Group& grp, int g_kvh, int chunk,
                                int qs, int hs, bool prefetched) {
   constexpr int LDS = D + 8;                  // padded smem row (bf16 elements) -> conflict-free fragment loads
   constexpr int VPR = D / 8;                  // 16-byte chunks per row
@@ -464,6 +489,11 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
     const int j = j_lo + tile / ntt;
     const int i0 = q0 + (tile % ntt) * 16;
     if (key_lo > ctx + min(i0 + 15, len - 1)) return;      // inactive tile (no visible key in this chunk)
+    if (c.debug_skip & 32) {                               // timing experiment: no query loads
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) { q[ks][0] = q[ks][1] = q[ks][2] = q[ks][3] = 0x3c003c00u + tile; }
+      return;
+    }
     const int head = g_kvh * md.n_rep + j;
     const __nv_bfloat16* qa = c.qbuf + (size_t)(row0 + min(i0 + r0, len - 1)) * md.q_dim + head * D;
     const __nv_bfloat16* qb = c.qbuf + (size_t)(row0 + min(i0 + r0 + 8, len - 1)) * md.q_dim + head * D;
@@ -513,6 +543,7 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
         workers_sync();
       }
       if (!tactive || k0 > ctx + min(i0 + 15, len - 1)) continue;
+      if (c.debug_skip & 256) continue;                    // timing experiment: no math
 
       float s[8][4];
       // K fragments with ldmatrix: matrix m of one x4 = keys nt*8..+7 (rows) x dims (ks2*32 + m*8)..+7, i.e. (b0, b1) of
@@ -567,6 +598,7 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
       }
       l_a = l_a * sca + suma;
       l_b = l_b * scb + sumb;
+      if (c.debug_skip & 128) continue;                    // timing experiment: no P V
 #pragma unroll
       for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] *= sca; o[nd][1] *= sca; o[nd][2] *= scb; o[nd][3] *= scb; }
       // O += P V
@@ -594,7 +626,7 @@ __device__ __noinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w,
     }
 
     prof_mark(c, w, 403);
-    if (tactive) {
+    if (tactive && !(c.debug_skip & 64)) {
       l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
       l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
       l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
@@ -650,7 +682,8 @@ __device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, int u, i
 // sub-tile of the unit this CTA will run in the attention stage do not depend on this layer's projections, so their
 // HBM latency hides behind the QKV GEMM and the rope stage.  attention_unit(prefetched = true) then only adds the
 // in-flight rows.  (The tile buffer is free: the previous attention stage and LM head ended grid barriers ago.)
-__device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
+__device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerShared* ws, int layer, int G, int units) {
+  const WorkerCtx w = load_wctx(ws);
   if (w.cta >= units || !c.attn_prefetch) return;
   const AttnUnitId id = decode_attn_unit(c, w.cta, G);
   const ModelDims& md = c.md;
@@ -673,7 +706,8 @@ __device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerCtx
   cp_async_commit();
 }
 
-__device__ __noinline__ void stage_attention(const DevCtx& c, const WorkerCtx& w, int layer, int G, int units) {
+__device__ __noinline__ void stage_attention(const DevCtx& c, const WorkerShared* ws, int layer, int G, int units) {
+  const WorkerCtx w = load_wctx(ws);
   for (int u = w.cta; u < units; u += w.nctas) {
     prof_mark(c, w, 398);
     const AttnUnitId id = decode_attn_unit(c, u, G);
@@ -702,7 +736,8 @@ __device__ __forceinline__ void combine_store(const DevCtx& c, int t, int head, 
   }
 }
 
-__device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerCtx& w, int T) {
+__device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerShared* ws, int T) {
+  const WorkerCtx w = load_wctx(ws);
   const ModelDims& md = c.md;
   const int D = md.d;
   const int vpl = D >> 5;                                  // floats per lane: 4 (d=128) or 2 (d=64)
@@ -815,7 +850,8 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerCtx
 }
 
 // accepted in-flight K/V rows -> their pages (all layers)
-__device__ __noinline__ void stage_commit(const DevCtx& c, const WorkerCtx& w, int n_commit) {
+__device__ __noinline__ void stage_commit(const DevCtx& c, const WorkerShared* ws, int n_commit) {
+  const WorkerCtx w = load_wctx(ws);
   const ModelDims& md = c.md;
   const int per = md.layers * 2;
   const int items = n_commit * per;
