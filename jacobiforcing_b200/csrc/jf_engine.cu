@@ -284,8 +284,6 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     c.w_evict_first = e4 ? atoi(e4) : 1;
     const char* e5 = getenv("JF_FUSE_NORM");
     c.fuse_norm = e5 ? atoi(e5) : 1;
-    const char* e2 = getenv("JF_PREFETCH_TILES");
-    c.prefetch_tiles = e2 ? atoi(e2) : 0;   // measured: no gain from L2 prefetch on B200 (profiles/r01_stage_experiments.txt)
   }
   ALLOC(c.seq_state, c.S_cap, h->bytes_act);
   ALLOC(c.seq_slot, c.S_cap, h->bytes_act);

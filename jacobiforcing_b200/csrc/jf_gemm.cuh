@@ -175,25 +175,6 @@ __device__ __forceinline__ void gemm_produce_w(const GemmTask& t, GemmSmem* gs, 
   }
 }
 
-// ---- warp 0, lane 0: pull the first tiles this CTA will need of the NEXT task into L2 while the SIMT stages run.
-// Weights do not depend on activations, so this is always safe; it only has to stay well inside the 126 MB L2.
-__device__ __forceinline__ void gemm_prefetch_l2(const GemmTask& t, int cta, int nctas, int max_tiles) {
-  const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
-  const int units = t.n_tiles * t.splits;
-  int budget = max_tiles;
-  for (int u = cta; u < units && budget > 0; u += nctas) {
-    const UnitRange r = unit_range(t, u);
-    for (int k = r.k0; k < r.k1 && budget > 0; ++k) {
-      bulk_prefetch_l2(t.W + ((size_t)r.n_tile * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes);
-      --budget;
-      if (dual) {
-        bulk_prefetch_l2(t.W + ((size_t)(r.n_tile + t.n_tiles) * t.k_chunks + k) * (kTileN * kTileK), kWTileBytes);
-        --budget;
-      }
-    }
-  }
-}
-
 // ---- warp 6, lane 0 (after it has seen the grid barrier that publishes X) ----------------------------------------
 __device__ __forceinline__ void gemm_produce_x(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
                                                int slot_bytes, int cta, int nctas, PipeState& pipe) {

@@ -234,7 +234,6 @@ enum Role : int { ROLE_W = 0, ROLE_MMA = 1, ROLE_WORKER = 2, ROLE_X = 3 };
 enum StageId : int { SID_NONE = 0, SID_EMBED = 1, SID_QKV = 2, SID_ROPE = 3, SID_ATTN = 4, SID_COMBINE = 5, SID_O = 6,
                      SID_O_NORM = 7, SID_GU = 8, SID_DOWN = 9, SID_DOWN_NORM = 10, SID_LM = 11, SID_POLICY = 12,
                      SID_O_FUSED = 13, SID_DOWN_FUSED = 14, SID_QKV_FUSED = 15 };
-constexpr int kPrefetchTiles = 24;    // 384 KiB per SM, 57 MB chip-wide: well inside the 126 MB L2
 
 struct IterPlan {
   int T, G, done, n_commit, attn_units, n_lm, want_logits;
@@ -263,12 +262,11 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   // fuse_kind: 0 = plain GEMM stage; 1 / 2 = O / down projection whose split-K reduce + residual + RMSNorm runs as the
   // tail of the epilogue: the CTAs of an n-tile's k-splits wait for each other on the tile's arrival counter and then
   // share its rows (needs one unit per CTA at most: no CTA may owe a second unit while it waits)
-  auto gemm_stage = [&](const GemmTask& t, bool barrier_after, int stage_id, const GemmTask* next = nullptr,
-                        bool xgpu = false, int fuse_kind = 0, const __nv_bfloat16* normw = nullptr) {
+  auto gemm_stage = [&](const GemmTask& t, bool barrier_after, int stage_id, bool xgpu = false, int fuse_kind = 0,
+                        const __nv_bfloat16* normw = nullptr) {
     if (ROLE == ROLE_W) {
       if (c.debug_skip & 16) wait_epoch(c.bar_counter, bs.target(nctas));   // experiment: no run-ahead
       gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, c.w_evict_first != 0, w_policy);
-      if (next != nullptr) gemm_prefetch_l2(*next, cta, nctas, c.prefetch_tiles);
     } else if (ROLE == ROLE_X) {
       wait_epoch(c.bar_counter, bs.target(nctas));
       fence_proxy_async_all();
@@ -399,35 +397,23 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
 
     for (int l = 0; l < md.layers; ++l) {
       const LayerW& lw = c.layer[l];
-      const GemmTask tq = task_qkv(l), to = task_o(l), tg = task_gu(l), td = task_down(l);
-      const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
       if (ROLE == ROLE_WORKER) attention_prefetch(c, ws, l, ip.G, ip.attn_units);
-      gemm_stage(tq, true, SID_QKV, &to);
+      gemm_stage(task_qkv(l), true, SID_QKV);
       JF_SIMT_STAGE_X(false, SID_ROPE, if (!(c.debug_skip & 1)) stage_qkv_rope(c, ws, T, l));
-      JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) {
-        stage_attention(c, ws, l, ip.G, ip.attn_units);
-        if (c.debug_skip & 512) {                          // timing experiment: the same stage again, code and data warm
-          workers_sync(); prof_mark(c, w, 396);
-          stage_attention(c, ws, l, ip.G, ip.attn_units);
-          workers_sync(); prof_mark(c, w, 397);
-        }
-      });
+      JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) stage_attention(c, ws, l, ip.G, ip.attn_units));
       JF_SIMT_STAGE(SID_COMBINE, if (!(c.debug_skip & 4)) stage_attn_combine(c, ws, T));
       if (fuse_o) {
-        gemm_stage(to, true, SID_O_FUSED, &tg, false, 1, lw.ln2);
+        gemm_stage(task_o(l), true, SID_O_FUSED, false, 1, lw.ln2);
       } else {
-        gemm_stage(to, true, SID_O, &tg, tp);
+        gemm_stage(task_o(l), true, SID_O, tp);
         JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, ws, T, false, c.splits_o, lw.ln2, 0));
       }
-      gemm_stage(tg, true, SID_GU, &td);
-      GemmTask tn;
-      const GemmTask* tnp = nullptr;
-      if (l + 1 < md.layers) { tn = task_qkv(l + 1); tnp = &tn; }
-      else if (ip.n_lm > 0) { tn = task_lm(0); tnp = &tn; }
+      gemm_stage(task_gu(l), true, SID_GU);
+      const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
       if (fuse_d) {
-        gemm_stage(td, true, SID_DOWN_FUSED, tnp, false, 2, next_norm);
+        gemm_stage(task_down(l), true, SID_DOWN_FUSED, false, 2, next_norm);
       } else {
-        gemm_stage(td, true, SID_DOWN, tnp, tp);
+        gemm_stage(task_down(l), true, SID_DOWN, tp);
         JF_SIMT_STAGE(SID_DOWN_NORM, stage_rows_norm(c, ws, T, false, c.splits_down, next_norm, 1));
       }
     }
@@ -435,8 +421,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     // LM head: fused bf16-rounded argmax (no logits in HBM); optional fp32 logits for the tolerance checks
     for (int i = 0; i < ip.n_lm; ++i) {
       GemmTask t = task_lm(i);
-      const GemmTask tn = task_qkv(0);               // the next forward's first weights (harmless if there is none)
-      gemm_stage(t, false, SID_LM, (i + 1 == ip.n_lm) ? &tn : nullptr);
+      gemm_stage(t, false, SID_LM);
       if (i == 0 && ip.want_logits) {
         t.out = c.logits - (size_t)t.x_row0 * md.vocab;
         t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = md.vocab; t.out_split_stride = 0;

@@ -157,7 +157,6 @@ struct alignas(16) DevCtx {
   int debug_skip;                    // timing experiments only: bit s = skip the body of SIMT stage s (results invalid)
   int w_evict_first;                 // 1: weight tiles are streamed with the L2 evict_first hint (see jf_ptx.cuh)
   int attn_prefetch;                 // 1: committed K/V of each CTA's first attention unit is fetched during the QKV GEMM
-  int prefetch_tiles;                // weight tiles per SM the W producer pulls into L2 ahead of the next GEMM
 };
 
 enum RunMode : int { RUN_PLAN = 0, RUN_JACOBI = 1 };
