@@ -259,11 +259,11 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   unsigned int fuse_seq[3] = {0u, 0u, 0u};     // fused GEMM stages of each kind executed so far in this launch
 
   auto skip_barrier = [&](bool xgpu) { bs.epoch += 1; if (xgpu) bs.xcount += 1; };
-  // fuse_kind: 0 = plain GEMM stage; 1 / 2 = O / down projection whose split-K reduce + residual + RMSNorm runs as the
-  // tail of the epilogue: the CTAs of an n-tile's k-splits wait for each other on the tile's arrival counter and then
+  // fuse_kind: 0 = plain GEMM stage; 3 = QKV projection with bias + rotary + scatter as its tail; 1 / 2 = O / down
+  // projection whose split-K reduce + residual + RMSNorm runs as the tail of the epilogue: the CTAs of an n-tile's k-splits wait for each other on the tile's arrival counter and then
   // share its rows (needs one unit per CTA at most: no CTA may owe a second unit while it waits)
   auto gemm_stage = [&](const GemmTask& t, bool barrier_after, int stage_id, bool xgpu = false, int fuse_kind = 0,
-                        const __nv_bfloat16* normw = nullptr) {
+                        const __nv_bfloat16* normw = nullptr, int layer = 0) {
     if (ROLE == ROLE_W) {
       if (c.debug_skip & 16) wait_epoch(c.bar_counter, bs.target(nctas));   // experiment: no run-ahead
       gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, c.w_evict_first != 0, w_policy);
@@ -288,13 +288,14 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
             wait_epoch<false>(ctr, fuse_seq[fuse_kind - 1] * (unsigned int)t.splits);   // all k-splits of the tile
           }
           workers_sync();
-          gemm_norm_tail(c, ws, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
+          if (fuse_kind == 3) qkv_rope_tail(c, ws, t.M, layer, n_tile, split, t.splits);
+          else gemm_norm_tail(c, ws, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
         }
       }
     }
     if (barrier_after) {
       if (ROLE == ROLE_WORKER)
-        grid_barrier(c, w, bs, prof_slot, t.epilogue == EPI_SWIGLU_BF16 || fuse_kind != 0, xgpu, stage_id);
+        grid_barrier(c, w, bs, prof_slot, t.epilogue == EPI_SWIGLU_BF16 || fuse_kind == 1 || fuse_kind == 2, xgpu, stage_id);
       else skip_barrier(xgpu);
     }
   };
@@ -355,6 +356,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     const bool fuse_ok = c.fuse_norm != 0 && !tp && T <= kFuseMaxRows;
     const bool fuse_o = fuse_ok && nt_h * c.splits_o <= nctas;
     const bool fuse_d = fuse_ok && nt_h * c.splits_down <= nctas;
+    const bool fuse_q = c.fuse_rope != 0 && T <= kFuseMaxRows && nt_qkv * c.splits_qkv <= nctas && nt_qkv <= kMaxTilesPerKind;
 
     auto base_task = [&]() {
       GemmTask t;
@@ -398,8 +400,12 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     for (int l = 0; l < md.layers; ++l) {
       const LayerW& lw = c.layer[l];
       if (ROLE == ROLE_WORKER) attention_prefetch(c, ws, l, ip.G, ip.attn_units);
-      gemm_stage(task_qkv(l), true, SID_QKV);
-      JF_SIMT_STAGE_X(false, SID_ROPE, if (!(c.debug_skip & 1)) stage_qkv_rope(c, ws, T, l));
+      if (fuse_q) {
+        gemm_stage(task_qkv(l), true, SID_QKV_FUSED, false, 3, nullptr, l);
+      } else {
+        gemm_stage(task_qkv(l), true, SID_QKV);
+        JF_SIMT_STAGE_X(false, SID_ROPE, if (!(c.debug_skip & 1)) stage_qkv_rope(c, ws, T, l));
+      }
       JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) stage_attention(c, ws, l, ip.G, ip.attn_units));
       JF_SIMT_STAGE(SID_COMBINE, if (!(c.debug_skip & 4)) stage_attn_combine(c, ws, T));
       if (fuse_o) {

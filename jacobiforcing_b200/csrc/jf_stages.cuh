@@ -313,17 +313,19 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerShared
 // q/k/v: split-K reduce + bias -> bf16, rotary embedding in bf16 arithmetic, scatter to qbuf / in-flight KV scratch.
 // One warp per (row, head slot); two items are processed together so both items' loads are in flight at once.
 // ---------------------------------------------------------------------------------------------------------------
+// Items are (row, head slot) pairs of the slot range [slot_base, slot_base + nslots); this warp takes items first,
+// first + stride, ...  (stand-alone stage: every slot, warps of the whole grid; fused tail: the slots of one n-tile,
+// the warps of the CTAs that hold the tile's k-splits).
 template <int SPLITS, int PPL>
-__device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& w, int T, int layer) {
+__device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& w, int T, int layer, int first, int stride,
+                                              int slot_base, int nslots) {
   const ModelDims& md = c.md;
   const int d = md.d, half = d >> 1;
-  const int nslots = md.n_q + 2 * md.n_kv;
   const float* bias = c.layer[layer].bqkv;
   const int items = T * nslots;
-  const int stride = w.nctas * 4;
   const size_t sstride = (size_t)c.part_n;
   prof_mark(c, w, 100);
-  for (int item0 = w.cta * 4 + w.wwarp; item0 < items; item0 += 2 * stride) {
+  for (int item0 = first; item0 < items; item0 += 2 * stride) {
     float lo[2][2], hi[2][2];
     int tt[2], slot[2], pos[2];
     const float* p0[2];
@@ -334,7 +336,7 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
       if (item >= items) item = item0;                    // keep the second lane of work well-formed; result unused
       const int t = item / nslots;
       if (tt[q] > 0) tt[q] = t;
-      slot[q] = item - t * nslots;
+      slot[q] = slot_base + item - t * nslots;
       pos[q] = ld_weak(&c.row_pos[t]);
       p0[q] = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane * PPL;
     }
@@ -405,15 +407,37 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
 __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerShared* ws, int T, int layer) {
   const WorkerCtx w = load_wctx(ws);
   const int splits = c.splits_qkv;
+  const int first = w.cta * 4 + w.wwarp, stride = w.nctas * 4, nslots = c.md.n_q + 2 * c.md.n_kv;
 #define JF_ROPE_CASE(S)                                                                   \
   case S:                                                                                 \
-    if (c.md.d == 128) qkv_rope_impl<S, 2>(c, w, T, layer); else qkv_rope_impl<S, 1>(c, w, T, layer); \
+    if (c.md.d == 128) qkv_rope_impl<S, 2>(c, w, T, layer, first, stride, 0, nslots);      \
+    else qkv_rope_impl<S, 1>(c, w, T, layer, first, stride, 0, nslots);                    \
     break;
   switch (splits) {
     JF_ROPE_CASE(1) JF_ROPE_CASE(2) JF_ROPE_CASE(3) JF_ROPE_CASE(4) JF_ROPE_CASE(5) JF_ROPE_CASE(6) JF_ROPE_CASE(7)
-    default:
-      if (c.md.d == 128) qkv_rope_impl<8, 2>(c, w, T, layer); else qkv_rope_impl<8, 1>(c, w, T, layer);
-      break;
+    default: JF_ROPE_CASE(8)
+  }
+#undef JF_ROPE_CASE
+}
+
+// The same bias + rotary + scatter as the TAIL of the QKV GEMM: once every k-split of n-tile `n_tile` has stored its
+// partial sums, the 4 * splits worker warps of those CTAs share the tile's (row, head slot) items.
+__device__ __noinline__ void qkv_rope_tail(const DevCtx& c, const WorkerShared* ws, int T, int layer, int n_tile, int split,
+                                           int splits) {
+  const WorkerCtx w = load_wctx(ws);
+  const int hpt = kTileN / c.md.d;                         // head slots per 128-feature tile (1 or 2)
+  const int slot_base = n_tile * hpt;
+  const int nslots = min(hpt, c.md.n_q + 2 * c.md.n_kv - slot_base);
+  if (nslots <= 0) return;
+  const int first = split * 4 + w.wwarp, stride = splits * 4;
+#define JF_ROPE_CASE(S)                                                                   \
+  case S:                                                                                 \
+    if (c.md.d == 128) qkv_rope_impl<S, 2>(c, w, T, layer, first, stride, slot_base, nslots); \
+    else qkv_rope_impl<S, 1>(c, w, T, layer, first, stride, slot_base, nslots);            \
+    break;
+  switch (splits) {
+    JF_ROPE_CASE(1) JF_ROPE_CASE(2) JF_ROPE_CASE(3) JF_ROPE_CASE(4) JF_ROPE_CASE(5) JF_ROPE_CASE(6) JF_ROPE_CASE(7)
+    default: JF_ROPE_CASE(8)
   }
 #undef JF_ROPE_CASE
 }

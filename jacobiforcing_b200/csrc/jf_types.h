@@ -146,6 +146,7 @@ struct alignas(16) DevCtx {
   // ---- sync
   unsigned int* bar_counter;
   unsigned int* tile_ctr;            // [3][kMaxTilesPerKind] k-split arrivals per n-tile of the fused GEMM stages (zeroed per launch)
+  int fuse_rope;                     // 1: the QKV projection runs bias + rotary + q/k/v scatter as its epilogue tail
   int fuse_norm;                     // 1: O / down projections run reduce + residual + RMSNorm as their epilogue tail
   // ---- optional stage profile: SM-clock stamps taken by CTA 0 after every grid barrier of forward `prof_forward`
   long long* prof;
