@@ -36,6 +36,8 @@ constexpr int kWorkerThreads = 128;
 enum GemmEpilogue : int {
   EPI_PARTIAL_F32 = 0,   // out[slot][m][n] fp32 partial sums (slot = k_split); the consumer stage reduces in slot order
   EPI_SWIGLU_BF16 = 1,   // two accumulators (gate tile, up tile) -> silu(g)*u -> bf16 in packed-X layout
+  EPI_PARTIAL_TAGGED = 3, // the same partial sums as 64-bit {stage tag, fp32 bits} words: the fused tails poll the DATA,
+                          // so no flag / fence / barrier separates the k-splits' stores from their consumers
   EPI_ARGMAX      = 2,   // LM head: bf16-rounded logits, running (max, lowest index) per row -> atomicMax of packed keys
 };
 
@@ -55,6 +57,7 @@ struct GemmTask {
   int epilogue;
   int out_rows_cap;          // SWIGLU: xrows_cap of the destination packed buffer
   int index_offset;          // ARGMAX: added to the local feature index (vocabulary slice of this rank)
+  unsigned int tag;          // PARTIAL_TAGGED: stage tag stored with every partial sum
 };
 
 struct GemmSmem {
@@ -294,6 +297,20 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
           for (int j = 0; j < 16; ++j) {
             const int m = t.x_row0 + m0 + c0 + j;
             if (nvalid && c0 + j < mlive) out[(size_t)m * t.out_row_stride + n] = __uint_as_float(v[j]);
+          }
+        }
+      } else if (t.epilogue == EPI_PARTIAL_TAGGED) {
+        unsigned long long* out = reinterpret_cast<unsigned long long*>(t.out) + (size_t)r.split * t.out_split_stride;
+        const unsigned long long tg = (unsigned long long)t.tag << 32;
+        const bool nvalid = n < t.N;
+        for (int c0 = 0; c0 < mpad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = t.x_row0 + m0 + c0 + j;
+            if (nvalid && c0 + j < mlive) out[(size_t)m * t.out_row_stride + n] = tg | (unsigned long long)v[j];
           }
         }
       } else if (t.epilogue == EPI_SWIGLU_BF16) {

@@ -256,12 +256,12 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   int prof_n = 0;
   int* prof_slot = nullptr;
   const uint64_t w_policy = (ROLE == ROLE_W) ? l2_policy_evict_first() : 0ull;
-  unsigned int fuse_seq[3] = {0u, 0u, 0u};     // fused GEMM stages of each kind executed so far in this launch
 
   auto skip_barrier = [&](bool xgpu) { bs.epoch += 1; if (xgpu) bs.xcount += 1; };
   // fuse_kind: 0 = plain GEMM stage; 3 = QKV projection with bias + rotary + scatter as its tail; 1 / 2 = O / down
-  // projection whose split-K reduce + residual + RMSNorm runs as the tail of the epilogue: the CTAs of an n-tile's k-splits wait for each other on the tile's arrival counter and then
-  // share its rows (needs one unit per CTA at most: no CTA may owe a second unit while it waits)
+  // projection whose split-K reduce + residual + RMSNorm runs as the tail of the epilogue.  The CTAs that hold an
+  // n-tile's k-splits share the tile's rows and poll the tagged partial sums (EPI_PARTIAL_TAGGED) of the other splits
+  // (needs one unit per CTA at most: no CTA may owe a second unit while it polls)
   auto gemm_stage = [&](const GemmTask& t, bool barrier_after, int stage_id, bool xgpu = false, int fuse_kind = 0,
                         const __nv_bfloat16* normw = nullptr, int layer = 0) {
     if (ROLE == ROLE_W) {
@@ -277,20 +277,11 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u);
       ws->tag = w.tag;
       gemm_epilogue(t, gs, cta, nctas, acc);
-      if (fuse_kind != 0) {
-        fuse_seq[fuse_kind - 1] += 1u;
-        if (cta < t.n_tiles * t.splits) {
-          const int n_tile = cta / t.splits, split = cta - n_tile * t.splits;
-          workers_sync();                                 // every worker's partial sums are stored
-          if (w.wtid == 0) {
-            unsigned int* ctr = c.tile_ctr + (fuse_kind - 1) * kMaxTilesPerKind + n_tile;
-            red_release_gpu_add_u32(ctr, 1u);
-            wait_epoch<false>(ctr, fuse_seq[fuse_kind - 1] * (unsigned int)t.splits);   // all k-splits of the tile
-          }
-          workers_sync();
-          if (fuse_kind == 3) qkv_rope_tail(c, ws, t.M, layer, n_tile, split, t.splits);
-          else gemm_norm_tail(c, ws, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
-        }
+      if (fuse_kind != 0 && cta < t.n_tiles * t.splits) {
+        // no flag, fence or barrier: the tails poll the tagged partial sums themselves
+        const int n_tile = cta / t.splits, split = cta - n_tile * t.splits;
+        if (fuse_kind == 3) qkv_rope_tail(c, ws, t.M, layer, n_tile, split, t.splits);
+        else gemm_norm_tail(c, ws, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
       }
     }
     if (barrier_after) {
@@ -360,20 +351,23 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
 
     auto base_task = [&]() {
       GemmTask t;
+      t.tag = 0u;
       t.M = T; t.x_row0 = 0; t.xrows_cap = c.xrows_cap; t.out_rows_cap = c.xrows_cap; t.index_offset = 0;
       t.out_row_stride = c.part_splits * c.part_n; t.out_split_stride = c.part_n;
       return t;
     };
-    auto task_qkv = [&](int l) {      // QKV projection (split-K partial sums)
+    auto task_qkv = [&](int l, bool fused = false) {      // QKV projection (split-K partial sums)
       GemmTask t = base_task();
       t.W = c.layer[l].wqkv; t.X = c.xn; t.out = c.part; t.n_tiles = nt_qkv; t.k_chunks = kc_h; t.splits = c.splits_qkv;
       t.N = md.qkv_dim; t.epilogue = EPI_PARTIAL_F32;
+      if (fused) { t.out = c.tpart; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); }
       return t;
     };
-    auto task_o = [&](int l) {
+    auto task_o = [&](int l, bool fused = false) {
       GemmTask t = base_task();
       t.W = c.layer[l].wo; t.X = c.xa; t.out = c.part_rs[0]; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
       t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
+      if (fused) { t.out = c.tpart_rs[0]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); }
       return t;
     };
     auto task_gu = [&](int l) {       // gate/up projection with the SwiGLU epilogue
@@ -382,10 +376,11 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       t.N = md.inter; t.epilogue = EPI_SWIGLU_BF16;
       return t;
     };
-    auto task_down = [&](int l) {
+    auto task_down = [&](int l, bool fused = false) {
       GemmTask t = base_task();
       t.W = c.layer[l].wd; t.X = c.xact; t.out = c.part_rs[1]; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
       t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
+      if (fused) { t.out = c.tpart_rs[1]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); }
       return t;
     };
     auto task_lm = [&](int i) {
@@ -401,7 +396,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       const LayerW& lw = c.layer[l];
       if (ROLE == ROLE_WORKER) attention_prefetch(c, ws, l, ip.G, ip.attn_units);
       if (fuse_q) {
-        gemm_stage(task_qkv(l), true, SID_QKV_FUSED, false, 3, nullptr, l);
+        gemm_stage(task_qkv(l, true), true, SID_QKV_FUSED, false, 3, nullptr, l);
       } else {
         gemm_stage(task_qkv(l), true, SID_QKV);
         JF_SIMT_STAGE_X(false, SID_ROPE, if (!(c.debug_skip & 1)) stage_qkv_rope(c, ws, T, l));
@@ -409,7 +404,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) stage_attention(c, ws, l, ip.G, ip.attn_units));
       JF_SIMT_STAGE(SID_COMBINE, if (!(c.debug_skip & 4)) stage_attn_combine(c, ws, T));
       if (fuse_o) {
-        gemm_stage(task_o(l), true, SID_O_FUSED, false, 1, lw.ln2);
+        gemm_stage(task_o(l, true), true, SID_O_FUSED, false, 1, lw.ln2);
       } else {
         gemm_stage(task_o(l), true, SID_O, tp);
         JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, ws, T, false, c.splits_o, lw.ln2, 0));
@@ -417,7 +412,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       gemm_stage(task_gu(l), true, SID_GU);
       const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
       if (fuse_d) {
-        gemm_stage(task_down(l), true, SID_DOWN_FUSED, false, 2, next_norm);
+        gemm_stage(task_down(l, true), true, SID_DOWN_FUSED, false, 2, next_norm);
       } else {
         gemm_stage(task_down(l), true, SID_DOWN, tp);
         JF_SIMT_STAGE(SID_DOWN_NORM, stage_rows_norm(c, ws, T, false, c.splits_down, next_norm, 1));

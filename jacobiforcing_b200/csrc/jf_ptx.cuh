@@ -252,6 +252,19 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c
 template <typename T>
 __device__ __forceinline__ T ld_weak(const T* p) { return *p; }
 
+// Polling loads of data another SM is writing: served by L2 (never this SM's possibly stale L1) and `volatile`, so the
+// compiler re-issues them on every iteration of a polling loop.  Unlike ld.relaxed / ld.acquire they pipeline freely.
+__device__ __forceinline__ ulonglong2 ld_cg_poll_u64x2(const unsigned long long* p) {
+  ulonglong2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_cg_poll_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 }  // namespace jf

@@ -81,6 +81,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // load in flight at once); every slice publishes the sums of squares of its 128-column tiles, polls the row's other
 // tiles and normalises its own columns.
 // ---------------------------------------------------------------------------------------------------------------
+// Tagged partial sums (EPI_PARTIAL_TAGGED): a 64-bit word carries {stage tag, fp32 bits}, so the consumer polls the data
+// itself with L2 (.cg) loads until every word it needs has the tag of the stage in flight - one L2 round trip between the
+// producers' stores and the consumer, instead of store -> fence -> flag -> poll -> fence -> load.
+__device__ __forceinline__ bool tagged_ok(unsigned long long wd, unsigned int tag) { return (unsigned int)(wd >> 32) == tag; }
+__device__ __forceinline__ float tagged_val(unsigned long long wd) { return __uint_as_float((unsigned int)(wd & 0xffffffffull)); }
+
 // Canonical row statistic (identical in the stand-alone stage and in the fused GEMM tail, so a row's RMSNorm does not
 // depend on which of the two produced it): every 128-column tile publishes its sum of squares - 8 columns per lane
 // added in column order, then a 16-lane xor tree - as one tagged 64-bit word {stage tag, value}; a single relaxed
@@ -198,7 +204,7 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
 // `it` (8 rows: one per half-warp) belongs to split it % SPLITS - and each owns the tile's 128 columns of its rows
 // (8 columns per lane).  The arithmetic (split order, rounding points, the canonical row statistic) is that of
 // rows_norm_impl, bit for bit.
-constexpr int kFuseMaxRows = 64;
+constexpr int kFuseMaxRows = kFuseRows;
 template <int SPLITS>
 __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerShared* ws, int T, int n_tile, int split,
                                                  const __nv_bfloat16* normw, int which) {
@@ -211,8 +217,8 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
   const bool cvalid = v < (h >> 3);
   const int nit = (T + 7) >> 3;
   if (split >= nit) return;
-  const size_t sstride4 = (size_t)h >> 2;
-  const float* src = c.part_rs[which];
+  const size_t sstride2 = (size_t)h >> 1;                  // 16-byte vectors between the k-split slices of a row
+  const unsigned long long* tsrc = c.tpart_rs[which];
   uint4 xs[MAXJ];
   uint4 wraw = make_uint4(0u, 0u, 0u, 0u);
   if (cvalid) wraw = __ldg(reinterpret_cast<const uint4*>(normw) + v);
@@ -223,23 +229,29 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     if (it < nit) {
       const int t = it * 8 + w.wwarp * 2 + hw;
       uint4 rr = make_uint4(0u, 0u, 0u, 0u);
-      float4 pa[SPLITS], pb[SPLITS];
-#pragma unroll
-      for (int s2 = 0; s2 < SPLITS; ++s2) { pa[s2] = make_float4(0.f, 0.f, 0.f, 0.f); pb[s2] = pa[s2]; }
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (t < T && cvalid) {
         rr = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
-        const float4* p = reinterpret_cast<const float4*>(src + (size_t)t * c.part_splits * h) + v * 2;
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8);
+        ulonglong2 wd[SPLITS][4];
+        const long long t0 = clock64();
+        for (;;) {                                          // every split's 8 words in flight, then one check
+          bool ok = true;
 #pragma unroll
-        for (int s2 = 0; s2 < SPLITS; ++s2) {
-          pa[s2] = ld_weak(p + s2 * sstride4);
-          pb[s2] = ld_weak(p + s2 * sstride4 + 1);
+          for (int s2 = 0; s2 < SPLITS; ++s2)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wd[s2][k] = ld_cg_poll_u64x2(reinterpret_cast<const unsigned long long*>(p + (size_t)s2 * sstride2 + k));
+#pragma unroll
+          for (int s2 = 0; s2 < SPLITS; ++s2)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
+          if (ok) break;
+          if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
         }
-      }
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int s2 = 0; s2 < SPLITS; ++s2) {
-        acc[0] += pa[s2].x; acc[1] += pa[s2].y; acc[2] += pa[s2].z; acc[3] += pa[s2].w;
-        acc[4] += pb[s2].x; acc[5] += pb[s2].y; acc[6] += pb[s2].z; acc[7] += pb[s2].w;
+        for (int s2 = 0; s2 < SPLITS; ++s2)                 // split order: deterministic
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { acc[2 * k] += tagged_val(wd[s2][k].x); acc[2 * k + 1] += tagged_val(wd[s2][k].y); }
       }
       float r[8], x[8];
       unpack8(rr, r);
@@ -316,7 +328,7 @@ __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerShared
 // Items are (row, head slot) pairs of the slot range [slot_base, slot_base + nslots); this warp takes items first,
 // first + stride, ...  (stand-alone stage: every slot, warps of the whole grid; fused tail: the slots of one n-tile,
 // the warps of the CTAs that hold the tile's k-splits).
-template <int SPLITS, int PPL>
+template <int SPLITS, int PPL, bool TAGGED>
 __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& w, int T, int layer, int first, int stride,
                                               int slot_base, int nslots) {
   const ModelDims& md = c.md;
@@ -340,7 +352,48 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
       pos[q] = ld_weak(&c.row_pos[t]);
       p0[q] = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane * PPL;
     }
-    if (PPL == 2) {
+    if (TAGGED) {
+      // fused tail: poll the tagged partial sums (2 * PPL words per item and split) until all of them are this stage's
+      const unsigned long long* tp[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        tp[q] = c.tpart + (size_t)(tt[q] < 0 ? 0 : tt[q]) * c.part_splits * c.part_n + slot[q] * d + w.lane * PPL;
+      unsigned long long wl[2][SPLITS][PPL], wh[2][SPLITS][PPL];
+      const long long t0 = clock64();
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int s2 = 0; s2 < SPLITS; ++s2) {
+            if constexpr (PPL == 2) {
+              const ulonglong2 a = ld_cg_poll_u64x2(tp[q] + s2 * sstride);
+              const ulonglong2 b = ld_cg_poll_u64x2(tp[q] + s2 * sstride + half);
+              wl[q][s2][0] = a.x; wl[q][s2][PPL - 1] = a.y; wh[q][s2][0] = b.x; wh[q][s2][PPL - 1] = b.y;
+            } else {
+              wl[q][s2][0] = ld_cg_poll_u64(tp[q] + s2 * sstride);
+              wh[q][s2][0] = ld_cg_poll_u64(tp[q] + s2 * sstride + half);
+            }
+          }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int s2 = 0; s2 < SPLITS; ++s2)
+#pragma unroll
+            for (int j = 0; j < PPL; ++j)
+              ok = ok && (tt[q] < 0 || (tagged_ok(wl[q][s2][j], w.tag) && tagged_ok(wh[q][s2][j], w.tag)));
+        if (ok) break;
+        if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        lo[q][0] = lo[q][1] = hi[q][0] = hi[q][1] = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < SPLITS; ++s2)               // slice order: deterministic
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) { lo[q][j] += tagged_val(wl[q][s2][j]); hi[q][j] += tagged_val(wh[q][s2][j]); }
+      }
+    } else if (PPL == 2) {
       float2 vl[2][SPLITS], vh[2][SPLITS];
 #pragma unroll
       for (int q = 0; q < 2; ++q)
@@ -410,8 +463,8 @@ __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerShared*
   const int first = w.cta * 4 + w.wwarp, stride = w.nctas * 4, nslots = c.md.n_q + 2 * c.md.n_kv;
 #define JF_ROPE_CASE(S)                                                                   \
   case S:                                                                                 \
-    if (c.md.d == 128) qkv_rope_impl<S, 2>(c, w, T, layer, first, stride, 0, nslots);      \
-    else qkv_rope_impl<S, 1>(c, w, T, layer, first, stride, 0, nslots);                    \
+    if (c.md.d == 128) qkv_rope_impl<S, 2, false>(c, w, T, layer, first, stride, 0, nslots); \
+    else qkv_rope_impl<S, 1, false>(c, w, T, layer, first, stride, 0, nslots);                    \
     break;
   switch (splits) {
     JF_ROPE_CASE(1) JF_ROPE_CASE(2) JF_ROPE_CASE(3) JF_ROPE_CASE(4) JF_ROPE_CASE(5) JF_ROPE_CASE(6) JF_ROPE_CASE(7)
@@ -432,8 +485,8 @@ __device__ __noinline__ void qkv_rope_tail(const DevCtx& c, const WorkerShared* 
   const int first = split * 4 + w.wwarp, stride = splits * 4;
 #define JF_ROPE_CASE(S)                                                                   \
   case S:                                                                                 \
-    if (c.md.d == 128) qkv_rope_impl<S, 2>(c, w, T, layer, first, stride, slot_base, nslots); \
-    else qkv_rope_impl<S, 1>(c, w, T, layer, first, stride, slot_base, nslots);            \
+    if (c.md.d == 128) qkv_rope_impl<S, 2, true>(c, w, T, layer, first, stride, slot_base, nslots); \
+    else qkv_rope_impl<S, 1, true>(c, w, T, layer, first, stride, slot_base, nslots);            \
     break;
   switch (splits) {
     JF_ROPE_CASE(1) JF_ROPE_CASE(2) JF_ROPE_CASE(3) JF_ROPE_CASE(4) JF_ROPE_CASE(5) JF_ROPE_CASE(6) JF_ROPE_CASE(7)
