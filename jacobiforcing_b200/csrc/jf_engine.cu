@@ -305,7 +305,7 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.part, (size_t)c.T_cap * c.part_splits * c.part_n, h->bytes_act);
   ALLOC(c.part_rs[0], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.part_rs[1], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
-  ALLOC(c.tpart, (size_t)kFuseRows * c.part_splits * c.part_n, h->bytes_act);
+  ALLOC(c.tpart, (size_t)kFuseRopeRows * c.part_splits * c.part_n, h->bytes_act);
   ALLOC(c.tpart_rs[0], (size_t)kFuseRows * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.tpart_rs[1], (size_t)kFuseRows * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.attn_ml, (size_t)c.attn_slots_cap * md.n_q * 2, h->bytes_act);

@@ -204,85 +204,129 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
 // `it` (8 rows: one per half-warp) belongs to split it % SPLITS - and each owns the tile's 128 columns of its rows
 // (8 columns per lane).  The arithmetic (split order, rounding points, the canonical row statistic) is that of
 // rows_norm_impl, bit for bit.
-constexpr int kFuseMaxRows = kFuseRows;
 template <int SPLITS>
 __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerShared* ws, int T, int n_tile, int split,
                                                  const __nv_bfloat16* normw, int which) {
   const WorkerCtx w = load_wctx(ws);
-  constexpr int MAXJ = (kFuseMaxRows / 8 + SPLITS - 1) / SPLITS;     // row steps one split may own
+  constexpr int MW = kMaxHTiles / 16;                      // statistic words one lane may poll per row
   const int h = c.md.h;
   const int nt_h = (h + 127) >> 7;
   const int l16 = w.lane & 15, hw = w.lane >> 4;
   const int v = n_tile * 16 + l16;                       // 16-byte chunk of the row
   const bool cvalid = v < (h >> 3);
   const int nit = (T + 7) >> 3;
+  prof_mark(c, w, 500);
   if (split >= nit) return;
-  const size_t sstride2 = (size_t)h >> 1;                  // 16-byte vectors between the k-split slices of a row
+  const size_t sstride = (size_t)h;                        // words between the k-split slices of a row
   const unsigned long long* tsrc = c.tpart_rs[which];
-  uint4 xs[MAXJ];
+  const int trow = w.wwarp * 2 + hw;                       // this half-warp's row inside a step
   uint4 wraw = make_uint4(0u, 0u, 0u, 0u);
   if (cvalid) wraw = __ldg(reinterpret_cast<const uint4*>(normw) + v);
+  // phase 1, per row step: poll the tagged partial sums, add the residual, store the row, publish the tile statistic
+  for (int it = split; it < nit; it += SPLITS) {
+    const int t = it * 8 + trow;
+    const bool live = t < T && cvalid;
+    uint4 rr = make_uint4(0u, 0u, 0u, 0u);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      rr = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
+      const unsigned long long* p = tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8;
+      ulonglong2 wd[SPLITS][4];
+      const long long t0 = clock64();
+      for (;;) {                                            // every split's 8 words in flight, then one check
+        bool ok = true;
 #pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    const int it = split + j * SPLITS;
-    xs[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (it < nit) {
-      const int t = it * 8 + w.wwarp * 2 + hw;
-      uint4 rr = make_uint4(0u, 0u, 0u, 0u);
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (t < T && cvalid) {
-        rr = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
-        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8);
-        ulonglong2 wd[SPLITS][4];
-        const long long t0 = clock64();
-        for (;;) {                                          // every split's 8 words in flight, then one check
-          bool ok = true;
+        for (int s2 = 0; s2 < SPLITS; ++s2)
 #pragma unroll
-          for (int s2 = 0; s2 < SPLITS; ++s2)
+          for (int k = 0; k < 4; ++k) wd[s2][k] = ld_cg_poll_u64x2(p + s2 * sstride + 2 * k);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) wd[s2][k] = ld_cg_poll_u64x2(reinterpret_cast<const unsigned long long*>(p + (size_t)s2 * sstride2 + k));
+        for (int s2 = 0; s2 < SPLITS; ++s2)
 #pragma unroll
-          for (int s2 = 0; s2 < SPLITS; ++s2)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
-          if (ok) break;
-          if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
-        }
-#pragma unroll
-        for (int s2 = 0; s2 < SPLITS; ++s2)                 // split order: deterministic
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { acc[2 * k] += tagged_val(wd[s2][k].x); acc[2 * k + 1] += tagged_val(wd[s2][k].y); }
+          for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
+        if (ok) break;
+        if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
       }
-      float r[8], x[8];
-      unpack8(rr, r);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) x[q] = bf16_round(r[q] + bf16_round(acc[q]));
-      xs[j] = pack8(x);
-      if (t < T && cvalid) reinterpret_cast<uint4*>(c.hidden + (size_t)t * h)[v] = xs[j];
-      const float tile_ss = halfwarp_tree(sumsq8(x));
-      if (l16 == 0 && t < T) publish_tile_ss(c, t, n_tile, w.tag, tile_ss);
+      for (int s2 = 0; s2 < SPLITS; ++s2)                   // split order: deterministic
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[2 * k] += tagged_val(wd[s2][k].x); acc[2 * k + 1] += tagged_val(wd[s2][k].y); }
     }
+    prof_mark(c, w, 501);
+    float r[8], x[8];
+    unpack8(rr, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = bf16_round(r[e] + bf16_round(acc[e]));
+    if (live) reinterpret_cast<uint4*>(c.hidden + (size_t)t * h)[v] = pack8(x);
+    const float tile_ss = halfwarp_tree(sumsq8(x));
+    if (l16 == 0 && t < T) publish_tile_ss(c, t, n_tile, w.tag, tile_ss);
+    prof_mark(c, w, 502);
   }
+  // phase 2, four row steps at a time: the statistic words of all four rows are polled together (one round trip when
+  // they are there) and added per row in the canonical order (lane l: tiles l, l+16, ...; 16-lane xor tree); the row
+  // itself is read back from `hidden` (this thread's own store) in the same round trip
   float wt[8];
   unpack8(wraw, wt);
+  for (int it0 = split; it0 < nit; it0 += 4 * SPLITS) {
+    uint4 xr[4];
+    unsigned long long sw[4][MW];
 #pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    const int it = split + j * SPLITS;
-    if (it < nit) {
-      const int t = it * 8 + w.wwarp * 2 + hw;
-      const float total = row_total_canonical(c, t, nt_h, w.tag, l16, t < T);
-      if (t < T && cvalid) {
-        const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
-        float x[8], o[8];
-        unpack8(xs[j], x);
+    for (int j = 0; j < 4; ++j) {
+      const int t = (it0 + j * SPLITS) * 8 + trow;
+      xr[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (t < T && cvalid) xr[j] = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
+    }
+    const long long t0 = clock64();
+    for (;;) {
+      bool ok = true;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = wt[q] * bf16_round(x[q] * rstd);
-        uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(v >> 3) * c.xrows_cap + t) * 128 +
-                       (((v & 7) ^ (t & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = pack8(o);
+      for (int j = 0; j < 4; ++j) {
+        const int t = (it0 + j * SPLITS) * 8 + trow;
+        if (t < T) {
+          const unsigned long long* slots = c.row_ss + (size_t)t * kMaxHTiles;
+#pragma unroll
+          for (int m = 0; m < MW; ++m)
+            if (l16 + 16 * m < nt_h) sw[j][m] = ld_relaxed_gpu_u64(slots + l16 + 16 * m);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = (it0 + j * SPLITS) * 8 + trow;
+        if (t < T) {
+#pragma unroll
+          for (int m = 0; m < MW; ++m)
+            if (l16 + 16 * m < nt_h) ok = ok && tagged_ok(sw[j][m], w.tag);
+        }
+      }
+      if (ok) break;
+      if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+    }
+    prof_mark(c, w, 503);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int it = it0 + j * SPLITS;
+      const int t = it * 8 + trow;
+      if (it < nit) {                                       // whole warps take part in the reduction of their rows
+        float pj = 0.f;
+        if (t < T) {
+#pragma unroll
+          for (int m = 0; m < MW; ++m)
+            if (l16 + 16 * m < nt_h) pj += tagged_val(sw[j][m]);
+        }
+        const float total = halfwarp_tree(pj);
+        if (t < T && cvalid) {
+          const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
+          float x[8], o[8];
+          unpack8(xr[j], x);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = wt[e] * bf16_round(x[e] * rstd);
+          uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(v >> 3) * c.xrows_cap + t) * 128 +
+                         (((v & 7) ^ (t & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = pack8(o);
+        }
       }
     }
   }
+  prof_mark(c, w, 504);
 }
 
 __device__ __forceinline__ void gemm_norm_tail(const DevCtx& c, const WorkerShared* w, int T, int n_tile, int split,

@@ -13,7 +13,8 @@ constexpr int kMaxLmTasks  = 16;     // LM-head row tiles of kArgmaxRows per for
 constexpr int kQTokPerUnit = 64;     // query tokens one attention unit covers
 constexpr int kMaxHTiles   = 64;     // 128-column tiles of a hidden row (h <= 8192)
 constexpr int kMaxTilesPerKind = 128; // arrival counters per fused GEMM kind (O, down, QKV)
-constexpr int kFuseRows    = 64;     // forwards of at most this many rows run the fused (tagged-partial) GEMM tails
+constexpr int kFuseRopeRows = 64;    // forwards of at most this many rows run the fused QKV + rotary tail
+constexpr int kFuseRows    = 320;    // row capacity of the tagged partial buffers of the fused O / down tails
 constexpr int kMaxTP       = 8;      // tensor-parallel ranks whose buffers one kernel may address (NVLink peers)
 
 struct ModelDims {
@@ -101,7 +102,7 @@ struct alignas(16) DevCtx {
   float* part;                       // [T_cap][part_splits][part_n] split-K partial sums, row-major by ROW so the live
                                      // rows of a forward share a few 2 MB pages (TLB reach matters: see DESIGN.md)
   int part_splits, part_n;
-  unsigned long long* tpart;         // [kFuseRows][part_splits][part_n] tagged {stage tag, fp32} partial sums of the fused QKV stage
+  unsigned long long* tpart;         // [kFuseRopeRows][part_splits][part_n] tagged {stage tag, fp32} partial sums of the fused QKV stage
   unsigned long long* tpart_rs[2];   // [kFuseRows][part_splits][h] the same for the fused O / down stages
   float* part_rs[2];                 // [T_cap][part_splits][h]: partials of the row-split GEMMs (0 = O, 1 = down); with
                                      // tensor parallelism the peers read them over NVLink, hence double-buffered

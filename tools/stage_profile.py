@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--gen", type=int, default=128)
     ap.add_argument("--n", type=int, default=32)
     ap.add_argument("--prompt", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--mode", default="single")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "stage_profile.json"))
     a = ap.parse_args()
     import torch
@@ -34,16 +36,16 @@ def main():
         group = dist.group.WORLD
     cfg = bench.SHAPES[a.model]
     pages = (a.prompt + a.gen + 3 * a.n + 255) // 256 + 1
-    rt = JacobiRuntime(cfg, device=rank, max_rows=max(a.prompt + a.n, 64), max_seqs=1, num_kv_pages=pages,
-                       max_pages_per_seq=pages, gen_capacity=a.prompt + a.gen + 4 * a.n + 8, tp_rank=rank, tp_size=world,
-                       tp_group=group)
+    rt = JacobiRuntime(cfg, device=rank, max_rows=max(a.prompt + a.n, 64, a.batch * a.n * 5), max_seqs=a.batch,
+                       num_kv_pages=pages * a.batch, max_pages_per_seq=pages, gen_capacity=a.prompt + a.gen + 4 * a.n + 8,
+                       tp_rank=rank, tp_size=world, tp_group=group)
     bench.load_random_weights(rt, cfg, 1234, f"cuda:{rank}")
     g = torch.Generator().manual_seed(1)
-    prompt = torch.randint(0, cfg["vocab_size"], (a.prompt,), generator=g).tolist()
+    prompts = [torch.randint(0, cfg["vocab_size"], (a.prompt,), generator=g).tolist() for _ in range(a.batch)]
     for rep in range(2):
         rt.profile_enable(a.forward if rep == 1 else -1)
-        seqs, results, run = hf_generate(rt, [prompt], n=a.n, max_new_tokens=a.gen, mode="single", pad=0,
-                                         rngs=[random.Random(2)])
+        seqs, results, run = hf_generate(rt, prompts, n=a.n, max_new_tokens=a.gen, mode=a.mode, pad=0, K=2, r=0.85,
+                                         n_gram_pool_size=4, rngs=[random.Random(2 + i) for i in range(a.batch)])
         for s in seqs:
             rt.release(s)
     if rank != 0:
