@@ -26,6 +26,10 @@ QWEN_SHAPES: Dict[str, dict] = {
     "tiny128": dict(hidden_size=512, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=1,
                     head_dim=128, intermediate_size=1152, vocab_size=2048, tie_word_embeddings=False,
                     rope_theta=1e4, max_position_embeddings=4096),
+    # small but with several k-splits per GEMM (QKV 4, O 4, down 8 on 148 SMs): exercises the fused split-K tails
+    "mid128": dict(hidden_size=1024, num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=2,
+                   head_dim=128, intermediate_size=2048, vocab_size=2048, tie_word_embeddings=False,
+                   rope_theta=1e6, max_position_embeddings=4096),
     "qwen2-0.5b": dict(hidden_size=896, num_hidden_layers=24, num_attention_heads=14, num_key_value_heads=2,
                        head_dim=64, intermediate_size=4864, vocab_size=151936, tie_word_embeddings=True,
                        rope_theta=1e6, max_position_embeddings=32768),
