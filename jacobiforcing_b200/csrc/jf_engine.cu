@@ -332,6 +332,7 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   h->arena_mode = 0;
   for (int r2 = 0; r2 < kMaxTP; ++r2) {            // until jf_tp_import: every 'peer' is this rank itself
     c.peer_part_rs[r2][0] = c.part_rs[0]; c.peer_part_rs[r2][1] = c.part_rs[1];
+    c.peer_tpart_rs[r2][0] = c.tpart_rs[0]; c.peer_tpart_rs[r2][1] = c.tpart_rs[1];
     c.peer_keys[r2] = c.argmax_keys; c.peer_xflag[r2] = c.xflag;
   }
   if ((rc = dev_alloc(h, &h->stage, h->stage_elems, (int64_t*)nullptr)) != JF_OK) return fail(rc, h->err);
@@ -399,6 +400,8 @@ extern "C" int jf_tp_import(jf_handle h, const void* handles) {
     // every rank lays its arena out identically, so a peer's buffer sits at the same offset
     c.peer_part_rs[r][0] = reinterpret_cast<const float*>(base + (reinterpret_cast<const uint8_t*>(c.part_rs[0]) - mine));
     c.peer_part_rs[r][1] = reinterpret_cast<const float*>(base + (reinterpret_cast<const uint8_t*>(c.part_rs[1]) - mine));
+    c.peer_tpart_rs[r][0] = reinterpret_cast<const unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.tpart_rs[0]) - mine));
+    c.peer_tpart_rs[r][1] = reinterpret_cast<const unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.tpart_rs[1]) - mine));
     c.peer_keys[r] = reinterpret_cast<const unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.argmax_keys) - mine));
     c.peer_xflag[r] = reinterpret_cast<unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.xflag) - mine));
   }

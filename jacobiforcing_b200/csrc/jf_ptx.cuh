@@ -259,6 +259,14 @@ __device__ __forceinline__ ulonglong2 ld_cg_poll_u64x2(const unsigned long long*
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
+// Against a tensor-parallel peer's memory (NVLink) strong loads are served one at a time (~2 us each, measured), so
+// the peers' words are fetched with WEAK loads - they pipeline - and a failed tag check is followed by a system-scope
+// acquire fence (which also drops this SM's L1 copies) before the next attempt.
+__device__ __forceinline__ ulonglong2 ld_weak_poll_u64x2(const unsigned long long* p) {
+  ulonglong2 v;
+  asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long ld_cg_poll_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

@@ -204,7 +204,10 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
 // `it` (8 rows: one per half-warp) belongs to split it % SPLITS - and each owns the tile's 128 columns of its rows
 // (8 columns per lane).  The arithmetic (split order, rounding points, the canonical row statistic) is that of
 // rows_norm_impl, bit for bit.
-template <int SPLITS>
+// TP = tensor-parallel ranks: the row-split GEMM of every rank holds SPLITS partial sums of its K shard; every rank adds
+// all TP * SPLITS of them in (rank, split) order (its own from local memory, the peers' over NVLink), so all ranks end
+// with bit-identical rows and no cross-GPU barrier separates the projection from its consumers.
+template <int SPLITS, int TP>
 __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerShared* ws, int T, int n_tile, int split,
                                                  const __nv_bfloat16* normw, int which) {
   const WorkerCtx w = load_wctx(ws);
@@ -230,26 +233,32 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (live) {
       rr = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
-      const unsigned long long* p = tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8;
-      ulonglong2 wd[SPLITS][4];
-      const long long t0 = clock64();
-      for (;;) {                                            // every split's 8 words in flight, then one check
-        bool ok = true;
+#pragma unroll
+      for (int rk = 0; rk < TP; ++rk) {                     // rank order, then split order: deterministic
+        const unsigned long long* p = ((TP == 1) ? tsrc : c.peer_tpart_rs[rk][which]) +
+                                      ((size_t)t * c.part_splits) * h + (size_t)v * 8;
+        ulonglong2 wd[SPLITS][4];
+        const long long t0 = clock64();
+        for (;;) {                                          // every split's 8 words in flight, then one check
+          bool ok = true;
+#pragma unroll
+          for (int s2 = 0; s2 < SPLITS; ++s2)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              wd[s2][k] = (TP == 1) ? ld_cg_poll_u64x2(p + s2 * sstride + 2 * k) : ld_weak_poll_u64x2(p + s2 * sstride + 2 * k);
+#pragma unroll
+          for (int s2 = 0; s2 < SPLITS; ++s2)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
+          if (ok) break;
+          if (TP > 1) fence_acq_rel_sys();
+          if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+        }
 #pragma unroll
         for (int s2 = 0; s2 < SPLITS; ++s2)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) wd[s2][k] = ld_cg_poll_u64x2(p + s2 * sstride + 2 * k);
-#pragma unroll
-        for (int s2 = 0; s2 < SPLITS; ++s2)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
-        if (ok) break;
-        if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+          for (int k = 0; k < 4; ++k) { acc[2 * k] += tagged_val(wd[s2][k].x); acc[2 * k + 1] += tagged_val(wd[s2][k].y); }
       }
-#pragma unroll
-      for (int s2 = 0; s2 < SPLITS; ++s2)                   // split order: deterministic
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { acc[2 * k] += tagged_val(wd[s2][k].x); acc[2 * k + 1] += tagged_val(wd[s2][k].y); }
     }
     prof_mark(c, w, 501);
     float r[8], x[8];
@@ -331,10 +340,23 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
 
 __device__ __forceinline__ void gemm_norm_tail(const DevCtx& c, const WorkerShared* w, int T, int n_tile, int split,
                                             int splits, const __nv_bfloat16* normw, int which) {
-#define JF_TAIL_CASE(S) case S: gemm_norm_tail_impl<S>(c, w, T, n_tile, split, normw, which); break;
-  switch (splits) {
-    JF_TAIL_CASE(1) JF_TAIL_CASE(2) JF_TAIL_CASE(3) JF_TAIL_CASE(4) JF_TAIL_CASE(5) JF_TAIL_CASE(6) JF_TAIL_CASE(7)
-    default: gemm_norm_tail_impl<8>(c, w, T, n_tile, split, normw, which); break;
+#define JF_TAIL_CASE(S, TPN) case S: gemm_norm_tail_impl<S, TPN>(c, w, T, n_tile, split, normw, which); break;
+  if (c.tp_size == 1) {
+    switch (splits) {
+      JF_TAIL_CASE(1, 1) JF_TAIL_CASE(2, 1) JF_TAIL_CASE(3, 1) JF_TAIL_CASE(4, 1) JF_TAIL_CASE(5, 1) JF_TAIL_CASE(6, 1)
+      JF_TAIL_CASE(7, 1)
+      default: gemm_norm_tail_impl<8, 1>(c, w, T, n_tile, split, normw, which); break;
+    }
+  } else if (c.tp_size == 2) {                 // splits are capped at 4 (tp 2) / 2 (tp 4) when the engine is created
+    switch (splits) {
+      JF_TAIL_CASE(1, 2) JF_TAIL_CASE(2, 2) JF_TAIL_CASE(3, 2)
+      default: gemm_norm_tail_impl<4, 2>(c, w, T, n_tile, split, normw, which); break;
+    }
+  } else {
+    switch (splits) {
+      JF_TAIL_CASE(1, 4)
+      default: gemm_norm_tail_impl<2, 4>(c, w, T, n_tile, split, normw, which); break;
+    }
   }
 #undef JF_TAIL_CASE
 }

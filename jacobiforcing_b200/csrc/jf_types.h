@@ -143,6 +143,7 @@ struct alignas(16) DevCtx {
   // read straight out of the peers' memory (CUDA IPC mappings), cross-GPU barriers are flags in peer memory
   int tp_rank, tp_size;
   const float* peer_part_rs[kMaxTP][2];
+  const unsigned long long* peer_tpart_rs[kMaxTP][2];   // the peers' tagged partial buffers (fused tails under tensor parallelism)
   const unsigned long long* peer_keys[kMaxTP];
   unsigned long long* peer_xflag[kMaxTP];     // rank r's flag array (this rank writes element [tp_rank])
   unsigned long long* xflag;                  // own flag array [kMaxTP]
