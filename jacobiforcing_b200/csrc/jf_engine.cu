@@ -216,6 +216,12 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   c.splits_qkv = pick_splits(nt_qkv, kc_h, h->sm_count);
   c.splits_o = pick_splits(nt_h, kc_q, h->sm_count);
   c.splits_down = pick_splits(nt_h, kc_i, h->sm_count);
+  {
+    const int nt_i = (md.inter + 127) / 128;
+    c.splits_gu = std::min(4, pick_splits(nt_i, kc_h, h->sm_count));
+    if (nt_i * c.splits_gu > h->sm_count) c.splits_gu = 1;          // the SwiGLU tail needs one unit per CTA at most
+    if (const char* e = getenv("JF_GU_SPLITS")) c.splits_gu = std::max(1, std::min(c.splits_gu, atoi(e)));
+  }
   const int rs_cap = tp == 1 ? 8 : (tp == 2 ? 4 : 2);       // rows_norm keeps tp * splits slices in flight
   c.splits_o = std::min(c.splits_o, rs_cap);
   c.splits_down = std::min(c.splits_down, rs_cap);
@@ -306,6 +312,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.part_rs[0], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.part_rs[1], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.tpart, (size_t)kFuseRopeRows * c.part_splits * c.part_n, h->bytes_act);
+  c.tgu = nullptr;
+  if (c.splits_gu > 1) ALLOC(c.tgu, (size_t)c.T_cap * c.splits_gu * 2 * md.inter, h->bytes_act);
   ALLOC(c.tpart_rs[0], (size_t)kFuseRows * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.tpart_rs[1], (size_t)kFuseRows * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.attn_ml, (size_t)c.attn_slots_cap * md.n_q * 2, h->bytes_act);

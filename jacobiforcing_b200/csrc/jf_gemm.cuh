@@ -38,6 +38,8 @@ enum GemmEpilogue : int {
   EPI_SWIGLU_BF16 = 1,   // two accumulators (gate tile, up tile) -> silu(g)*u -> bf16 in packed-X layout
   EPI_PARTIAL_TAGGED = 3, // the same partial sums as 64-bit {stage tag, fp32 bits} words: the fused tails poll the DATA,
                           // so no flag / fence / barrier separates the k-splits' stores from their consumers
+  EPI_SWIGLU_TAGGED = 4, // split-K gate/up: both accumulators as tagged fp32 partial sums; the fused tail adds the splits
+                         // and applies SwiGLU (used when the gate/up tiles alone would leave SMs idle: tensor parallelism)
   EPI_ARGMAX      = 2,   // LM head: bf16-rounded logits, running (max, lowest index) per row -> atomicMax of packed keys
 };
 
@@ -141,16 +143,17 @@ __device__ __forceinline__ UnitRange unit_range(const GemmTask& t, int u) {
 // Rows one accumulator use covers.  SwiGLU needs two accumulators (gate, up): up to 128 rows they share one 256-column
 // TMEM buffer (double-buffered across units); 129..256 rows take the whole TMEM (gate in columns [0,256), up in
 // [256,512)) so the weight tiles are still streamed once - at the price of no overlap between units.
-__device__ __forceinline__ bool task_wide_dual(const GemmTask& t) { return t.epilogue == EPI_SWIGLU_BF16 && t.M > 128; }
+__device__ __forceinline__ bool task_dual(const GemmTask& t) { return t.epilogue == EPI_SWIGLU_BF16 || t.epilogue == EPI_SWIGLU_TAGGED; }
+__device__ __forceinline__ bool task_wide_dual(const GemmTask& t) { return task_dual(t) && t.M > 128; }
 __device__ __forceinline__ int task_rows_mma(const GemmTask& t) {
-  return t.epilogue == EPI_SWIGLU_BF16 ? (t.M > 128 ? 256 : 128) : kMaxRowsMMA;
+  return task_dual(t) ? (t.M > 128 ? 256 : 128) : kMaxRowsMMA;
 }
 
 // ---- warp 0, lane 0 ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gemm_produce_w(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
                                                int slot_bytes, int cta, int nctas, PipeState& pipe, bool hint,
                                                uint64_t policy) {
-  const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
+  const bool dual = task_dual(t);
   const int units = t.n_tiles * t.splits;
   const int rows_mma = task_rows_mma(t);
   const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
@@ -181,7 +184,7 @@ __device__ __forceinline__ void gemm_produce_w(const GemmTask& t, GemmSmem* gs, 
 // ---- warp 6, lane 0 (after it has seen the grid barrier that publishes X) ----------------------------------------
 __device__ __forceinline__ void gemm_produce_x(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
                                                int slot_bytes, int cta, int nctas, PipeState& pipe) {
-  const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
+  const bool dual = task_dual(t);
   const int units = t.n_tiles * t.splits;
   const int rows_mma = task_rows_mma(t);
   const int m_tiles = (t.M + rows_mma - 1) / rows_mma;
@@ -209,7 +212,7 @@ __device__ __forceinline__ void gemm_produce_x(const GemmTask& t, GemmSmem* gs, 
 // ---- warp 1, lane 0 -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gemm_issue_mma(const GemmTask& t, GemmSmem* gs, uint8_t* tiles, int nstages,
                                                int slot_bytes, int cta, int nctas, PipeState& pipe, AccState& acc) {
-  const bool dual = (t.epilogue == EPI_SWIGLU_BF16);
+  const bool dual = task_dual(t);
   const bool wide = task_wide_dual(t);
   const int units = t.n_tiles * t.splits;
   const int rows_mma = task_rows_mma(t);
@@ -311,6 +314,25 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
           for (int j = 0; j < 16; ++j) {
             const int m = t.x_row0 + m0 + c0 + j;
             if (nvalid && c0 + j < mlive) out[(size_t)m * t.out_row_stride + n] = tg | (unsigned long long)v[j];
+          }
+        }
+      } else if (t.epilogue == EPI_SWIGLU_TAGGED) {
+        // out[((m * splits + split) * 2 + {gate, up}) * N + n]
+        unsigned long long* out = reinterpret_cast<unsigned long long*>(t.out) + (size_t)r.split * t.out_split_stride;
+        const unsigned long long tg = (unsigned long long)t.tag << 32;
+        const bool nvalid = n < t.N;
+        for (int c0 = 0; c0 < mpad; c0 += 16) {
+          uint32_t g[16], up[16];
+          tmem_ld16(taddr + c0, g);
+          tmem_ld16(taddr + up_off + c0, up);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = t.x_row0 + m0 + c0 + j;
+            if (nvalid && c0 + j < mlive) {
+              out[(size_t)m * t.out_row_stride + n] = tg | (unsigned long long)g[j];
+              out[(size_t)m * t.out_row_stride + t.N + n] = tg | (unsigned long long)up[j];
+            }
           }
         }
       } else if (t.epilogue == EPI_SWIGLU_BF16) {

@@ -281,12 +281,13 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         // no flag, fence or barrier: the tails poll the tagged partial sums themselves
         const int n_tile = cta / t.splits, split = cta - n_tile * t.splits;
         if (fuse_kind == 3) qkv_rope_tail(c, ws, t.M, layer, n_tile, split, t.splits);
+        else if (fuse_kind == 4) gu_swiglu_tail(c, ws, t.M, n_tile, split, t.splits);
         else gemm_norm_tail(c, ws, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
       }
     }
     if (barrier_after) {
       if (ROLE == ROLE_WORKER)
-        grid_barrier(c, w, bs, prof_slot, t.epilogue == EPI_SWIGLU_BF16 || fuse_kind == 1 || fuse_kind == 2, xgpu, stage_id);
+        grid_barrier(c, w, bs, prof_slot, t.epilogue == EPI_SWIGLU_BF16 || fuse_kind == 1 || fuse_kind == 2 || fuse_kind == 4, xgpu, stage_id);
       else skip_barrier(xgpu);
     }
   };
@@ -347,6 +348,9 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     const bool fuse_ok = c.fuse_norm != 0 && T <= kFuseRows;
     const bool fuse_o = fuse_ok && nt_h * c.splits_o <= nctas;
     const bool fuse_d = fuse_ok && nt_h * c.splits_down <= nctas;
+    // split-K gate/up is a property of the engine (set when it is created), never of the forward: every forward must
+    // add the same partial sums in the same order (Jacobi == AR == chunked prefill, bit for bit)
+    const bool fuse_g = c.splits_gu > 1;
     const bool fuse_q = c.fuse_rope != 0 && T <= kFuseRopeRows && nt_qkv * c.splits_qkv <= nctas && nt_qkv <= kMaxTilesPerKind;
 
     auto base_task = [&]() {
@@ -370,10 +374,14 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       if (fused) { t.out = c.tpart_rs[0]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); }
       return t;
     };
-    auto task_gu = [&](int l) {       // gate/up projection with the SwiGLU epilogue
+    auto task_gu = [&](int l, bool fused = false) {       // gate/up projection with the SwiGLU epilogue
       GemmTask t = base_task();
       t.W = c.layer[l].wgu; t.X = c.xn; t.out = c.xact; t.n_tiles = nt_i; t.k_chunks = kc_h; t.splits = 1;
       t.N = md.inter; t.epilogue = EPI_SWIGLU_BF16;
+      if (fused) {                    // split-K: tagged gate / up partial sums, SwiGLU in the tail
+        t.out = c.tgu; t.splits = c.splits_gu; t.epilogue = EPI_SWIGLU_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u);
+        t.out_row_stride = c.splits_gu * 2 * md.inter; t.out_split_stride = 2 * md.inter;
+      }
       return t;
     };
     auto task_down = [&](int l, bool fused = false) {
@@ -409,7 +417,8 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         gemm_stage(task_o(l), true, SID_O, tp);
         JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, ws, T, false, c.splits_o, lw.ln2, 0));
       }
-      gemm_stage(task_gu(l), true, SID_GU);
+      if (fuse_g) gemm_stage(task_gu(l, true), true, SID_GU, false, 4);
+      else gemm_stage(task_gu(l), true, SID_GU);
       const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
       if (fuse_d) {
         gemm_stage(task_down(l, true), true, SID_DOWN_FUSED, false, 2, next_norm);

@@ -361,6 +361,69 @@ __device__ __forceinline__ void gemm_norm_tail(const DevCtx& c, const WorkerShar
 #undef JF_TAIL_CASE
 }
 
+// SwiGLU as the TAIL of the split-K gate/up projection (EPI_SWIGLU_TAGGED): the CTAs that hold an n-tile's k-splits
+// share the tile's rows (row step `it` belongs to split it % SPLITS; one row per half-warp, 8 features per lane), add the
+// splits' gate and up partial sums in split order and write silu(gate) * up into the down projection's operand.
+// Rounding points as in the single-accumulator epilogue (HF Qwen2MLP: every op in bf16).
+template <int SPLITS>
+__device__ __noinline__ void gu_swiglu_tail_impl(const DevCtx& c, const WorkerShared* ws, int T, int n_tile, int split) {
+  const WorkerCtx w = load_wctx(ws);
+  const int N = c.md.inter;
+  const int l16 = w.lane & 15, hw = w.lane >> 4;
+  const int n0 = n_tile * kTileN + l16 * 8;
+  const int nit = (T + 7) >> 3;
+  const int trow = w.wwarp * 2 + hw;
+  if (n0 >= N) return;
+  for (int it = split; it < nit; it += SPLITS) {
+    const int t = it * 8 + trow;
+    if (t >= T) continue;
+    const unsigned long long* p = c.tgu + ((size_t)t * SPLITS) * 2 * N + n0;
+    float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, us[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      ulonglong2 wd[SPLITS][4];
+      const long long t0 = clock64();
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int s2 = 0; s2 < SPLITS; ++s2)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) wd[s2][k] = ld_cg_poll_u64x2(p + ((size_t)s2 * 2 + g) * N + 2 * k);
+#pragma unroll
+        for (int s2 = 0; s2 < SPLITS; ++s2)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
+        if (ok) break;
+        if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < SPLITS; ++s2)                   // split order: deterministic
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (g == 0) { gs[2 * k] += tagged_val(wd[s2][k].x); gs[2 * k + 1] += tagged_val(wd[s2][k].y); }
+          else { us[2 * k] += tagged_val(wd[s2][k].x); us[2 * k + 1] += tagged_val(wd[s2][k].y); }
+        }
+    }
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gf = bf16_round(gs[e]);
+      const float uf = bf16_round(us[e]);
+      const float sl = bf16_round(gf / (1.f + __expf(-gf)));
+      o[e] = sl * uf;
+    }
+    uint8_t* dst = reinterpret_cast<uint8_t*>(c.xact) + ((size_t)(n0 >> 6) * c.xrows_cap) * 128 + sw128_offset(t, n0 & 63);
+    *reinterpret_cast<uint4*>(dst) = pack8(o);
+  }
+}
+__device__ __forceinline__ void gu_swiglu_tail(const DevCtx& c, const WorkerShared* ws, int T, int n_tile, int split, int splits) {
+  switch (splits) {
+    case 2: gu_swiglu_tail_impl<2>(c, ws, T, n_tile, split); break;
+    case 3: gu_swiglu_tail_impl<3>(c, ws, T, n_tile, split); break;
+    default: gu_swiglu_tail_impl<4>(c, ws, T, n_tile, split); break;
+  }
+}
+
 // which: 0 = after the O projection, 1 = after the down projection (selects the row-split partial buffer)
 __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerShared* ws, int T, bool embed, int splits,
                                              const __nv_bfloat16* normw, int which) {

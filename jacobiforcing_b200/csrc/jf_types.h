@@ -104,6 +104,7 @@ struct alignas(16) DevCtx {
   int part_splits, part_n;
   unsigned long long* tpart;         // [kFuseRopeRows][part_splits][part_n] tagged {stage tag, fp32} partial sums of the fused QKV stage
   unsigned long long* tpart_rs[2];   // [kFuseRows][part_splits][h] the same for the fused O / down stages
+  unsigned long long* tgu;           // [T_cap][splits_gu][2][inter] tagged gate / up partial sums (split-K gate/up)
   float* part_rs[2];                 // [T_cap][part_splits][h]: partials of the row-split GEMMs (0 = O, 1 = down); with
                                      // tensor parallelism the peers read them over NVLink, hence double-buffered
   __nv_bfloat16* qbuf;               // [T_cap][q_dim] rotated queries
@@ -116,6 +117,7 @@ struct alignas(16) DevCtx {
   unsigned long long* row_ss;        // [T_cap][kMaxHTiles] per-tile {stage tag, sum of squares} words of the row being normalised
   unsigned int launch_id;            // makes the stage tags unique across launches
   int splits_qkv, splits_o, splits_down;
+  int splits_gu;                     // > 1: the gate/up projection is split along K too (its tiles alone would idle SMs)
   // ---- plan (written by the host in plan mode, by the policy stage in Jacobi mode)
   PlanHdr* hdr;
   int* tok;                          // [T_cap]

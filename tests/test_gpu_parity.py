@@ -248,6 +248,8 @@ def _run_mid(monkeypatch, fused: bool, rows_list, gen_kw):
     from jacobiforcing_b200.runtime import hf_generate
     for k in ("JF_FUSE_NORM", "JF_FUSE_ROPE"):
         monkeypatch.setenv(k, "1" if fused else "0")          # read once, when the engine is created
+    # (mid128 also runs the split-K gate/up projection - 4 k-splits, SwiGLU in the tail - in BOTH engines: that is a
+    # property of the engine, not of the fusion switches)
     model, rt = make_pair("mid128")
     out = {"logits": [], "greedy": []}
     for rows in rows_list:
