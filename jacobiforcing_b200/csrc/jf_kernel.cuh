@@ -339,6 +339,17 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         if (w.wtid == 0 && c.prof_cap >= 3) { c.prof[0] = 0; c.prof[1] = clock64(); c.prof[2] = c.prof[1]; prof_n = 3; }
       }
     }
+    if (ROLE == ROLE_WORKER) {
+      // plan arrays of this forward -> shared memory (readers are at least one grid barrier away)
+      const int ok = (T <= kPlanRows && ip.G <= kPlanGroups) ? 1 : 0;
+      if (ok) {
+        PlanCache* pc = ws->plan;
+        for (int t = w.wtid; t < T; t += kWorkerThreads) { pc->row_pos[t] = ld_weak(&c.row_pos[t]); pc->row_attn[t] = ld_weak(&c.row_attn[t]); }
+        for (int g = w.wtid; g < ip.G; g += kWorkerThreads) pc->groups[g] = load_group(c, g);
+      }
+      if (w.wtid == 0) ws->plan_ok = ok;
+      w.plan = ok ? ws->plan : nullptr;
+    }
     slot_bytes = gemm_slot_bytes(min(kMaxRowsMMA, round_up16(T)));
     nstages = min(kMaxStages, ring_bytes / slot_bytes);
     pipe.stage = 0;
@@ -456,7 +467,7 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
   // The context (pointers, dims, per-layer weight table) is copied into shared memory once: every stage reads a dozen
   // of its fields, and from global memory each of them costs an L2 round trip after every grid barrier (the barrier's
   // acquire invalidates L1).
-  DevCtx* sctx = reinterpret_cast<DevCtx*>(red + 16);
+  DevCtx* sctx = reinterpret_cast<DevCtx*>(red + 32);        // red[0..7] scratch words, red[8..31] WorkerShared
   {
     const uint4* src = reinterpret_cast<const uint4*>(ctxp);
     uint4* dst = reinterpret_cast<uint4*>(sctx);
@@ -464,7 +475,8 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
   }
   __syncthreads();
   const DevCtx& c = *sctx;
-  uint8_t* attn = reinterpret_cast<uint8_t*>(sctx) + ((sizeof(DevCtx) + 15) & ~(size_t)15);
+  PlanCache* plan = reinterpret_cast<PlanCache*>(reinterpret_cast<uint8_t*>(sctx) + ((sizeof(DevCtx) + 15) & ~(size_t)15));
+  uint8_t* attn = reinterpret_cast<uint8_t*>(plan) + ((sizeof(PlanCache) + 15) & ~(size_t)15);
   const int attn_need = 2 * kAttnSub * (c.md.d + 8) * 2;
   const int best_need = 4 * kArgmaxRows * 8;
   const int attn_bytes = attn_need > best_need ? attn_need : best_need;
@@ -477,8 +489,9 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
   gemm_setup(gs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WorkerShared* ws = reinterpret_cast<WorkerShared*>(red + 8);      // red[8..15]
-  if (threadIdx.x == 0) { ws->red = red; ws->attn_smem = attn; ws->prof_on = 0; ws->tag = 0u; }
+  static_assert(sizeof(WorkerShared) <= 24 * sizeof(float), "WorkerShared must fit red[8..31]");
+  WorkerShared* ws = reinterpret_cast<WorkerShared*>(red + 8);      // red[8..31]
+  if (threadIdx.x == 0) { ws->red = red; ws->attn_smem = attn; ws->prof_on = 0; ws->tag = 0u; ws->plan = plan; ws->plan_ok = 0; }
   __syncthreads();
 
   if (warp == kWarpW) {

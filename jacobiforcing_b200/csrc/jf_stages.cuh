@@ -15,6 +15,7 @@
 
 namespace jf {
 
+struct PlanCache;
 struct WorkerCtx {
   int cta, nctas;
   int wtid;        // 0..127 among the worker warps
@@ -24,16 +25,27 @@ struct WorkerCtx {
   uint8_t* attn_smem;
   int prof_on;     // CTA 0, forward being profiled
   unsigned int tag; // unique id of the stage instance being executed (launch id, barrier count)
+  const PlanCache* plan;   // non-null: plan arrays of the forward in flight, in shared memory
 };
 // The part of the worker context that is not derivable from special registers lives in shared memory.  Non-inlined
 // stage functions receive a pointer to it and rebuild their WorkerCtx in registers: a struct passed by reference to a
 // non-inlined function lives on the caller's stack, and every field access becomes a local-memory load that misses L1
 // after each grid barrier (ncu: long-scoreboard stalls on w.lane / grp.slot0 inside the attention stage).
+// Per-forward copy of the small plan arrays every layer's stages index (row positions, attention slots, groups): read
+// from global memory they cost an L2 round trip per stage and layer; filled once per forward by the worker warps.
+constexpr int kPlanRows = 64, kPlanGroups = 8;
+struct PlanCache {
+  int row_pos[kPlanRows];
+  int2 row_attn[kPlanRows];
+  Group groups[kPlanGroups];
+};
 struct WorkerShared {
   float* red;
   uint8_t* attn_smem;
   int prof_on;
   unsigned int tag;
+  PlanCache* plan;     // shared-memory plan cache
+  int plan_ok;         // 1: the forward in flight fits the cache and it is filled
 };
 __device__ __forceinline__ WorkerCtx load_wctx(const WorkerShared* ws) {
   WorkerCtx w;
@@ -42,6 +54,7 @@ __device__ __forceinline__ WorkerCtx load_wctx(const WorkerShared* ws) {
   w.wwarp = (int)(threadIdx.x >> 5) - 2;          // kWarpWorker0
   w.wtid = (int)threadIdx.x - 2 * 32;
   w.red = ws->red; w.attn_smem = ws->attn_smem; w.prof_on = ws->prof_on; w.tag = ws->tag;
+  w.plan = ws->plan_ok ? ws->plan : nullptr;
   return w;
 }
 
@@ -478,7 +491,7 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
       const int t = item / nslots;
       if (tt[q] > 0) tt[q] = t;
       slot[q] = slot_base + item - t * nslots;
-      pos[q] = ld_weak(&c.row_pos[t]);
+      pos[q] = w.plan ? w.plan->row_pos[t] : ld_weak(&c.row_pos[t]);
       p0[q] = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane * PPL;
     }
     if (TAGGED) {
@@ -865,16 +878,16 @@ __device__ __forceinline__ Group load_group(const DevCtx& c, int g) {
 }
 
 struct AttnUnitId { Group grp; int kvh, hs, chunk, qs; };
-__device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, int u, int G) {
+__device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, const WorkerCtx& w, int u, int G) {
   AttnUnitId id;
   const int hsplit = c.attn_hsplit;
   int g = 0;
-  id.grp = load_group(c, 0);
+  id.grp = w.plan ? w.plan->groups[0] : load_group(c, 0);
   while (g + 1 < G) {                                   // groups are few; linear scan over unit ranges
     const int per = c.md.n_kv * id.grp.nchunks * id.grp.qsplit * hsplit;
     if (u < id.grp.unit0 + per) break;
     ++g;
-    id.grp = load_group(c, g);
+    id.grp = w.plan ? w.plan->groups[g] : load_group(c, g);
   }
   int local = u - id.grp.unit0;
   id.kvh = local % c.md.n_kv; local /= c.md.n_kv;
@@ -891,7 +904,7 @@ __device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, int u, i
 __device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerShared* ws, int layer, int G, int units) {
   const WorkerCtx w = load_wctx(ws);
   if (w.cta >= units || !c.attn_prefetch) return;
-  const AttnUnitId id = decode_attn_unit(c, w.cta, G);
+  const AttnUnitId id = decode_attn_unit(c, w, w.cta, G);
   const ModelDims& md = c.md;
   const int D = md.d, LDS = D + 8, VPR = D >> 3;
   const int ctx = id.grp.ctx;
@@ -916,7 +929,7 @@ __device__ __noinline__ void stage_attention(const DevCtx& c, const WorkerShared
   const WorkerCtx w = load_wctx(ws);
   for (int u = w.cta; u < units; u += w.nctas) {
     prof_mark(c, w, 398);
-    const AttnUnitId id = decode_attn_unit(c, u, G);
+    const AttnUnitId id = decode_attn_unit(c, w, u, G);
     const bool pf = c.attn_prefetch && u == w.cta;
     prof_mark(c, w, 399);
     if (c.md.d == 128) attention_unit<128>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf);
@@ -961,7 +974,7 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
       tt[q] = -1; cmax[q] = -1; base[q] = 0; hh[q] = 0;
       if (item < items) {
         tt[q] = item / md.n_q; hh[q] = item - tt[q] * md.n_q;
-        const int2 ra = ld_weak(&c.row_attn[tt[q]]);
+        const int2 ra = w.plan ? w.plan->row_attn[tt[q]] : ld_weak(&c.row_attn[tt[q]]);
         cmax[q] = ra.y;
         base[q] = (size_t)ra.x * md.n_q + hh[q];
       }
