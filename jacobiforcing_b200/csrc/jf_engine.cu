@@ -650,11 +650,19 @@ extern "C" int jf_set_rope_tables(jf_handle h, const float* cosv, const float* s
 // ---------------------------------------------------------------------------------------------------------------
 static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float* elapsed_ms) {
   JF_CUDA(h, cudaMemsetAsync(h->hctx.bar_counter, 0, (4 + 3 * kMaxTilesPerKind) * sizeof(unsigned int), h->stream));
-  h->hctx.launch_id = (h->hctx.launch_id + 1u) & 0xffu;
+  if (h->hctx.tag_base > 0xE0000000u) {          // 32-bit stage tags about to wrap: forget every stored tag (0 is never used)
+    DevCtx& c = h->hctx;
+    JF_CUDA(h, cudaMemsetAsync(c.row_ss, 0, (size_t)c.T_cap * kMaxHTiles * 8, h->stream));
+    JF_CUDA(h, cudaMemsetAsync(c.tpart, 0, (size_t)kFuseRopeRows * c.part_splits * c.part_n * 8, h->stream));
+    JF_CUDA(h, cudaMemsetAsync(c.tpart_rs[0], 0, (size_t)kFuseRows * c.part_splits * h->md.h * 8, h->stream));
+    JF_CUDA(h, cudaMemsetAsync(c.tpart_rs[1], 0, (size_t)kFuseRows * c.part_splits * h->md.h * 8, h->stream));
+    if (c.tgu) JF_CUDA(h, cudaMemsetAsync(c.tgu, 0, (size_t)c.T_cap * c.splits_gu * 2 * h->md.inter * 8, h->stream));
+    c.tag_base = 0u;
+  }
   h->hctx.xflag_base += (1ull << 32);
   JF_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->dctx) + offsetof(DevCtx, xflag_base), &h->hctx.xflag_base, 8,
                              cudaMemcpyHostToDevice, h->stream));
-  JF_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->dctx) + offsetof(DevCtx, launch_id), &h->hctx.launch_id, 4,
+  JF_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->dctx) + offsetof(DevCtx, tag_base), &h->hctx.tag_base, 4,
                              cudaMemcpyHostToDevice, h->stream));
   const DevCtx* dctx = h->dctx;
   int smem_total = h->smem_optin;
@@ -669,6 +677,13 @@ static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     *elapsed_ms = ms;
+  }
+  {   // advance the stage-tag base past every barrier this launch can have passed (forwards executed is in the header)
+    int iters = 0;
+    JF_CUDA(h, cudaMemcpy(&iters, reinterpret_cast<const uint8_t*>(h->hctx.hdr) + offsetof(PlanHdr, iter), 4,
+                          cudaMemcpyDeviceToHost));
+    if (iters < 0) iters = 0;
+    h->hctx.tag_base += (unsigned int)(iters + 2) * (unsigned int)(9 * h->md.layers + 8) + 16u;
   }
   return JF_OK;
 }

@@ -274,7 +274,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     } else if (ROLE == ROLE_MMA) {
       gemm_issue_mma(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, acc);
     } else {
-      w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u);
+      w.tag = c.tag_base + bs.epoch + 1u;
       ws->tag = w.tag;
       gemm_epilogue(t, gs, cta, nctas, acc);
       if (fuse_kind != 0 && cta < t.n_tiles * t.splits) {
@@ -293,7 +293,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   };
 #define JF_SIMT_STAGE_X(tma_out, sid, body)                    \
   do {                                                        \
-    if (ROLE == ROLE_WORKER) { w.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); ws->tag = w.tag; body; grid_barrier(c, w, bs, prof_slot, tma_out, false, sid); } else { skip_barrier(false); } \
+    if (ROLE == ROLE_WORKER) { w.tag = c.tag_base + bs.epoch + 1u; ws->tag = w.tag; body; grid_barrier(c, w, bs, prof_slot, tma_out, false, sid); } else { skip_barrier(false); } \
   } while (0)
 
 #define JF_SIMT_STAGE(sid, body) JF_SIMT_STAGE_X(true, sid, body)
@@ -375,14 +375,14 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       GemmTask t = base_task();
       t.W = c.layer[l].wqkv; t.X = c.xn; t.out = c.part; t.n_tiles = nt_qkv; t.k_chunks = kc_h; t.splits = c.splits_qkv;
       t.N = md.qkv_dim; t.epilogue = EPI_PARTIAL_F32;
-      if (fused) { t.out = c.tpart; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); }
+      if (fused) { t.out = c.tpart; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; }
       return t;
     };
     auto task_o = [&](int l, bool fused = false) {
       GemmTask t = base_task();
       t.W = c.layer[l].wo; t.X = c.xa; t.out = c.part_rs[0]; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
       t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
-      if (fused) { t.out = c.tpart_rs[0]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); }
+      if (fused) { t.out = c.tpart_rs[0]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; }
       return t;
     };
     auto task_gu = [&](int l, bool fused = false) {       // gate/up projection with the SwiGLU epilogue
@@ -390,7 +390,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       t.W = c.layer[l].wgu; t.X = c.xn; t.out = c.xact; t.n_tiles = nt_i; t.k_chunks = kc_h; t.splits = 1;
       t.N = md.inter; t.epilogue = EPI_SWIGLU_BF16;
       if (fused) {                    // split-K: tagged gate / up partial sums, SwiGLU in the tail
-        t.out = c.tgu; t.splits = c.splits_gu; t.epilogue = EPI_SWIGLU_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u);
+        t.out = c.tgu; t.splits = c.splits_gu; t.epilogue = EPI_SWIGLU_TAGGED; t.tag = c.tag_base + bs.epoch + 1u;
         t.out_row_stride = c.splits_gu * 2 * md.inter; t.out_split_stride = 2 * md.inter;
       }
       return t;
@@ -399,7 +399,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       GemmTask t = base_task();
       t.W = c.layer[l].wd; t.X = c.xact; t.out = c.part_rs[1]; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
       t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
-      if (fused) { t.out = c.tpart_rs[1]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = (c.launch_id << 24) ^ (bs.epoch + 1u); }
+      if (fused) { t.out = c.tpart_rs[1]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; }
       return t;
     };
     auto task_lm = [&](int i) {

@@ -115,7 +115,8 @@ struct alignas(16) DevCtx {
   int attn_hsplit;                   // attention units per kv head along its q heads (2 when n_rep >= 4)
   unsigned long long* argmax_keys;   // [2][T_cap] packed (value, ~index) keys, double-buffered by forward parity
   unsigned long long* row_ss;        // [T_cap][kMaxHTiles] per-tile {stage tag, sum of squares} words of the row being normalised
-  unsigned int launch_id;            // makes the stage tags unique across launches
+  unsigned int tag_base;             // stage tag = tag_base + barriers passed + 1: a 32-bit count of all stages this engine
+                                     // ever ran, so a word's stale tag (its LAST writer's) never equals a later stage's
   int splits_qkv, splits_o, splits_down;
   int splits_gu;                     // > 1: the gate/up projection is split along K too (its tiles alone would idle SMs)
   // ---- plan (written by the host in plan mode, by the policy stage in Jacobi mode)
