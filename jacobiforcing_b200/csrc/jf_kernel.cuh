@@ -297,9 +297,19 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   } while (0)
 
 #define JF_SIMT_STAGE(sid, body) JF_SIMT_STAGE_X(true, sid, body)
+  auto launch_mark = [&](int id) {     // developer aid (JF_DEBUG_SKIP & 2048): coarse marks of the launch itself
+    if (ROLE == ROLE_WORKER && (c.debug_skip & 2048) && cta == 0 && w.wtid == 0 && c.prof_marks != nullptr) {
+      int* cnt = reinterpret_cast<int*>(w.red) + 5;
+      if (id == 990) *cnt = 0;
+      const int n = *cnt;
+      if (n + 2 <= 8192) { c.prof_marks[n] = id; c.prof_marks[n + 1] = clock64(); *cnt = n + 2; *c.prof_marks_n = n + 2; }
+    }
+  };
+  launch_mark(990);
   if (run_mode == RUN_JACOBI) {
     JF_SIMT_STAGE(SID_POLICY, if (cta == 0) policy_stage_jacobi(c, ws, true, max_forwards));
   }
+  launch_mark(991);
 
   for (;;) {
     if (ROLE != ROLE_WORKER) wait_epoch(c.bar_counter, bs.target(nctas));
@@ -311,6 +321,10 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     if (ip.done) {
       if (ROLE == ROLE_WORKER) {
         if (prof_slot != nullptr && w.wtid == 0) {
+          if (prof_n + 3 <= c.prof_cap) {
+            c.prof[prof_n] = -(long long)globaltimer_ns(); c.prof[prof_n + 1] = clock64(); c.prof[prof_n + 2] = c.prof[prof_n + 1];
+            prof_n += 3;
+          }
           *c.prof_count = prof_n;
           if (c.prof_marks_n) *c.prof_marks_n = reinterpret_cast<int*>(w.red)[4];
         }
@@ -319,11 +333,22 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
           for (int t = w.wtid; t < 2 * c.T_cap; t += kWorkerThreads) c.argmax_keys[t] = 0ull;   // clean for the next launch
         stage_commit(c, ws, ip.n_commit);
       }
+      launch_mark(992);
       break;
     }
     const int T = ip.T;
+    if (ROLE == ROLE_WORKER && (c.debug_skip & 2048) && cta == 0 && w.wtid == 0 && c.prof_marks != nullptr) {
+      // developer aid: one (1000 + rows, clock) mark per forward of the launch (per-forward durations)
+      int* cnt = reinterpret_cast<int*>(w.red) + 5;
+      const int n = *cnt;
+      if (n + 2 <= 8192) { c.prof_marks[n] = 1000 + T; c.prof_marks[n + 1] = clock64(); *cnt = n + 2; *c.prof_marks_n = n + 2; }
+    }
     if (ROLE == ROLE_WORKER) {
       if (prof_slot != nullptr && w.wtid == 0) {                           // forward profiled: publish and stop
+        if (prof_n + 3 <= c.prof_cap) {        // closing record: (-wall clock ns, SM clock) calibrates cycles -> time
+          c.prof[prof_n] = -(long long)globaltimer_ns(); c.prof[prof_n + 1] = clock64(); c.prof[prof_n + 2] = c.prof[prof_n + 1];
+          prof_n += 3;
+        }
         *c.prof_count = prof_n;
         if (c.prof_marks_n) *c.prof_marks_n = reinterpret_cast<int*>(w.red)[4];
       }
@@ -336,7 +361,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         w.prof_on = 1;
         ws->prof_on = 1;
         if (w.wtid == 0) reinterpret_cast<int*>(w.red)[4] = 0;
-        if (w.wtid == 0 && c.prof_cap >= 3) { c.prof[0] = 0; c.prof[1] = clock64(); c.prof[2] = c.prof[1]; prof_n = 3; }
+        if (w.wtid == 0 && c.prof_cap >= 3) { c.prof[0] = -(long long)globaltimer_ns(); c.prof[1] = clock64(); c.prof[2] = c.prof[1]; prof_n = 3; }
       }
     }
     if (ROLE == ROLE_WORKER) {

@@ -134,13 +134,23 @@ class JacobiRuntime:
         n, khz = C.c_int32(0), C.c_int32(0)
         _cabi.check(self.lib.jf_profile_read(self.h, stamps.ctypes.data_as(C.POINTER(C.c_int64)), 4096, C.byref(n),
                                              C.byref(khz)), self.h)
-        st = stamps[:n.value].astype(np.float64) / (khz.value / 1e3)       # microseconds
+        nrec = n.value // 3
+        # the opening and the closing record carry -(wall clock ns) in their id slot: measured SM clock of the profiled
+        # forward (the attribute clock rate is the maximum; under load the SMs run slower)
+        khz_eff = float(khz.value)
+        if nrec >= 2 and stamps[0] < 0 and stamps[3 * (nrec - 1)] < 0:
+            dt_ns = float(-stamps[3 * (nrec - 1)] - (-stamps[0]))
+            dclk = float(stamps[3 * (nrec - 1) + 1] - stamps[1])
+            if dt_ns > 0 and dclk > 0:
+                khz_eff = dclk / dt_ns * 1e6
+            nrec -= 1                                       # the closing record is not a stage
+        st = stamps[:n.value].astype(np.float64) / (khz_eff / 1e3)       # microseconds
         kinds = {1: "embed+norm", 2: "qkv_gemm", 3: "qkv_rope", 4: "attention", 5: "attn_combine", 6: "o_gemm",
                  7: "o_reduce_norm", 8: "gate_up_gemm", 9: "down_gemm", 10: "down_reduce_norm", 11: "lm_head_argmax",
                  12: "policy", 13: "o_gemm+norm", 14: "down_gemm+norm", 15: "qkv_gemm+rope"}
         rows = []
         layer, seen_qkv = -1, False
-        for i in range(1, n.value // 3):                    # triples (stage id, arrival of CTA 0, release)
+        for i in range(1, nrec):                            # triples (stage id, arrival of CTA 0, release)
             sid = int(stamps[3 * i])
             arrive, release = st[3 * i + 1], st[3 * i + 2]
             prev_release = st[3 * i - 1]
@@ -150,7 +160,7 @@ class JacobiRuntime:
             if 2 <= sid <= 10 or sid >= 13:
                 name = f"L{layer}.{name}"
             rows.append({"stage": name, "work_us": arrive - prev_release, "wait_us": release - arrive})
-        return {"sm_clock_khz": khz.value, "stages": rows}
+        return {"sm_clock_khz": khz.value, "sm_clock_khz_measured": khz_eff, "stages": rows}
 
     # ---- weights (loader.py:27-47 loop stays with the caller; this is the per-tensor weight_loader) ---------------
     def load_tensor(self, name: str, t) -> None:

@@ -57,6 +57,7 @@ def main():
         k = row["stage"].split(".")[-1]
         kinds[k][0] += row["work_us"]; kinds[k][1] += row["wait_us"]; kinds[k][2] += 1
         total += row["work_us"] + row["wait_us"]
+    print(f"SM clock during the profiled forward: {prof.get('sm_clock_khz_measured', 0) / 1e3:.0f} MHz (attribute: {prof['sm_clock_khz'] / 1e3:.0f})")
     print(f"forward {a.forward}: {total:.1f} us over {len(prof['stages'])} stages; run: {run['forwards']} forwards, "
           f"{run['device_ms']:.2f} ms -> {run['device_ms'] * 1e3 / max(1, run['forwards']):.1f} us / forward")
     print(f"{'stage':<20}{'count':>6}{'work_us(mean)':>16}{'wait_us(mean)':>16}{'total_us':>12}{'share':>8}")
