@@ -708,11 +708,6 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
     const int j = j_lo + tile / ntt;
     const int i0 = q0 + (tile % ntt) * 16;
     if (key_lo > ctx + min(i0 + 15, len - 1)) return;      // inactive tile (no visible key in this chunk)
-    if (c.debug_skip & 32) {                               // timing experiment: no query loads
-#pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks) { q[ks][0] = q[ks][1] = q[ks][2] = q[ks][3] = 0x3c003c00u + tile; }
-      return;
-    }
     const int head = g_kvh * md.n_rep + j;
     const __nv_bfloat16* qa = c.qbuf + (size_t)(row0 + min(i0 + r0, len - 1)) * md.q_dim + head * D;
     const __nv_bfloat16* qb = c.qbuf + (size_t)(row0 + min(i0 + r0 + 8, len - 1)) * md.q_dim + head * D;
@@ -762,7 +757,6 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
         workers_sync();
       }
       if (!tactive || k0 > ctx + min(i0 + 15, len - 1)) continue;
-      if (c.debug_skip & 256) continue;                    // timing experiment: no math
 
       float s[8][4];
       // K fragments with ldmatrix: matrix m of one x4 = keys nt*8..+7 (rows) x dims (ks2*32 + m*8)..+7, i.e. (b0, b1) of
@@ -817,7 +811,6 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
       }
       l_a = l_a * sca + suma;
       l_b = l_b * scb + sumb;
-      if (c.debug_skip & 128) continue;                    // timing experiment: no P V
 #pragma unroll
       for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] *= sca; o[nd][1] *= sca; o[nd][2] *= scb; o[nd][3] *= scb; }
       // O += P V
@@ -845,7 +838,7 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
     }
 
     prof_mark(c, w, 403);
-    if (tactive && !(c.debug_skip & 64)) {
+    if (tactive) {
       l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
       l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
       l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
