@@ -290,6 +290,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     c.w_evict_first = e4 ? atoi(e4) : 1;
     const char* e6 = getenv("JF_FUSE_ROPE");
     c.fuse_rope = e6 ? atoi(e6) : 1;
+    const char* e8 = getenv("JF_DATAFLOW_GD");
+    c.dataflow_gd = e8 ? atoi(e8) : 1;
     const char* e5 = getenv("JF_FUSE_NORM");
     c.fuse_norm = e5 ? atoi(e5) : 1;
   }

@@ -233,7 +233,7 @@ enum Role : int { ROLE_W = 0, ROLE_MMA = 1, ROLE_WORKER = 2, ROLE_X = 3 };
 // stage ids recorded with every profiled grid barrier (jacobiforcing_b200/runtime.py maps them to names)
 enum StageId : int { SID_NONE = 0, SID_EMBED = 1, SID_QKV = 2, SID_ROPE = 3, SID_ATTN = 4, SID_COMBINE = 5, SID_O = 6,
                      SID_O_NORM = 7, SID_GU = 8, SID_DOWN = 9, SID_DOWN_NORM = 10, SID_LM = 11, SID_POLICY = 12,
-                     SID_O_FUSED = 13, SID_DOWN_FUSED = 14, SID_QKV_FUSED = 15 };
+                     SID_O_FUSED = 13, SID_DOWN_FUSED = 14, SID_QKV_FUSED = 15, SID_GU_DOWN_FUSED = 16 };
 
 struct IterPlan {
   int T, G, done, n_commit, attn_units, n_lm, want_logits;
@@ -256,19 +256,29 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   int prof_n = 0;
   int* prof_slot = nullptr;
   const uint64_t w_policy = (ROLE == ROLE_W) ? l2_policy_evict_first() : 0ull;
+  unsigned int df_uses = 0u;                   // gate/up -> down dataflow hand-overs so far in this launch
 
   auto skip_barrier = [&](bool xgpu) { bs.epoch += 1; if (xgpu) bs.xcount += 1; };
   // fuse_kind: 0 = plain GEMM stage; 3 = QKV projection with bias + rotary + scatter as its tail; 1 / 2 = O / down
   // projection whose split-K reduce + residual + RMSNorm runs as the tail of the epilogue.  The CTAs that hold an
   // n-tile's k-splits share the tile's rows and poll the tagged partial sums (EPI_PARTIAL_TAGGED) of the other splits
   // (needs one unit per CTA at most: no CTA may owe a second unit while it polls)
+  // df_wait >= 0: instead of a grid barrier, this stage's X producer waits until the df_wait producer tiles of the
+  // previous stage that its k-range reads have arrived on the range counter of its k-split (see fuse_kind 5)
   auto gemm_stage = [&](const GemmTask& t, bool barrier_after, int stage_id, bool xgpu = false, int fuse_kind = 0,
-                        const __nv_bfloat16* normw = nullptr, int layer = 0) {
+                        const __nv_bfloat16* normw = nullptr, int layer = 0, bool df_wait = false) {
     if (ROLE == ROLE_W) {
       if (c.debug_skip & 16) wait_epoch(c.bar_counter, bs.target(nctas));   // experiment: no run-ahead
       gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, c.w_evict_first != 0, w_policy);
     } else if (ROLE == ROLE_X) {
-      wait_epoch(c.bar_counter, bs.target(nctas));
+      if (!df_wait) {
+        wait_epoch(c.bar_counter, bs.target(nctas));
+      } else if (cta < t.n_tiles * t.splits) {
+        // dataflow: the gate/up tiles whose features are this unit's k-range (tile j holds k-chunks 2j, 2j+1)
+        const UnitRange r = unit_range(t, cta);
+        const unsigned int need = (unsigned int)(((r.k1 - 1) >> 1) - (r.k0 >> 1) + 1);
+        wait_epoch(c.tile_ctr + r.split, df_uses * need);
+      }
       fence_proxy_async_all();
       gemm_produce_x(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
     } else if (ROLE == ROLE_MMA) {
@@ -277,7 +287,18 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       w.tag = c.tag_base + bs.epoch + 1u;
       ws->tag = w.tag;
       gemm_epilogue(t, gs, cta, nctas, acc);
-      if (fuse_kind != 0 && cta < t.n_tiles * t.splits) {
+      if (fuse_kind == 5) {
+        // gate/up -> down without a grid barrier: publish this tile to the k-splits of the down projection that read it
+        fence_proxy_async_all();                        // the tile is read by bulk copies (async proxy) of other CTAs
+        workers_sync();
+        if (w.wtid == 0 && cta < t.n_tiles) {
+          const int ka = 2 * cta, kb = min(2 * cta + 1, kc_i - 1);
+          for (int s2 = 0; s2 < c.splits_down; ++s2) {
+            const int k0 = (int)(((long long)s2 * kc_i) / c.splits_down), k1 = (int)(((long long)(s2 + 1) * kc_i) / c.splits_down);
+            if (ka < k1 && kb >= k0) red_release_gpu_add_u32(c.tile_ctr + s2, 1u);
+          }
+        }
+      } else if (fuse_kind != 0 && cta < t.n_tiles * t.splits) {
         // no flag, fence or barrier: the tails poll the tagged partial sums themselves
         const int n_tile = cta / t.splits, split = cta - n_tile * t.splits;
         if (fuse_kind == 3) qkv_rope_tail(c, ws, t.M, layer, n_tile, split, t.splits);
@@ -387,6 +408,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     // split-K gate/up is a property of the engine (set when it is created), never of the forward: every forward must
     // add the same partial sums in the same order (Jacobi == AR == chunked prefill, bit for bit)
     const bool fuse_g = c.splits_gu > 1;
+    const bool dflow = c.dataflow_gd != 0 && fuse_d && !fuse_g && !tp && 2 * nt_i >= kc_i && c.splits_down <= kMaxTilesPerKind;
     const bool fuse_q = c.fuse_rope != 0 && T <= kFuseRopeRows && nt_qkv * c.splits_qkv <= nctas && nt_qkv <= kMaxTilesPerKind;
 
     auto base_task = [&]() {
@@ -453,9 +475,17 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         gemm_stage(task_o(l), true, SID_O, tp);
         JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, ws, T, false, c.splits_o, lw.ln2, 0));
       }
+      const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
+      if (dflow) {
+        // no grid barrier between gate/up and down: the down projection's X producers wait for exactly the gate/up
+        // tiles they read (every down tile's tail still needs all of them, so nothing of gate/up's input is overwritten early)
+        df_uses += 1u;
+        gemm_stage(task_gu(l), false, SID_GU, false, 5);
+        gemm_stage(task_down(l, true), true, SID_GU_DOWN_FUSED, false, 2, next_norm, 0, true);
+        continue;
+      }
       if (fuse_g) gemm_stage(task_gu(l, true), true, SID_GU, false, 4);
       else gemm_stage(task_gu(l), true, SID_GU);
-      const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
       if (fuse_d) {
         gemm_stage(task_down(l, true), true, SID_DOWN_FUSED, false, 2, next_norm);
       } else {

@@ -153,8 +153,9 @@ struct alignas(16) DevCtx {
   unsigned long long xflag_base;              // launch sequence << 32 (flags are monotonic, never reset)
   // ---- sync
   unsigned int* bar_counter;
-  unsigned int* tile_ctr;            // [3][kMaxTilesPerKind] k-split arrivals per n-tile of the fused GEMM stages (zeroed per launch)
+  unsigned int* tile_ctr;            // [3][kMaxTilesPerKind] arrival counters, zeroed per launch ([0..splits_down): gate/up tiles per down k-split)
   int fuse_rope;                     // 1: the QKV projection runs bias + rotary + q/k/v scatter as its epilogue tail
+  int dataflow_gd;                   // 1: no grid barrier between gate/up and down (per-k-split arrival counters instead)
   int fuse_norm;                     // 1: O / down projections run reduce + residual + RMSNorm as their epilogue tail
   // ---- optional stage profile: SM-clock stamps taken by CTA 0 after every grid barrier of forward `prof_forward`
   long long* prof;

@@ -147,7 +147,7 @@ class JacobiRuntime:
         st = stamps[:n.value].astype(np.float64) / (khz_eff / 1e3)       # microseconds
         kinds = {1: "embed+norm", 2: "qkv_gemm", 3: "qkv_rope", 4: "attention", 5: "attn_combine", 6: "o_gemm",
                  7: "o_reduce_norm", 8: "gate_up_gemm", 9: "down_gemm", 10: "down_reduce_norm", 11: "lm_head_argmax",
-                 12: "policy", 13: "o_gemm+norm", 14: "down_gemm+norm", 15: "qkv_gemm+rope"}
+                 12: "policy", 13: "o_gemm+norm", 14: "down_gemm+norm", 15: "qkv_gemm+rope", 16: "gate_up+down_gemm+norm"}
         rows = []
         layer, seen_qkv = -1, False
         for i in range(1, nrec):                            # triples (stage id, arrival of CTA 0, release)
