@@ -19,6 +19,7 @@
 // (acc_full/acc_empty) and the static unit loop (unit = (n_tile, k_split)), walked identically by all roles.
 #pragma once
 #include "jf_ptx.cuh"
+#include "jf_sched.h"
 
 namespace jf {
 
@@ -136,8 +137,8 @@ __device__ __forceinline__ UnitRange unit_range(const GemmTask& t, int u) {
   UnitRange r;
   r.n_tile = u / t.splits;
   r.split = u - r.n_tile * t.splits;
-  r.k0 = (int)(((long long)r.split * t.k_chunks) / t.splits);
-  r.k1 = (int)(((long long)(r.split + 1) * t.k_chunks) / t.splits);
+  r.k0 = split_k0(r.split, t.splits, t.k_chunks);
+  r.k1 = split_k1(r.split, t.splits, t.k_chunks);
   return r;
 }
 // Rows one accumulator use covers.  SwiGLU needs two accumulators (gate, up): up to 128 rows they share one 256-column

@@ -276,7 +276,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       } else if (cta < t.n_tiles * t.splits) {
         // dataflow: the gate/up tiles whose features are this unit's k-range (tile j holds k-chunks 2j, 2j+1)
         const UnitRange r = unit_range(t, cta);
-        const unsigned int need = (unsigned int)(((r.k1 - 1) >> 1) - (r.k0 >> 1) + 1);
+        const unsigned int need = (unsigned int)df_tiles_needed(r.k0, r.k1);
         wait_epoch(c.tile_ctr + r.split, df_uses * need);
       }
       fence_proxy_async_all();
@@ -292,11 +292,8 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         fence_proxy_async_all();                        // the tile is read by bulk copies (async proxy) of other CTAs
         workers_sync();
         if (w.wtid == 0 && cta < t.n_tiles) {
-          const int ka = 2 * cta, kb = min(2 * cta + 1, kc_i - 1);
-          for (int s2 = 0; s2 < c.splits_down; ++s2) {
-            const int k0 = (int)(((long long)s2 * kc_i) / c.splits_down), k1 = (int)(((long long)(s2 + 1) * kc_i) / c.splits_down);
-            if (ka < k1 && kb >= k0) red_release_gpu_add_u32(c.tile_ctr + s2, 1u);
-          }
+          for (int s2 = 0; s2 < c.splits_down; ++s2)
+            if (df_tile_feeds_split(cta, s2, c.splits_down, kc_i)) red_release_gpu_add_u32(c.tile_ctr + s2, 1u);
         }
       } else if (fuse_kind != 0 && cta < t.n_tiles * t.splits) {
         // no flag, fence or barrier: the tails poll the tagged partial sums themselves

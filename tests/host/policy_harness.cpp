@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "jf_policy.h"
+#include "jf_sched.h"
 
 using namespace jf;
 
@@ -54,5 +55,13 @@ int jf_policy_replay(const int* knobs_i /*12 ints in PolicyKnobs order*/, const 
 
 int jf_policy_state_bytes() { return (int)sizeof(SeqState); }
 int jf_policy_knob_ints() { return (int)(sizeof(PolicyKnobs) / sizeof(int)); }
+
+// scheduling arithmetic shared with the kernel (jf_sched.h)
+int jf_sched_split_k0(int split, int splits, int k_chunks) { return split_k0(split, splits, k_chunks); }
+int jf_sched_split_k1(int split, int splits, int k_chunks) { return split_k1(split, splits, k_chunks); }
+int jf_sched_tile_feeds_split(int tile, int split, int splits, int k_chunks) {
+  return df_tile_feeds_split(tile, split, splits, k_chunks) ? 1 : 0;
+}
+int jf_sched_tiles_needed(int k0, int k1) { return df_tiles_needed(k0, k1); }
 
 }  // extern "C"
