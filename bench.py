@@ -424,7 +424,7 @@ def main():
     ap.add_argument("--gen", type=int, default=512)
     ap.add_argument("--ref-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel group size (0 = largest of 1/2/4 dividing N)")
+    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel group size: 2 or 4 shard the kernel over NVLink; default (0) = N independent engines")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                  # timing rule: at least three warm-up steps
