@@ -38,18 +38,29 @@ class Config:
     device: int = 0
 
     def __post_init__(self):
-        model_path = self.model
-        if model_path is not None and os.path.isdir(model_path):
-            ckpts = [d for d in os.listdir(model_path)
-                     if d.startswith("checkpoint-") and os.path.isdir(os.path.join(model_path, d))]
-            if ckpts:                                      # config.py:31-41: latest DeepSpeed checkpoint sub-directory
-                model_path = os.path.join(model_path, max(ckpts, key=lambda x: int(x.split("-")[1])))
-                self.model = model_path
-        assert self.kvcache_block_size % 256 == 0
-        assert 1 <= self.tensor_parallel_size <= 8
+        self.model = _resolve_checkpoint_dir(self.model)
+        if self.kvcache_block_size % 256:
+            raise AssertionError("kvcache_block_size must be a multiple of 256")
+        if not 1 <= self.tensor_parallel_size <= 8:
+            raise AssertionError("tensor_parallel_size must lie in [1, 8]")
         if self.hf_config is None:
-            assert model_path is not None and os.path.isdir(model_path), f"Model path does not exist: {model_path}"
+            if self.model is None or not os.path.isdir(self.model):
+                raise AssertionError(f"Model path does not exist: {self.model}")
             from transformers import AutoConfig
-            self.hf_config = AutoConfig.from_pretrained(model_path)
+            self.hf_config = AutoConfig.from_pretrained(self.model)
         self.max_model_len = min(self.max_model_len, self.hf_config.max_position_embeddings)
-        assert self.max_num_batched_tokens >= self.max_model_len
+        if self.max_num_batched_tokens < self.max_model_len:
+            raise AssertionError("max_num_batched_tokens must cover max_model_len")
+
+
+def _resolve_checkpoint_dir(path: Optional[str]) -> Optional[str]:
+    """A training output directory is replaced by its latest `checkpoint-N` sub-directory, as the reference does
+    (inference_engine/config.py:31-41)."""
+    if path is None or not os.path.isdir(path):
+        return path
+    steps = []
+    for name in os.listdir(path):
+        head, _, tail = name.partition("-")
+        if head == "checkpoint" and tail.isdigit() and os.path.isdir(os.path.join(path, name)):
+            steps.append(int(tail))
+    return os.path.join(path, f"checkpoint-{max(steps)}") if steps else path

@@ -1,5 +1,14 @@
-"""Scheduler — prefill-first continuous batching (inference_engine/engine/scheduler.py:28-97)."""
+"""Prefill-first continuous batching over the paged KV cache.
+
+Behaviourally equivalent to the reference's scheduler (inference_engine/engine/scheduler.py:28-97): a step either admits
+waiting requests for prefill (bounded by `max_num_seqs`, `max_num_batched_tokens` and free pages) or, when none can be
+admitted, schedules the running ones for a decode call, preempting from the tail when pages run out.  Jacobi requests
+get their pages from the runner (the draft length is only known there), and `postprocess_jacobi` only decides whether
+a request is finished - its tokens were appended by the decode call itself (:80-97)."""
+from __future__ import annotations
+
 from collections import deque
+from typing import Deque, List, Sequence as Seq, Tuple
 
 from ..config import Config
 from .block_manager import BlockManager
@@ -12,70 +21,83 @@ class Scheduler:
         self.max_num_batched_tokens = config.max_num_batched_tokens
         self.eos = config.eos
         self.block_manager = BlockManager(config.num_kvcache_blocks, config.kvcache_block_size)
-        self.waiting = deque()
-        self.running = deque()
+        self.waiting: Deque[Sequence] = deque()
+        self.running: Deque[Sequence] = deque()
 
-    def set_kv_cache(self, kv_cache):
+    # ---- queue -------------------------------------------------------------------------------------------------
+    def set_kv_cache(self, kv_cache) -> None:
         self.block_manager.kv_cache = kv_cache
 
-    def is_finished(self):
-        return not self.waiting and not self.running
-
-    def add(self, seq: Sequence):
+    def add(self, seq: Sequence) -> None:
         self.waiting.append(seq)
 
-    def schedule(self):
-        scheduled, num_seqs, num_batched = [], 0, 0
-        while self.waiting and num_seqs < self.max_num_seqs:
+    def is_finished(self) -> bool:
+        return not (self.waiting or self.running)
+
+    # ---- one scheduling decision -------------------------------------------------------------------------------
+    def schedule(self) -> Tuple[List[Sequence], bool]:
+        """(sequences, is_prefill)."""
+        admitted = self._admit_waiting()
+        if admitted:
+            return admitted, True
+        chosen = self._pick_running()
+        assert chosen, "nothing can be scheduled"
+        self.running.extendleft(reversed(chosen))        # keep them at the head, in order
+        return chosen, False
+
+    def _admit_waiting(self) -> List[Sequence]:
+        admitted: List[Sequence] = []
+        budget = self.max_num_batched_tokens
+        while self.waiting and len(admitted) < self.max_num_seqs:
             seq = self.waiting[0]
-            if num_batched + len(seq) > self.max_num_batched_tokens or not self.block_manager.can_allocate(seq):
+            if len(seq) > budget or not self.block_manager.can_allocate(seq):
                 break
-            num_seqs += 1
             self.block_manager.allocate(seq)
-            num_batched += len(seq) - seq.num_cached_tokens
+            budget -= len(seq) - seq.num_cached_tokens
             seq.status = SequenceStatus.RUNNING
-            self.waiting.popleft()
-            self.running.append(seq)
-            scheduled.append(seq)
-        if scheduled:
-            return scheduled, True
-        while self.running and num_seqs < self.max_num_seqs:
+            self.running.append(self.waiting.popleft())
+            admitted.append(seq)
+        return admitted
+
+    def _pick_running(self) -> List[Sequence]:
+        chosen: List[Sequence] = []
+        while self.running and len(chosen) < self.max_num_seqs:
             seq = self.running.popleft()
+            evicted_self = False
             while not self.block_manager.can_append(seq):
                 if self.running:
-                    self.preempt(self.running.pop())
+                    self.preempt(self.running.pop())     # youngest first
                 else:
                     self.preempt(seq)
+                    evicted_self = True
                     break
-            else:
-                num_seqs += 1
-                if not str(getattr(seq, "decode_strategy", "")).startswith("jacobi"):
-                    self.block_manager.may_append(seq)
-                scheduled.append(seq)
-        assert scheduled
-        self.running.extendleft(reversed(scheduled))
-        return scheduled, False
+            if evicted_self:
+                continue
+            if not str(getattr(seq, "decode_strategy", "")).startswith("jacobi"):
+                self.block_manager.may_append(seq)
+            chosen.append(seq)
+        return chosen
 
-    def preempt(self, seq: Sequence):
-        seq.status = SequenceStatus.WAITING
+    def preempt(self, seq: Sequence) -> None:
         self.block_manager.deallocate(seq)
+        seq.status = SequenceStatus.WAITING
         self.waiting.appendleft(seq)
 
-    def _finish(self, seq):
+    # ---- after a step ------------------------------------------------------------------------------------------
+    def _retire(self, seq: Sequence) -> None:
         seq.status = SequenceStatus.FINISHED
         self.block_manager.deallocate(seq)
         self.running.remove(seq)
 
-    def postprocess(self, seqs, token_ids):
-        for seq, token_id in zip(seqs, token_ids):
-            seq.append_token(token_id)
-            if (not seq.ignore_eos and token_id == self.eos) or seq.num_completion_tokens == seq.max_tokens:
-                self._finish(seq)
+    def postprocess(self, seqs: Seq[Sequence], token_ids: Seq[int]) -> None:
+        for seq, tok in zip(seqs, token_ids):
+            seq.append_token(tok)
+            hit_eos = tok == self.eos and not seq.ignore_eos
+            if hit_eos or seq.num_completion_tokens == seq.max_tokens:
+                self._retire(seq)
 
-    def postprocess_jacobi(self, seqs, token_ids_batch):
-        """Tokens were already appended by the decoder; only EOS / max_tokens are checked here (:80-97)."""
-        for seq, token_ids in zip(seqs, token_ids_batch):
-            if not seq.ignore_eos and self.eos in token_ids:
-                self._finish(seq)
-            elif seq.num_completion_tokens >= seq.max_tokens:
-                self._finish(seq)
+    def postprocess_jacobi(self, seqs: Seq[Sequence], token_ids_batch: Seq[Seq[int]]) -> None:
+        for seq, new_tokens in zip(seqs, token_ids_batch):
+            hit_eos = (not seq.ignore_eos) and self.eos in new_tokens
+            if hit_eos or seq.num_completion_tokens >= seq.max_tokens:
+                self._retire(seq)

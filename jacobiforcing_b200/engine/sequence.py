@@ -1,9 +1,18 @@
-"""Sequence state (inference_engine/engine/sequence.py:14-156): token ids, block table, Jacobi draft fields."""
-from copy import copy
+"""Request state seen by the scheduler, the block manager and the model runner.
+
+Mirrors the attribute surface of the reference's `Sequence` (inference_engine/engine/sequence.py:14-156: token ids,
+prompt / completion split, block table, the per-request Jacobi knobs copied from `SamplingParams`, draft fields) so the
+reference's engine code and tests can use it unchanged; the implementation is this repository's own."""
+from __future__ import annotations
+
+import itertools
 from enum import Enum, auto
-from itertools import count
+from typing import Iterable, List, Optional
 
 from ..sampling_params import SamplingParams
+
+_JACOBI_KNOBS = ("jacobi_block_len", "jacobi_max_blocks", "jacobi_spawn_ratio", "jacobi_lookahead_start_ratio",
+                 "jacobi_n_gram_pool_size", "jacobi_max_iterations", "jacobi_on_policy")
 
 
 class SequenceStatus(Enum):
@@ -12,79 +21,78 @@ class SequenceStatus(Enum):
     FINISHED = auto()
 
 
-class Sequence:
-    block_size = 256
-    counter = count()
+def _as_int(tok) -> int:
+    return int(tok.item()) if hasattr(tok, "item") else int(tok)
 
-    def __init__(self, token_ids, sampling_params=SamplingParams()):
+
+class Sequence:
+    block_size = 256                      # KV page size in tokens
+    counter = itertools.count()           # process-wide request ids
+
+    def __init__(self, token_ids: List[int], sampling_params: Optional[SamplingParams] = None):
+        sp = sampling_params if sampling_params is not None else SamplingParams()
         self.seq_id = next(Sequence.counter)
         self.status = SequenceStatus.WAITING
-        self.token_ids = copy(token_ids)
-        self.last_token = token_ids[-1]
-        self.num_tokens = len(self.token_ids)
-        self.num_prompt_tokens = len(token_ids)
+        self.token_ids = list(token_ids)
+        self.num_prompt_tokens = self.num_tokens = len(self.token_ids)
+        self.last_token = self.token_ids[-1]
         self.num_cached_tokens = 0
-        self.block_table = []
-        self.temperature = sampling_params.temperature
-        self.max_tokens = sampling_params.max_tokens
-        self.ignore_eos = sampling_params.ignore_eos
-        self.decode_strategy = sampling_params.decode_strategy
-        self.jacobi_block_len = sampling_params.jacobi_block_len
-        self.jacobi_max_blocks = sampling_params.jacobi_max_blocks
-        self.jacobi_spawn_ratio = sampling_params.jacobi_spawn_ratio
-        self.jacobi_lookahead_start_ratio = sampling_params.jacobi_lookahead_start_ratio
-        self.jacobi_n_gram_pool_size = sampling_params.jacobi_n_gram_pool_size
-        self.jacobi_max_iterations = sampling_params.jacobi_max_iterations
-        self.jacobi_on_policy = sampling_params.jacobi_on_policy
-        self.sampling_params = sampling_params
+        self.block_table: List[int] = []
+        # per-request sampling / decoding knobs
+        self.sampling_params = sp
+        self.temperature, self.max_tokens, self.ignore_eos = sp.temperature, sp.max_tokens, sp.ignore_eos
+        self.decode_strategy = sp.decode_strategy
+        for knob in _JACOBI_KNOBS:
+            setattr(self, knob, getattr(sp, knob))
+        # Jacobi draft state
         self.draft_tokens = None
         self._prefill_draft = None
-        self._first_correct = None            # HF-convention strategies: first_correct_token of the prefill
+        self._first_correct = None        # HF-convention strategies: first_correct_token of the prefill
 
-    def __len__(self):
+    # ---- container protocol ------------------------------------------------------------------------------------
+    def __len__(self) -> int:
         return self.num_tokens
 
     def __getitem__(self, key):
         return self.token_ids[key]
 
+    # ---- derived quantities ------------------------------------------------------------------------------------
     @property
-    def is_finished(self):
-        return self.status == SequenceStatus.FINISHED
+    def is_finished(self) -> bool:
+        return self.status is SequenceStatus.FINISHED
 
     @property
-    def num_completion_tokens(self):
+    def num_completion_tokens(self) -> int:
         return self.num_tokens - self.num_prompt_tokens
 
     @property
-    def prompt_token_ids(self):
+    def prompt_token_ids(self) -> List[int]:
         return self.token_ids[:self.num_prompt_tokens]
 
     @property
-    def completion_token_ids(self):
+    def completion_token_ids(self) -> List[int]:
         return self.token_ids[self.num_prompt_tokens:]
 
     @property
-    def num_blocks(self):
-        return (self.num_tokens + self.block_size - 1) // self.block_size
+    def num_blocks(self) -> int:
+        return -(-self.num_tokens // self.block_size)
 
-    def append_token(self, token_id):
+    # ---- growth ------------------------------------------------------------------------------------------------
+    def append_token(self, token_id) -> None:
         if isinstance(token_id, (list, tuple)):
             raise ValueError(f"append_token expects a single integer, got {type(token_id)} with {len(token_id)} elements")
-        token_id = int(token_id.item()) if hasattr(token_id, "item") else int(token_id)
-        self.token_ids.append(token_id)
-        self.last_token = token_id
-        self.num_tokens += 1
+        self.extend_tokens((token_id,))
 
-    def extend_tokens(self, tokens):
-        if not tokens:
-            return
-        toks = [int(t.item()) if hasattr(t, "item") else int(t) for t in tokens]
-        self.token_ids.extend(toks)
-        self.last_token = toks[-1]
-        self.num_tokens += len(toks)
+    def extend_tokens(self, tokens: Iterable) -> None:
+        new = [_as_int(t) for t in tokens] if tokens else []
+        if new:
+            self.token_ids += new
+            self.last_token = new[-1]
+            self.num_tokens = len(self.token_ids)
 
-    def has_draft(self):
-        return self.draft_tokens is not None and len(self.draft_tokens) > 0
+    # ---- drafts ------------------------------------------------------------------------------------------------
+    def has_draft(self) -> bool:
+        return bool(self.draft_tokens is not None and len(self.draft_tokens))
 
-    def clear_draft(self):
+    def clear_draft(self) -> None:
         self.draft_tokens = None
