@@ -40,7 +40,7 @@ struct jf_engine {
   size_t arena_off[3] = {0, 0, 0};
   int64_t launches = 0;
   // weight bookkeeping
-  std::vector<uint8_t> seen_layer;   // bitmask per layer
+  std::vector<uint32_t> seen_layer;  // W_* / B_* bits per layer (jf_finalize_weights refuses a partial checkpoint)
   int seen_global = 0;
   __nv_bfloat16* stage = nullptr;    // staging for row-major -> tile re-layout
   size_t stage_elems = 0;
@@ -49,6 +49,9 @@ struct jf_engine {
   bool finalized = false;
   // host mirrors
   std::vector<SeqState> h_states;
+  // per-call draft sources of jf_jacobi_run (first-call tokens, MT19937 states, pad streams): grown on demand, kept
+  int* run_scratch[3] = {nullptr, nullptr, nullptr};
+  size_t run_scratch_words[3] = {0, 0, 0};
 };
 
 #define JF_CUDA(h, call)                                                                         \
@@ -364,6 +367,7 @@ extern "C" int jf_destroy(jf_handle h) {
   cudaStreamSynchronize(h->stream);
   for (void* p : h->ipc_maps) cudaIpcCloseMemHandle(p);
   for (void* p : h->allocs) cudaFree(p);
+  for (int* p : h->run_scratch) if (p) cudaFree(p);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -579,36 +583,38 @@ extern "C" int jf_load_tensor(jf_handle h, const char* name, const void* data, c
     if (r2 != JF_OK) return r2;
     JF_CUDA(h, cudaMemcpyAsync(const_cast<__nv_bfloat16*>(dst), h->stage, n * 2, cudaMemcpyDeviceToDevice, h->stream));
     JF_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->seen_layer[l] |= 0;   // placeholder, real bits tracked in seen_bits below
-    (void)bit;
+    h->seen_layer[l] |= (uint32_t)bit;
     return JF_OK;
   };
-  auto mat_pack = [&](const __nv_bfloat16* dst, int64_t R, int64_t K, int dest_row0) -> int {
+  auto mat_pack = [&](const __nv_bfloat16* dst, int64_t R, int64_t K, int dest_row0, int bit) -> int {
     if (!want(R, K)) return JF_ERR_INVALID;
     int r2 = stage_tensor(h, data, n, dtype);
     if (r2 != JF_OK) return r2;
-    return pack_staged(h, const_cast<__nv_bfloat16*>(dst), (int)R, (int)K, dest_row0);
+    r2 = pack_staged(h, const_cast<__nv_bfloat16*>(dst), (int)R, (int)K, dest_row0);
+    if (r2 == JF_OK) h->seen_layer[l] |= (uint32_t)bit;
+    return r2;
   };
-  auto bias_copy = [&](int off, int64_t len) -> int {
+  auto bias_copy = [&](int off, int64_t len, int bit) -> int {
     if (!want1(len)) return JF_ERR_INVALID;
     int r2 = stage_tensor(h, data, n, dtype);
     if (r2 != JF_OK) return r2;
     bf16_to_f32_kernel<<<64, 256, 0, h->stream>>>(h->stage, const_cast<float*>(lw.bqkv) + off, n);
     ++h->launches;
     JF_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->seen_layer[l] |= (uint32_t)bit;
     return JF_OK;
   };
   const int nt_i = (md.inter + 127) / 128;
-  if (rest == "self_attn.q_proj.weight") return mat_pack(lw.wqkv, md.q_dim, md.h, 0);
-  if (rest == "self_attn.k_proj.weight") return mat_pack(lw.wqkv, md.kv_dim, md.h, md.q_dim);
-  if (rest == "self_attn.v_proj.weight") return mat_pack(lw.wqkv, md.kv_dim, md.h, md.q_dim + md.kv_dim);
-  if (rest == "self_attn.q_proj.bias") return bias_copy(0, md.q_dim);
-  if (rest == "self_attn.k_proj.bias") return bias_copy(md.q_dim, md.kv_dim);
-  if (rest == "self_attn.v_proj.bias") return bias_copy(md.q_dim + md.kv_dim, md.kv_dim);
-  if (rest == "self_attn.o_proj.weight") return mat_pack(lw.wo, md.h, md.q_dim, 0);
-  if (rest == "mlp.gate_proj.weight") return mat_pack(lw.wgu, md.inter, md.h, 0);
-  if (rest == "mlp.up_proj.weight") return mat_pack(lw.wgu, md.inter, md.h, nt_i * 128);
-  if (rest == "mlp.down_proj.weight") return mat_pack(lw.wd, md.h, md.inter, 0);
+  if (rest == "self_attn.q_proj.weight") return mat_pack(lw.wqkv, md.q_dim, md.h, 0, W_Q);
+  if (rest == "self_attn.k_proj.weight") return mat_pack(lw.wqkv, md.kv_dim, md.h, md.q_dim, W_K);
+  if (rest == "self_attn.v_proj.weight") return mat_pack(lw.wqkv, md.kv_dim, md.h, md.q_dim + md.kv_dim, W_V);
+  if (rest == "self_attn.q_proj.bias") return bias_copy(0, md.q_dim, B_Q);
+  if (rest == "self_attn.k_proj.bias") return bias_copy(md.q_dim, md.kv_dim, B_K);
+  if (rest == "self_attn.v_proj.bias") return bias_copy(md.q_dim + md.kv_dim, md.kv_dim, B_V);
+  if (rest == "self_attn.o_proj.weight") return mat_pack(lw.wo, md.h, md.q_dim, 0, W_O);
+  if (rest == "mlp.gate_proj.weight") return mat_pack(lw.wgu, md.inter, md.h, 0, W_G);
+  if (rest == "mlp.up_proj.weight") return mat_pack(lw.wgu, md.inter, md.h, nt_i * 128, W_U);
+  if (rest == "mlp.down_proj.weight") return mat_pack(lw.wd, md.h, md.inter, 0, W_D);
   if (rest == "input_layernorm.weight") return vec_copy(lw.ln1, md.h, W_LN1);
   if (rest == "post_attention_layernorm.weight") return vec_copy(lw.ln2, md.h, W_LN2);
   if (rest == "self_attn.rotary_emb.inv_freq") return JF_OK;
@@ -622,6 +628,18 @@ extern "C" int jf_finalize_weights(jf_handle h) {
   if (!(h->seen_global & G_EMBED)) { h->err = "model.embed_tokens.weight was never loaded"; return JF_ERR_INVALID; }
   if (!(h->seen_global & G_HEAD)) { h->err = "lm_head.weight was never loaded (and tie_word_embeddings is off)"; return JF_ERR_INVALID; }
   if (!(h->seen_global & G_NORM)) { h->err = "model.norm.weight was never loaded"; return JF_ERR_INVALID; }
+  {   // every layer must have received all of its matrices and norms (the q/k/v biases are optional: zero when absent)
+    static const struct { int bit; const char* name; } kNeeded[] = {
+        {W_Q, "self_attn.q_proj.weight"}, {W_K, "self_attn.k_proj.weight"}, {W_V, "self_attn.v_proj.weight"},
+        {W_O, "self_attn.o_proj.weight"}, {W_G, "mlp.gate_proj.weight"}, {W_U, "mlp.up_proj.weight"},
+        {W_D, "mlp.down_proj.weight"}, {W_LN1, "input_layernorm.weight"}, {W_LN2, "post_attention_layernorm.weight"}};
+    for (int l = 0; l < h->md.layers; ++l)
+      for (const auto& nd : kNeeded)
+        if (!(h->seen_layer[l] & (uint32_t)nd.bit)) {
+          h->err = "model.layers." + std::to_string(l) + "." + nd.name + " was never loaded";
+          return JF_ERR_INVALID;
+        }
+  }
   JF_CUDA(h, cudaMemcpyAsync(h->dctx, &h->hctx, sizeof(DevCtx), cudaMemcpyHostToDevice, h->stream));
   JF_CUDA(h, cudaStreamSynchronize(h->stream));
   h->finalized = true;
@@ -816,29 +834,34 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
   const int cr = (rng_state && rng_words >= 625) ? rng_words : 0;
   // device copies of the draft sources
   int *d_first = nullptr, *d_choice = nullptr, *d_pad = nullptr;
-  std::vector<void*> tmp_allocs;
-  auto tmp_alloc = [&](int** p, size_t count) -> int {
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, count * 4 > 0 ? count * 4 : 16);
-    if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return JF_ERR_CUDA; }
-    tmp_allocs.push_back(q);
-    *p = reinterpret_cast<int*>(q);
+  // engine-owned scratch, grown on demand and kept between calls (no cudaMalloc / cudaFree on the per-call path)
+  auto tmp_alloc = [&](int** p, size_t count, int which) -> int {
+    if (count > h->run_scratch_words[which]) {
+      void* q = nullptr;
+      const size_t words = count + count / 2 + 256;
+      cudaError_t e = cudaMalloc(&q, words * 4);
+      if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return JF_ERR_CUDA; }
+      if (h->run_scratch[which]) cudaFree(h->run_scratch[which]);
+      h->run_scratch[which] = reinterpret_cast<int*>(q);
+      h->run_scratch_words[which] = words;
+    }
+    *p = h->run_scratch[which];
     return JF_OK;
   };
-  auto cleanup = [&]() { for (void* p : tmp_allocs) cudaFree(p); };
+  auto cleanup = [&]() {};
   int rc = JF_OK;
 #define TRY(x) do { rc = (x); if (rc != JF_OK) { cleanup(); return rc; } } while (0)
 #define TRYC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); return JF_ERR_CUDA; } } while (0)
   if (first_call_tokens) {
-    TRY(tmp_alloc(&d_first, (size_t)n_seqs * n));
+    TRY(tmp_alloc(&d_first, (size_t)n_seqs * n, 0));
     TRYC(cudaMemcpyAsync(d_first, first_call_tokens, (size_t)n_seqs * n * 4, cudaMemcpyHostToDevice, h->stream));
   }
   if (cr > 0) {
-    TRY(tmp_alloc(&d_choice, (size_t)n_seqs * cr));
+    TRY(tmp_alloc(&d_choice, (size_t)n_seqs * cr, 1));
     TRYC(cudaMemcpyAsync(d_choice, rng_state, (size_t)n_seqs * cr * 4, cudaMemcpyHostToDevice, h->stream));
   }
   if (pad_stream && pad_stream_len > 0) {
-    TRY(tmp_alloc(&d_pad, (size_t)n_seqs * pad_stream_len));
+    TRY(tmp_alloc(&d_pad, (size_t)n_seqs * pad_stream_len, 2));
     TRYC(cudaMemcpyAsync(d_pad, pad_stream, (size_t)n_seqs * pad_stream_len * 4, cudaMemcpyHostToDevice, h->stream));
   }
   std::vector<PolicyKnobs> hk(n_seqs, kn);

@@ -57,7 +57,7 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
       for (int r = 0; r < c.tp_size; ++r) {
         if (r == c.tp_rank) continue;
         while (ld_relaxed_sys_u64(c.xflag + r) < val)
-          if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+          if (clock64() - t0 > JF_XSPIN_LIMIT_CYCLES) jf_trap_timeout();
       }
       fence_acq_rel_sys();
       red_release_gpu_add_u32(c.bar_counter, 1u);              // the extra arrival releases this GPU's CTAs

@@ -19,7 +19,14 @@ namespace jf {
 // error reporting / watchdog
 // ----------------------------------------------------------------------------------------------------------
 #ifndef JF_SPIN_LIMIT_CYCLES
-#define JF_SPIN_LIMIT_CYCLES (4000000000LL)   // ~2 s at 1.9 GHz: far above any legitimate wait on this path
+#define JF_SPIN_LIMIT_CYCLES (20000000000LL)  // ~10 s at 1.9 GHz: far above any legitimate wait on this path.  Under
+#endif                                        // tensor parallelism EVERY wait can transitively depend on a peer process.
+
+// Waits on ANOTHER GPU (tensor-parallel peers are separate processes: host-side skew - page faults, GC, a first-call
+// overhead on one rank - is legitimate) get a larger budget still; the host ranks also meet before every TP launch
+// (JacobiRuntime._tp_sync), so the skew a kernel sees is launch jitter, not Python time.
+#ifndef JF_XSPIN_LIMIT_CYCLES
+#define JF_XSPIN_LIMIT_CYCLES (40000000000LL)
 #endif
 
 __device__ __forceinline__ void jf_trap_timeout() {
@@ -265,8 +272,9 @@ __device__ __forceinline__ ulonglong2 ld_cg_poll_u64x2(const unsigned long long*
   return v;
 }
 // Against a tensor-parallel peer's memory (NVLink) strong loads are served one at a time (~2 us each, measured), so
-// the peers' words are fetched with WEAK loads - they pipeline - and a failed tag check is followed by a system-scope
-// acquire fence (which also drops this SM's L1 copies) before the next attempt.
+// the peers' words are fetched with WEAK loads - they pipeline - and a failed tag check is followed by
+// fence.acq_rel.sys (system scope: the writer is another device; it also drops this SM's L1 copies) before the next
+// attempt, the same pattern grid_barrier uses for the cross-GPU flags.
 __device__ __forceinline__ ulonglong2 ld_weak_poll_u64x2(const unsigned long long* p) {
   ulonglong2 v;
   asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");

@@ -264,8 +264,8 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
 #pragma unroll
             for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
           if (ok) break;
-          if (TP > 1) fence_acq_rel_gpu();              // drops the L1 copies of the words that were not there yet
-          if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
+          if (TP > 1) fence_acq_rel_sys();              // system scope (the writer is a peer GPU); drops the stale L1 copies
+          if (clock64() - t0 > (TP > 1 ? JF_XSPIN_LIMIT_CYCLES : JF_SPIN_LIMIT_CYCLES)) jf_trap_timeout();
         }
 #pragma unroll
         for (int s2 = 0; s2 < SPLITS; ++s2)

@@ -39,8 +39,16 @@ class BlockManager:
         seq.num_cached_tokens = 0
         seq.block_table.clear()
 
-    def can_append(self, seq: Sequence) -> bool:
-        return len(self.free_block_ids) >= 1
+    def pages_missing(self, seq: Sequence, n_tokens: int) -> int:
+        """Pages the table lacks to cover n_tokens."""
+        return max(0, (n_tokens + self.block_size - 1) // self.block_size - len(seq.block_table))
+
+    def can_append(self, seq: Sequence, need_tokens: int = None) -> bool:
+        """Reference predicate (:192-193): a page is needed only when the next token opens one.  A Jacobi decode call
+        appends many tokens; the scheduler passes the token count the call must be able to hold."""
+        if need_tokens is not None:
+            return len(self.free_block_ids) >= self.pages_missing(seq, need_tokens)
+        return len(self.free_block_ids) >= (len(seq) % self.block_size == 1)
 
     def may_append(self, seq: Sequence) -> None:
         self.ensure(seq, len(seq))

@@ -131,10 +131,28 @@ class ModelRunner:
         return [[] for _ in seqs]
 
     # ---- decode -------------------------------------------------------------------------------------------------------
+    def _fit_new_tokens(self, seqs: List[Sequence], remaining: int, L: int) -> int:
+        """Largest per-call token budget <= remaining whose KV reservation (len + budget + 3L + 1 per request) fits the
+        free pages.  The reference grows pages per iteration and preempts (scheduler.py:47-60); one device-resident call
+        cannot, so a call that does not fit entirely is SHORTENED and the request returns to the scheduler, which
+        re-schedules or preempts.  The scheduler has already reserved one block's worth per request."""
+        bm = self.block_manager
+        free = len(bm.free_block_ids)
+        need = lambda new: sum(bm.pages_missing(s, len(s) + new + 3 * L + 1) for s in seqs)
+        new = remaining
+        while new > L and need(new) > free:
+            new = max(L, new - PAGE // 2)
+        new = min(new, remaining)
+        if need(new) > free:
+            raise RuntimeError("out of KV cache blocks: not even one Jacobi block fits "
+                               f"({need(new)} pages needed, {free} free)")
+        return new
+
     def _run_jacobi_group(self, seqs: List[Sequence], mode: str) -> List[List[int]]:
         s0 = seqs[0]
         L = int(s0.jacobi_block_len)
         remaining = max(1, int(s0.max_tokens) - s0.num_completion_tokens)
+        remaining = self._fit_new_tokens(seqs, remaining, L)
         eos = self.config.eos if self.config.eos is not None and self.config.eos >= 0 else None
         pad = self.config.pad if self.config.pad is not None and self.config.pad >= 0 else None
         V = self.rt.vocab
@@ -197,7 +215,8 @@ class ModelRunner:
         groups: Dict[tuple, List[int]] = {}
         for i, s in enumerate(seqs):                                          # group-by-L (jacobi_decoding.py:500-515)
             key = (int(s.jacobi_block_len), int(s.jacobi_max_iterations), int(s.max_tokens) - s.num_completion_tokens,
-                   int(s.jacobi_max_blocks), float(s.jacobi_spawn_ratio), int(s.jacobi_n_gram_pool_size))
+                   int(s.jacobi_max_blocks), float(s.jacobi_spawn_ratio), int(s.jacobi_n_gram_pool_size),
+                   float(s.jacobi_lookahead_start_ratio))
             groups.setdefault(key, []).append(i)
         out: List[Optional[List[int]]] = [None] * len(seqs)
         for idxs in groups.values():

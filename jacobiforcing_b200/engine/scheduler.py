@@ -41,7 +41,10 @@ class Scheduler:
         if admitted:
             return admitted, True
         chosen = self._pick_running()
-        assert chosen, "nothing can be scheduled"
+        if not chosen:
+            # the reference asserts here too (scheduler.py:58); say why
+            raise AssertionError("nothing can be scheduled: the KV cache / token budget cannot hold a single request "
+                                 "(raise num_kvcache_blocks / max_num_batched_tokens or lower jacobi_block_len)")
         self.running.extendleft(reversed(chosen))        # keep them at the head, in order
         return chosen, False
 
@@ -59,12 +62,22 @@ class Scheduler:
             admitted.append(seq)
         return admitted
 
+    @staticmethod
+    def jacobi_min_tokens(seq: Sequence) -> int:
+        """Tokens the next Jacobi decode call must be able to hold to make progress: one block of accepted tokens plus
+        the in-flight margin the device loop writes past them (draft + pseudo block + next token)."""
+        L = int(seq.jacobi_block_len)
+        remaining = max(1, int(seq.max_tokens) - seq.num_completion_tokens)
+        return len(seq) + min(remaining, L) + 3 * L + 1
+
     def _pick_running(self) -> List[Sequence]:
         chosen: List[Sequence] = []
         while self.running and len(chosen) < self.max_num_seqs:
             seq = self.running.popleft()
+            jacobi = str(getattr(seq, "decode_strategy", "")).startswith("jacobi")
+            need = self.jacobi_min_tokens(seq) if jacobi else None
             evicted_self = False
-            while not self.block_manager.can_append(seq):
+            while not self.block_manager.can_append(seq, need):
                 if self.running:
                     self.preempt(self.running.pop())     # youngest first
                 else:
@@ -73,7 +86,11 @@ class Scheduler:
                     break
             if evicted_self:
                 continue
-            if not str(getattr(seq, "decode_strategy", "")).startswith("jacobi"):
+            if jacobi:
+                # reserve the minimum now (several requests may pass can_append against the same free pages); the
+                # runner grows the reservation towards the whole remaining budget when pages allow, else caps the call
+                self.block_manager.ensure(seq, need)
+            else:
                 self.block_manager.may_append(seq)
             chosen.append(seq)
         return chosen

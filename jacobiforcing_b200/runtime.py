@@ -86,8 +86,18 @@ class JacobiRuntime:
         self.free_pages = list(range(num_kv_pages - 1, -1, -1))
         self._next_seq = 0
         self.stats = {"forwards": 0, "device_ms": 0.0, "rows": 0}
+        self._tp_group = tp_group
         if tp_size > 1:
             self._connect_peers(tp_group)
+
+    def _tp_sync(self) -> None:
+        """Host-side rendezvous before every tensor-parallel launch: the ranks are independent processes and only meet
+        inside the kernel, whose cross-GPU waits are bounded (a rank that is seconds late - GC, tokenizer, page faults -
+        would otherwise trip its peers' watchdog)."""
+        if self.tp_size > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.barrier(group=self._tp_group)
 
     def _connect_peers(self, group) -> None:
         """Exchange the CUDA IPC handles of the activation arenas (torch.distributed is only the transport) so the
@@ -234,6 +244,7 @@ class JacobiRuntime:
         logits = np.zeros((lm_rows, self.vocab_local), np.float32) if want_logits else None   # this rank's vocabulary slice
         hidden = np.zeros((T, self.hidden), np.uint16) if want_hidden else None
         ms = C.c_float()
+        self._tp_sync()
         _cabi.check(self.lib.jf_forward(self.h, T, _ptr(tokens), groups.shape[0], _ptr(groups), len(seqs), _ptr(bt),
                                         lm_row0, lm_rows, commits.shape[0], _ptr(commits), _ptr(greedy), _ptr(logits),
                                         _ptr(hidden), C.byref(ms)), self.h)
@@ -248,6 +259,7 @@ class JacobiRuntime:
         if commits.shape[0] == 0:
             return
         bt = self._block_tables(seqs)
+        self._tp_sync()
         _cabi.check(self.lib.jf_commit_rows(self.h, len(seqs), _ptr(bt), commits.shape[0], _ptr(commits)), self.h)
 
     # ---- prefill-with-drafting (unified.py:175-225 / model_runner.py:777-963) ---------------------------------------
@@ -323,6 +335,7 @@ class JacobiRuntime:
         stats = np.zeros(4, np.float32)
         trace = np.zeros(max(self.trace_capacity, 1), np.int32) if want_trace else None
         tl = C.c_int32(0)
+        self._tp_sync()
         rc = self.lib.jf_jacobi_run(self.h, B, C.byref(kc), _ptr(prompts), _ptr(plens), _ptr(ctxs), _ptr(fc), _ptr(fct),
                                     _ptr(ch), ch_rows, _ptr(pad), pad_len, _ptr(bt), max_forwards, _ptr(out), out_cap,
                                     _ptr(summ), _ptr(iters), _ptr(stats), _ptr(trace), C.byref(tl))

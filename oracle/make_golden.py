@@ -199,8 +199,19 @@ def main():
     run_case("multi_n8_k3_quirk", "tiny", 0, 24, 8, 40, "multiblock", K=3, r=0.5, pool=4, max_iteration_count=40)
 
 
-if __name__ == "__main__" and "--engine" not in sys.argv:
+def main_r2():
+    """Round-2 additions: the headline block size n=32 (BASELINE configs 2-4) and the README-recommended n=64
+    (config 5), single block and multiblock + rejection recycling."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    run_case("single_n32", "tiny", 11, 40, 32, 64, "single")
+    run_case("multi_n32_k2_pool4", "tiny", 12, 40, 32, 96, "multiblock", K=2, r=0.85, pool=4)
+    run_case("multi_n64_k2_pool4_tiny128", "tiny128", 13, 48, 64, 128, "multiblock", K=2, r=0.85, pool=4)
+
+
+if __name__ == "__main__" and "--engine" not in sys.argv and "--r2" not in sys.argv:
     main()
+if __name__ == "__main__" and "--r2" in sys.argv:
+    main_r2()
 
 
 # --------------------------------------------------------------------------------------------------------------------

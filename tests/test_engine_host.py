@@ -120,3 +120,61 @@ def test_scheduler_respects_limits_and_preempts():
     big.add(Sequence(list(range(9))))
     with pytest.raises(AssertionError):                  # nothing can be scheduled: the reference asserts too (:58)
         big.schedule()
+
+
+def test_jacobi_requests_under_kv_memory_pressure_finish_without_crashing():
+    """8 Jacobi requests with max_tokens=2048 on a 40-page cache.  The scheduler reserves one block's worth
+    per admitted request and preempts the youngest when pages run out; the runner shortens a decode call whose whole
+    remaining budget does not fit instead of raising 'out of KV cache blocks'."""
+    from types import SimpleNamespace
+    from jacobiforcing_b200.engine.model_runner import ModelRunner
+    cfg = _cfg()
+    cfg.num_kvcache_blocks = 40
+    sch = Scheduler(cfg)
+    bm = sch.block_manager
+    runner = SimpleNamespace(block_manager=bm)
+    L = 32
+    sp = SamplingParams(temperature=0.0, max_tokens=2048, decode_strategy="jacobi", jacobi_block_len=L, ignore_eos=True)
+    reqs = [Sequence(list(range(1, 300 + 7 * i)), sp) for i in range(8)]
+    for r in reqs:
+        sch.add(r)
+    steps = preempted = 0
+    while not sch.is_finished():
+        steps += 1
+        assert steps < 2000, "scheduler does not make progress"
+        before = len(sch.waiting)
+        seqs, is_prefill = sch.schedule()
+        if not is_prefill:
+            preempted += max(0, len(sch.waiting) - before)
+        if is_prefill:
+            for s in seqs:
+                s.num_cached_tokens = len(s)
+            continue
+        remaining = max(1, sp.max_tokens - seqs[0].num_completion_tokens)
+        groups = {}
+        for s in seqs:
+            groups.setdefault(sp.max_tokens - s.num_completion_tokens, []).append(s)
+        outs = {}
+        for rem, grp in groups.items():
+            new = ModelRunner._fit_new_tokens(runner, grp, max(1, rem), L)
+            assert 1 <= new <= max(1, rem)
+            for s in grp:
+                bm.ensure(s, len(s) + new + 3 * L + 1)        # what _run_jacobi_group reserves; must not raise
+                toks = [7] * new
+                s.extend_tokens(toks)
+                outs[s.seq_id] = toks
+        sch.postprocess_jacobi(seqs, [outs[s.seq_id] for s in seqs])
+    assert all(r.num_completion_tokens >= 2048 for r in reqs)
+    assert len(bm.free_block_ids) == 40 and not bm.used_block_ids
+    assert preempted > 0                                       # the pressure was real
+
+
+def test_can_append_predicates():
+    bm = BlockManager(1, 256)
+    s = Sequence(list(range(256)))
+    bm.allocate(s)
+    assert not bm.free_block_ids
+    assert bm.can_append(s)                                    # reference predicate: only a page-opening token needs one
+    s.extend_tokens([1])
+    assert not bm.can_append(s)                                # len % 256 == 1 and nothing free
+    assert bm.can_append(s, need_tokens=256) and not bm.can_append(s, need_tokens=258)

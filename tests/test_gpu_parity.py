@@ -25,7 +25,8 @@ NEAR_TIE = 3e-2
 @pytest.fixture(scope="module", params=["tiny", "tiny128"])
 def pair(request):
     from tests.gpu_helpers import make_pair
-    model, rt = make_pair(request.param)
+    # rows: n=64 multiblock keeps up to (1 + pool) candidate rows of 2n columns in flight
+    model, rt = make_pair(request.param, max_rows=1024)
     yield request.param, model, rt
     rt.close()
 
@@ -89,7 +90,10 @@ def test_prefill_chunked_equals_unchunked(pair):
 
 CASES = [("single", 8, 40, dict()), ("multiblock", 8, 40, dict(K=2, r=0.85, pool=4)),
          ("multiblock", 16, 64, dict(K=2, r=0.5, pool=8)), ("multiblock", 8, 32, dict(K=1, r=0.85, pool=1)),
-         ("multiblock", 8, 40, dict(K=2, r=0.85, pool=4, lsr=0.5))]
+         ("multiblock", 8, 40, dict(K=2, r=0.85, pool=4, lsr=0.5)),
+         # the headline block size (BASELINE configs 2-4) and the README-recommended n=64 (config 5)
+         ("single", 32, 96, dict()), ("multiblock", 32, 96, dict(K=2, r=0.85, pool=4)),
+         ("multiblock", 64, 160, dict(K=2, r=0.85, pool=4)), ("multiblock", 32, 64, dict(K=2, r=0.5, pool=8))]
 
 
 def _oracle_on_device(rt, prompt, mode, n, max_new, K=2, r=0.85, pool=4, lsr=0.0, eos=None, seed=2):
@@ -139,6 +143,40 @@ def test_device_loop_equals_oracle_policy_bit_exact(pair, mode, n, max_new, kw):
     assert run["forwards"] == sum(iters)
     for s in seqs:
         rt.release(s)
+
+
+def test_batch8_multiblock_equals_oracle_policy_bit_exact():
+    """BASELINE config 3 shape of work (B=8 multiblock + rejection recycling, n=32): every sequence of the batched
+    device-resident loop equals the oracle policy run on that sequence alone (ids, per-call iterations, stop reason)."""
+    from jacobiforcing_b200.runtime import hf_generate
+    from tests.gpu_helpers import make_pair
+    model, rt = make_pair("tiny128", max_rows=2560, max_seqs=8, num_kv_pages=32, max_pages_per_seq=4)
+    prompts = [_prompt(model, 20 + 5 * i, seed=30 + i) for i in range(8)]
+    mk = lambda: [random.Random(200 + i) for i in range(8)]
+    kw = dict(K=2, r=0.85, pool=4)
+    seqs, batch, run = hf_generate(rt, prompts, n=32, max_new_tokens=64, mode="multiblock", K=2, r=0.85,
+                                   n_gram_pool_size=4, pad=0, rngs=mk())
+    for s in seqs:
+        rt.release(s)
+    assert run["rows"] / run["forwards"] > 32 * 4          # really a batched forward
+    for i in range(8):
+        toks, iters, stop, _ = _oracle_on_device(rt, prompts[i], "multiblock", 32, 64, seed=200 + i, **kw)
+        assert batch[i].tokens == toks, f"sequence {i}"
+        assert batch[i].iters == iters and batch[i].stop_reason == stop
+    rt.close()
+
+
+def test_finalize_rejects_partial_checkpoint():
+    """a checkpoint that lacks a layer tensor must not finalize (zero weights would decode garbage)."""
+    from jacobiforcing_b200.runtime import JacobiRuntime
+    from oracle.hf_model import build_model, state_dict_bf16
+    model = build_model("tiny", seed=0, dtype=torch.float32)
+    sd = state_dict_bf16(model)
+    del sd["model.layers.1.mlp.up_proj.weight"]
+    rt = JacobiRuntime(model.config, max_rows=64, max_seqs=1, num_kv_pages=2, max_pages_per_seq=2)
+    with pytest.raises(ValueError, match="model.layers.1.mlp.up_proj.weight"):
+        rt.load_state_dict(sd)
+    rt.close()
 
 
 def test_eos_paths_bit_exact(pair):
