@@ -44,16 +44,20 @@ SHAPES = {
 }
 
 
-def algorithmic_bytes_per_forward(cfg: dict, rows: float, ctx: float, batch_groups: float, tp: int = 1) -> float:
-    """SURVEY.md section 8(d), per GPU: every layer weight + LM head once (1/tp of them), committed KV once per group,
-    in-flight KV written and read (1/tp of the heads), embedding rows gathered.  Logits are never materialised."""
+def algorithmic_bytes_per_forward(cfg: dict, rows: float, ctx: float, batch_groups: float, tp: int = 1,
+                                  shard_attention: bool = False) -> float:
+    """SURVEY.md section 8(d), per GPU: every layer weight + LM head once, committed KV once per group, in-flight KV
+    written and read, embedding rows gathered.  Logits are never materialised.  Tensor parallelism: the MLP and the LM
+    head are sharded tp ways; the attention block (weights, KV) is sharded only with shard_attention, else replicated."""
     h, L, I, V = cfg["hidden_size"], cfg["num_hidden_layers"], cfg["intermediate_size"], cfg["vocab_size"]
     q = cfg["num_attention_heads"] * cfg["head_dim"]
     kv = cfg["num_key_value_heads"] * cfg["head_dim"]
-    w_layer = 2 * (h * (q + 2 * kv) + (q + 2 * kv) + q * h + 3 * h * I + 2 * h)
-    w_head = 2 * V * h
-    kvb = L * 2 * kv * 2
-    return (L * w_layer + w_head + batch_groups * ctx * kvb + rows * kvb) / tp + rows * h * 2
+    tpa = tp if shard_attention else 1
+    w_attn = 2 * (h * (q + 2 * kv) + (q + 2 * kv) + q * h) / tpa
+    w_mlp = 2 * (3 * h * I) / tp
+    w_head = 2 * V * h / tp
+    kvb = L * 2 * kv * 2 / tpa
+    return L * (w_attn + w_mlp + 2 * 2 * h) + w_head + batch_groups * ctx * kvb + rows * kvb + rows * h * 2
 
 
 class ClockSampler:
@@ -217,9 +221,13 @@ def workload_config(args, world: int, where: str) -> dict:
                                "single-block Jacobi",
             "parallelism": ("single GPU" if world == 1 else
                             (f"{world} independent engines, one sequence batch per GPU, no data-path collective "
-                             "(tensor-parallel kernel available with --tp 2|4)") if getattr(args, "_tp", 1) == 1 else
-                            (f"tp{args._tp} x {world // args._tp} group(s): tensor-parallel column/row split with in-kernel "
-                             "peer-memory all-reduce over NVLink inside a group, independent sequence batches across groups")),
+                             "(--replicas)") if getattr(args, "_tp", 1) == 1 else
+                            (f"tp{args._tp} x {world // args._tp} group(s): tensor-parallel column/row split of "
+                             + ("every linear layer (two exchanges per block)" if args.tp_shard_attention else
+                                "gate/up/down + vocabulary-parallel LM head, attention replicated (ONE exchange per "
+                                "transformer block)")
+                             + ", in-kernel reduce-scatter + all-gather by push over NVLink peer memory (no NCCL on the "
+                               "data path), independent sequence batches across groups")),
             "l2_policy": "inputs larger than L2: every forward streams 15.2 GB of weights (L2 = 126 MB)",
             "where": where}
 
@@ -237,14 +245,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
     cfg = SHAPES[args.model]
-    # Layout at N GPUs: tensor parallelism inside groups of tp ranks (the path shards along heads / intermediate /
-    # vocabulary), independent sequence batches across groups.  Qwen2.5-7B has 4 KV heads -> tp <= 4.
-    # Default: tp = 1 (N independent engines, weak scaling).  The tensor-parallel kernel is selected with --tp 2|4; at
-    # batch 1 it does not yet beat one GPU (latency-bound stages + cross-GPU barriers, profiles/r01_tp_*.txt), so the
-    # aggregate-throughput headline uses replicas, exactly how the reference's own sweep uses several GPUs
-    # (JacobiForcing/scripts/inference/scanning_hyperparameter_jacobi_decoding_mr.sh:31-45).
-    tp = args.tp if args.tp > 0 else 1
-    if world % tp or cfg["num_key_value_heads"] % tp or tp not in (1, 2, 4):
+    # Layout at N GPUs (BASELINE.json north_star): ONE tensor-parallel group of N ranks - the path shards along the
+    # intermediate / vocabulary dimensions (and the heads with --tp-shard-attention), strong scaling of the batch-1
+    # headline.  --tp T < N: N / T groups with independent sequence batches; --replicas: N independent engines (how the
+    # reference's own sweep uses several GPUs, scripts/inference/scanning_hyperparameter_jacobi_decoding_mr.sh:31-45).
+    tp = 1 if args.replicas else (args.tp if args.tp > 0 else world)
+    if world % tp or tp not in (1, 2, 4, 8) or (args.tp_shard_attention and cfg["num_key_value_heads"] % tp):
         raise SystemExit(f"--tp {tp} does not fit {world} GPUs / {cfg['num_key_value_heads']} KV heads")
     groups = world // tp
     args._tp = tp
@@ -262,7 +268,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     pages = (P + G + 3 * n + 255) // 256 + 1
     rt = JacobiRuntime(cfg, device=local_rank, max_rows=rows_cap, max_seqs=B, num_kv_pages=pages * B,
                        max_pages_per_seq=pages, gen_capacity=P + G + 4 * n + 8, max_calls=G // n + 8,
-                       tp_rank=tp_rank, tp_size=tp, tp_group=tp_group)
+                       tp_rank=tp_rank, tp_size=tp, tp_group=tp_group, tp_shard_attention=args.tp_shard_attention)
     load_random_weights(rt, cfg, seed=1234 + group_id, device=device)
 
     knobs = PolicyKnobs(mode=MODES[args.mode], n=n, K=args.K, r=args.r, n_gram_pool_size=args.pool, eos=None, pad=0,
@@ -341,7 +347,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     mean_rows = rows / max(1, fwd)
     mean_ctx = P + G / 2.0
     groups_per_fwd = mean_rows / max(1.0, float(n)) if args.mode == "single" else max(1.0, mean_rows / (2.0 * n))
-    bytes_fwd = algorithmic_bytes_per_forward(cfg, mean_rows, mean_ctx, max(float(B), groups_per_fwd), tp)
+    bytes_fwd = algorithmic_bytes_per_forward(cfg, mean_rows, mean_ctx, max(float(B), groups_per_fwd), tp,
+                                              args.tp_shard_attention)
     bytes_launch = bytes_fwd * fwd / max(1, len(steps))
     launch_s = dev_s / max(1, len(steps))
     achieved = bytes_launch / launch_s / 1e9
@@ -350,11 +357,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "algorithmic_bytes_per_forward": bytes_fwd, "forwards_per_launch": fwd / max(1, len(steps)),
                 "ms_per_forward": 1e3 * dev_s / max(1, fwd)}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and tp == 1 and args.model == "qwen2.5-coder-7b" and B == 1:
         try:
             per_fwd = json.load(open(prof)).get("dram_bytes_per_forward")
             # ncu capture was one 32-forward launch; a bench launch runs `forwards_per_launch` forwards of the same shape
             roofline["traffic"] = per_fwd * roofline["forwards_per_launch"] if per_fwd else None
+            roofline["traffic_source"] = ("not measured in this run: dram__bytes_read+write per forward from the ncu "
+                                          "--set full capture recorded in profiles/traffic.json, times this launch's "
+                                          "forward count")
             roofline["achieved_bytes_per_launch"] = bytes_launch
         except Exception:
             pass
@@ -424,7 +434,9 @@ def main():
     ap.add_argument("--gen", type=int, default=512)
     ap.add_argument("--ref-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel group size: 2 or 4 shard the kernel over NVLink; default (0) = N independent engines")
+    ap.add_argument("--tp", type=int, default=0, help="tensor-parallel group size (1, 2, 4, 8); default (0) = all N GPUs in one group")
+    ap.add_argument("--replicas", action="store_true", help="N independent engines instead of tensor parallelism")
+    ap.add_argument("--tp-shard-attention", action="store_true", help="shard the attention block too (heads must divide tp)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                  # timing rule: at least three warm-up steps

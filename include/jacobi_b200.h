@@ -51,7 +51,10 @@ typedef struct {
   int32_t gen_capacity;           /* tokens (prompt + generated) kept per sequence on the device */
   int32_t max_calls;              /* rows of the per-call iteration log */
   int32_t trace_capacity;         /* int32 words of forward trace kept per run (0 = off) */
-  int32_t tp_rank, tp_size;       /* tensor parallelism: this process's rank / ranks (1, 2 or 4; 0 = 1) */
+  int32_t tp_rank, tp_size;       /* tensor parallelism: this rank / ranks (1, 2, 4 or 8; 0 = 1) */
+  int32_t tp_attn;                /* ranks the attention block is sharded over: 0 / 1 = replicated on every rank (MLP-only
+                                     tensor parallelism, one exchange per transformer block); tp_size = sharded */
+  int32_t num_ctas;               /* CTAs of the persistent kernel (0 = one per SM); fewer lets several ranks share a GPU */
 } jf_runtime_cfg;
 
 /* Greedy Jacobi policy knobs (field order = struct jf::PolicyKnobs, csrc/jf_policy.h).  mode: 0 = HF single block
@@ -127,13 +130,18 @@ int jf_profile_enable(jf_handle h, int32_t forward_index);
 int jf_profile_read(jf_handle h, int64_t* stamps, int32_t capacity, int32_t* n_stamps, int32_t* sm_clock_khz);
 
 /* Tensor parallelism over NVLink peer memory (reference: column/row-parallel linears + dist.all_reduce,
- * inference_engine/layers/linear.py:76-153, vocab-parallel LM head + gather, layers/embed_head.py:56-66).  One process
- * per GPU; jf_model_cfg describes the FULL model, jf_load_tensor receives this rank's shard of each sharded tensor
- * (q/k/v/gate/up rows, o/down columns, lm_head rows; embeddings and norms whole).  After jf_create every rank exports a
- * 64-byte IPC handle, the host exchanges them (any transport) and imports all of them in rank order; the kernel then
- * reads the peers' partial sums / argmax keys and signals barriers directly in peer memory.  Calls are collective. */
+ * inference_engine/layers/linear.py:76-153, vocab-parallel LM head + gather, layers/embed_head.py:56-66).  One rank per
+ * GPU; jf_model_cfg describes the FULL model, jf_load_tensor receives this rank's shard of each sharded tensor (gate/up
+ * rows, down columns, lm_head rows always; q/k/v rows and o columns when tp_attn = tp_size; embeddings and norms
+ * whole).  After jf_create every rank exports a 64-byte IPC handle, the host exchanges them (any transport) and imports
+ * all of them in rank order; the kernel then stores partial sums / finished rows straight into the peers' memory and
+ * reads their argmax keys there (no NCCL on the data path).  Calls are collective: every rank issues the same sequence
+ * of jf_forward / jf_commit_rows / jf_jacobi_run calls. */
 int jf_tp_export(jf_handle h, void* handle64);
 int jf_tp_import(jf_handle h, const void* handles /* tp_size x 64 bytes, rank order */);
+/* The same wiring for ranks that live in ONE process (one host thread per rank): peers[tp_size] = the ranks' handles in
+ * rank order.  The ranks may sit on different devices with peer access, or share one device (num_ctas splits its SMs). */
+int jf_tp_attach_local(jf_handle h, const jf_handle* peers);
 
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches claim). */
 int64_t jf_launch_count(jf_handle h);

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libjacobi_b200.so")
 EXPORTS = [
     "jf_create", "jf_destroy", "jf_last_error", "jf_device_info", "jf_load_tensor", "jf_finalize_weights",
     "jf_set_rope_tables", "jf_kv_info", "jf_forward", "jf_commit_rows", "jf_jacobi_run", "jf_launch_count",
-    "jf_profile_enable", "jf_profile_read", "jf_tp_export", "jf_tp_import",
+    "jf_profile_enable", "jf_profile_read", "jf_tp_export", "jf_tp_import", "jf_tp_attach_local",
 ]
 
 JF_OK, JF_ERR_INVALID, JF_ERR_CUDA, JF_ERR_CAPACITY, JF_ERR_UNSUPPORTED, JF_ERR_POLICY = 0, -1, -2, -3, -4, -5
@@ -28,7 +28,7 @@ class ModelCfg(C.Structure):
 class RuntimeCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "device", "max_rows", "max_seqs", "num_kv_pages", "max_pages_per_seq", "attn_chunk", "attn_slots",
-        "gen_capacity", "max_calls", "trace_capacity", "tp_rank", "tp_size")]
+        "gen_capacity", "max_calls", "trace_capacity", "tp_rank", "tp_size", "tp_attn", "num_ctas")]
 
 
 class PolicyKnobsC(C.Structure):
@@ -67,6 +67,7 @@ def load() -> C.CDLL:
     lib.jf_profile_read.argtypes = [vp, i64p, i32, i32p, i32p]
     lib.jf_tp_export.argtypes = [vp, vp]
     lib.jf_tp_import.argtypes = [vp, vp]
+    lib.jf_tp_attach_local.argtypes = [vp, C.POINTER(vp)]
     lib.jf_launch_count.argtypes = [vp]
     lib.jf_launch_count.restype = C.c_int64
     for name in EXPORTS:

@@ -15,13 +15,14 @@
 using namespace jf;
 
 static_assert(sizeof(jf_policy_knobs) == sizeof(PolicyKnobs), "jf_policy_knobs must mirror jf::PolicyKnobs");
-static_assert(sizeof(DevCtx) % 16 == 0 && sizeof(DevCtx) <= 4608, "DevCtx is staged in shared memory");
+static_assert(sizeof(DevCtx) % 16 == 0 && sizeof(DevCtx) <= 4864, "DevCtx is staged in shared memory");
 
 static thread_local std::string g_create_error;
 
 struct jf_engine {
   int device = 0;
   int sm_count = 0;
+  int num_ctas = 0;                  // CTAs of the persistent kernel (= sm_count unless jf_runtime_cfg.num_ctas asks for fewer)
   int smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -168,15 +169,24 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ModelDims& md = h->md;
   const int tp = r->tp_size > 1 ? r->tp_size : 1;
   const int tpr = r->tp_size > 1 ? r->tp_rank : 0;
-  if (tp != 1 && tp != 2 && tp != 4) { g_create_error = "tp_size must be 1, 2 or 4"; delete h; return JF_ERR_UNSUPPORTED; }
+  if (tp != 1 && tp != 2 && tp != 4 && tp != 8) { g_create_error = "tp_size must be 1, 2, 4 or 8"; delete h; return JF_ERR_UNSUPPORTED; }
   if (tpr < 0 || tpr >= tp) { g_create_error = "tp_rank outside [0, tp_size)"; delete h; return JF_ERR_INVALID; }
-  if (m->num_attention_heads % tp || m->num_key_value_heads % tp || m->intermediate_size % tp || m->vocab_size % tp) {
-    g_create_error = "heads / kv heads / intermediate_size / vocab_size must be divisible by tp_size "
-                     "(reference: inference_engine/models/qwen3.py:31,34)";
+  // tp_attn: ranks the attention block is sharded over.  0 / 1 = replicated on every rank (MLP-only tensor parallelism:
+  // one exchange per transformer block, no head-divisibility constraint); tp_size = sharded like the reference.
+  const int tpa = (tp > 1 && r->tp_attn == tp) ? tp : 1;
+  if (r->tp_attn != 0 && r->tp_attn != 1 && r->tp_attn != tp) { g_create_error = "tp_attn must be 0, 1 or tp_size"; delete h; return JF_ERR_INVALID; }
+  if (m->num_attention_heads % tpa || m->num_key_value_heads % tpa) {
+    g_create_error = "heads / kv heads must be divisible by tp_attn (reference: inference_engine/models/qwen3.py:31,34); "
+                     "use tp_attn = 1 (attention replicated) otherwise";
     delete h; return JF_ERR_INVALID;
   }
-  md.h = m->hidden_size; md.layers = m->num_hidden_layers; md.n_q = m->num_attention_heads / tp;
-  md.n_kv = m->num_key_value_heads / tp; md.d = m->head_dim; md.inter = m->intermediate_size / tp;
+  if (m->intermediate_size % tp || m->vocab_size % tp) {
+    g_create_error = "intermediate_size / vocab_size must be divisible by tp_size";
+    delete h; return JF_ERR_INVALID;
+  }
+  h->num_ctas = (r->num_ctas > 0 && r->num_ctas < h->sm_count) ? r->num_ctas : h->sm_count;
+  md.h = m->hidden_size; md.layers = m->num_hidden_layers; md.n_q = m->num_attention_heads / tpa;
+  md.n_kv = m->num_key_value_heads / tpa; md.d = m->head_dim; md.inter = m->intermediate_size / tp;
   md.vocab = m->vocab_size / tp; md.vocab_embed = m->vocab_size; md.vocab_offset = tpr * (m->vocab_size / tp);
   md.q_dim = md.n_q * md.d; md.kv_dim = md.n_kv * md.d; md.qkv_dim = md.q_dim + 2 * md.kv_dim;
   md.n_rep = md.n_kv > 0 ? md.n_q / md.n_kv : 0;
@@ -216,19 +226,17 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   const int kc_h = md.h / 64, kc_q = md.q_dim / 64, kc_i = md.inter / 64;
   const int nt_qkv = (md.qkv_dim + 127) / 128, nt_h = (md.h + 127) / 128, nt_i = (md.inter + 127) / 128;
   const int nt_v = (md.vocab + 127) / 128;
-  c.splits_qkv = pick_splits(nt_qkv, kc_h, h->sm_count);
-  c.splits_o = pick_splits(nt_h, kc_q, h->sm_count);
-  c.splits_down = pick_splits(nt_h, kc_i, h->sm_count);
+  c.splits_qkv = pick_splits(nt_qkv, kc_h, h->num_ctas);
+  c.splits_o = pick_splits(nt_h, kc_q, h->num_ctas);
+  c.splits_down = pick_splits(nt_h, kc_i, h->num_ctas);
   {
     const int nt_i = (md.inter + 127) / 128;
-    c.splits_gu = std::min(4, pick_splits(nt_i, kc_h, h->sm_count));
-    if (nt_i * c.splits_gu > h->sm_count) c.splits_gu = 1;          // the SwiGLU tail needs one unit per CTA at most
+    c.splits_gu = std::min(tp > 1 ? 8 : 4, pick_splits(nt_i, kc_h, h->num_ctas));
+    if (nt_i * c.splits_gu > h->num_ctas) c.splits_gu = 1;          // the SwiGLU tail needs one unit per CTA at most
     if (const char* e = getenv("JF_GU_SPLITS")) c.splits_gu = std::max(1, std::min(c.splits_gu, atoi(e)));
+    if (const char* e = getenv("JF_DOWN_SPLITS")) c.splits_down = std::max(1, std::min(c.splits_down, atoi(e)));
   }
-  const int rs_cap = tp == 1 ? 8 : (tp == 2 ? 4 : 2);       // rows_norm keeps tp * splits slices in flight
-  c.splits_o = std::min(c.splits_o, rs_cap);
-  c.splits_down = std::min(c.splits_down, rs_cap);
-  c.tp_rank = tpr; c.tp_size = tp;
+  c.tp_rank = tpr; c.tp_size = tp; c.tp_attn = tpa;
   h->max_splits = std::max(c.splits_qkv, std::max(c.splits_o, c.splits_down));
 
   int rc = JF_OK;
@@ -316,6 +324,15 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.part, (size_t)c.T_cap * c.part_splits * c.part_n, h->bytes_act);
   ALLOC(c.part_rs[0], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.part_rs[1], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
+  c.part_rs[2] = c.part_rs[0];
+  if (tp > 1 && tpa == 1) ALLOC(c.part_rs[2], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
+  if (tp > 1) {
+    unsigned long long *pb = nullptr, *sb = nullptr;
+    c.push_rows_cap = (kFuseRows + tp - 1) / tp + 8;
+    ALLOC(pb, (size_t)c.push_rows_cap * tp * md.h, h->bytes_act);
+    ALLOC(sb, (size_t)kFuseRows * md.h, h->bytes_act);              // [rows][h / 8][8] words
+    c.push_buf[tpr] = pb; c.stage_buf[tpr] = sb;
+  }
   ALLOC(c.tpart, (size_t)kFuseRopeRows * c.part_splits * c.part_n, h->bytes_act);
   c.tgu = nullptr;
   if (c.splits_gu > 1) ALLOC(c.tgu, (size_t)c.T_cap * c.splits_gu * 2 * md.inter, h->bytes_act);
@@ -344,8 +361,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   if ((rc = layout()) != JF_OK) return fail(rc, h->err);
   h->arena_mode = 0;
   for (int r2 = 0; r2 < kMaxTP; ++r2) {            // until jf_tp_import: every 'peer' is this rank itself
-    c.peer_part_rs[r2][0] = c.part_rs[0]; c.peer_part_rs[r2][1] = c.part_rs[1];
-    c.peer_tpart_rs[r2][0] = c.tpart_rs[0]; c.peer_tpart_rs[r2][1] = c.tpart_rs[1];
+    for (int b = 0; b < 3; ++b) c.peer_part_rs[r2][b] = c.part_rs[b];
+    c.push_buf[r2] = c.push_buf[tpr]; c.stage_buf[r2] = c.stage_buf[tpr];
     c.peer_keys[r2] = c.argmax_keys; c.peer_xflag[r2] = c.xflag;
   }
   if ((rc = dev_alloc(h, &h->stage, h->stage_elems, (int64_t*)nullptr)) != JF_OK) return fail(rc, h->err);
@@ -377,7 +394,7 @@ extern "C" int jf_destroy(jf_handle h) {
 
 extern "C" int jf_device_info(jf_handle h, int32_t* sm_count, int64_t* bw, int64_t* bkv, int64_t* bact) {
   if (!h) return JF_ERR_INVALID;
-  if (sm_count) *sm_count = h->sm_count;
+  if (sm_count) *sm_count = h->num_ctas;
   if (bw) *bw = h->bytes_weights;
   if (bkv) *bkv = h->bytes_kv;
   if (bact) *bact = h->bytes_act;
@@ -396,28 +413,55 @@ extern "C" int jf_tp_export(jf_handle h, void* handle64) {
   return JF_OK;
 }
 
+// every rank lays its activation arena out identically, so a peer's buffer sits at the same offset from its arena base
+static void map_peer(jf_engine* h, int r, uint8_t* base) {
+  DevCtx& c = h->hctx;
+  const uint8_t* mine = h->arena_base[2];
+  auto at = [&](const void* own) { return base + (reinterpret_cast<const uint8_t*>(own) - mine); };
+  for (int b = 0; b < 3; ++b) c.peer_part_rs[r][b] = reinterpret_cast<const float*>(at(c.part_rs[b]));
+  c.push_buf[r] = reinterpret_cast<unsigned long long*>(at(c.push_buf[c.tp_rank]));
+  c.stage_buf[r] = reinterpret_cast<unsigned long long*>(at(c.stage_buf[c.tp_rank]));
+  c.peer_keys[r] = reinterpret_cast<const unsigned long long*>(at(c.argmax_keys));
+  c.peer_xflag[r] = reinterpret_cast<unsigned long long*>(at(c.xflag));
+}
+
 extern "C" int jf_tp_import(jf_handle h, const void* handles) {
   if (!h || !handles) return JF_ERR_INVALID;
   cudaSetDevice(h->device);
   DevCtx& c = h->hctx;
-  const uint8_t* mine = h->arena_base[2];
   for (int r = 0; r < c.tp_size; ++r) {
-    uint8_t* base = h->arena_base[2];
-    if (r != c.tp_rank) {
-      cudaIpcMemHandle_t ipc;
-      memcpy(&ipc, reinterpret_cast<const uint8_t*>(handles) + (size_t)r * 64, 64);
-      void* p = nullptr;
-      JF_CUDA(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
-      h->ipc_maps.push_back(p);
-      base = reinterpret_cast<uint8_t*>(p);
+    if (r == c.tp_rank) continue;
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, reinterpret_cast<const uint8_t*>(handles) + (size_t)r * 64, 64);
+    void* p = nullptr;
+    JF_CUDA(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_maps.push_back(p);
+    map_peer(h, r, reinterpret_cast<uint8_t*>(p));
+  }
+  if (h->finalized) JF_CUDA(h, cudaMemcpy(h->dctx, &h->hctx, sizeof(DevCtx), cudaMemcpyHostToDevice));
+  return JF_OK;
+}
+
+extern "C" int jf_tp_attach_local(jf_handle h, const jf_handle* peers) {
+  if (!h || !peers) return JF_ERR_INVALID;
+  cudaSetDevice(h->device);
+  DevCtx& c = h->hctx;
+  for (int r = 0; r < c.tp_size; ++r) {
+    if (r == c.tp_rank) continue;
+    const jf_engine* p = peers[r];
+    if (!p || p->hctx.tp_size != c.tp_size || p->hctx.tp_rank != r || p->arena_off[2] != h->arena_off[2]) {
+      h->err = "jf_tp_attach_local: peer " + std::to_string(r) + " is not a rank of the same tensor-parallel group";
+      return JF_ERR_INVALID;
     }
-    // every rank lays its arena out identically, so a peer's buffer sits at the same offset
-    c.peer_part_rs[r][0] = reinterpret_cast<const float*>(base + (reinterpret_cast<const uint8_t*>(c.part_rs[0]) - mine));
-    c.peer_part_rs[r][1] = reinterpret_cast<const float*>(base + (reinterpret_cast<const uint8_t*>(c.part_rs[1]) - mine));
-    c.peer_tpart_rs[r][0] = reinterpret_cast<const unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.tpart_rs[0]) - mine));
-    c.peer_tpart_rs[r][1] = reinterpret_cast<const unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.tpart_rs[1]) - mine));
-    c.peer_keys[r] = reinterpret_cast<const unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.argmax_keys) - mine));
-    c.peer_xflag[r] = reinterpret_cast<unsigned long long*>(base + (reinterpret_cast<const uint8_t*>(c.xflag) - mine));
+    if (p->device != h->device) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, h->device, p->device);
+      if (!can) { h->err = "jf_tp_attach_local: no peer access between the ranks' devices"; return JF_ERR_UNSUPPORTED; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = "cudaDeviceEnablePeerAccess failed"; return JF_ERR_CUDA; }
+      cudaGetLastError();
+    }
+    map_peer(h, r, p->arena_base[2]);
   }
   if (h->finalized) JF_CUDA(h, cudaMemcpy(h->dctx, &h->hctx, sizeof(DevCtx), cudaMemcpyHostToDevice));
   return JF_OK;
@@ -677,6 +721,10 @@ static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float
     JF_CUDA(h, cudaMemsetAsync(c.tpart_rs[0], 0, (size_t)kFuseRows * c.part_splits * h->md.h * 8, h->stream));
     JF_CUDA(h, cudaMemsetAsync(c.tpart_rs[1], 0, (size_t)kFuseRows * c.part_splits * h->md.h * 8, h->stream));
     if (c.tgu) JF_CUDA(h, cudaMemsetAsync(c.tgu, 0, (size_t)c.T_cap * c.splits_gu * 2 * h->md.inter * 8, h->stream));
+    if (c.tp_size > 1) {
+      JF_CUDA(h, cudaMemsetAsync(c.push_buf[c.tp_rank], 0, (size_t)c.push_rows_cap * c.tp_size * h->md.h * 8, h->stream));
+      JF_CUDA(h, cudaMemsetAsync(c.stage_buf[c.tp_rank], 0, (size_t)kFuseRows * h->md.h * 8, h->stream));
+    }
     c.tag_base = 0u;
   }
   h->hctx.xflag_base += (1ull << 32);
@@ -688,7 +736,7 @@ static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float
   int smem_total = h->smem_optin;
   void* args[] = {(void*)&dctx, (void*)&smem_total, (void*)&run_mode, (void*)&max_forwards};
   JF_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  JF_CUDA(h, cudaLaunchCooperativeKernel((void*)jf_persistent_kernel, dim3(h->sm_count), dim3(kNumThreads), args,
+  JF_CUDA(h, cudaLaunchCooperativeKernel((void*)jf_persistent_kernel, dim3(h->num_ctas), dim3(kNumThreads), args,
                                          (size_t)smem_total, h->stream));
   ++h->launches;
   JF_CUDA(h, cudaEventRecord(h->ev1, h->stream));

@@ -12,7 +12,7 @@
 namespace jf {
 
 template <bool kSleep = true>
-__device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned int target) {
+__device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned int target, bool sys = false) {
   if (ld_relaxed_gpu_u32(counter) < target) {
     const long long t0 = clock64();
     while (ld_relaxed_gpu_u32(counter) < target) {
@@ -20,7 +20,10 @@ __device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned
       if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
     }
   }
-  fence_acq_rel_gpu();          // one acquire (one L1 invalidation) per barrier, not one per probe
+  // one acquire (one L1 invalidation) per barrier, not one per probe; system scope when the data published before the
+  // barrier may have been written by a tensor-parallel peer (finished rows copied out of the staging buffer are local
+  // writes, but the flag barriers of the prefill path order peer reads)
+  if (sys) fence_acq_rel_sys(); else fence_acq_rel_gpu();
 }
 
 // Grid barrier of the worker warps.  Writer side: every worker's global stores are ordered before the CTA barrier,
@@ -62,7 +65,7 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
       fence_acq_rel_sys();
       red_release_gpu_add_u32(c.bar_counter, 1u);              // the extra arrival releases this GPU's CTAs
     }
-    wait_epoch<false>(c.bar_counter, bs.target(w.nctas));      // critical path: spin, do not sleep
+    wait_epoch<false>(c.bar_counter, bs.target(w.nctas), xgpu);      // critical path: spin, do not sleep
     if (prof_slot && *prof_slot + 3 <= c.prof_cap) {      // (stage id, arrival of CTA 0, release of the barrier)
       c.prof[*prof_slot] = stage_id;
       c.prof[*prof_slot + 1] = t_arrive;
@@ -300,7 +303,8 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         const int n_tile = cta / t.splits, split = cta - n_tile * t.splits;
         if (fuse_kind == 3) qkv_rope_tail(c, ws, t.M, layer, n_tile, split, t.splits);
         else if (fuse_kind == 4) gu_swiglu_tail(c, ws, t.M, n_tile, split, t.splits);
-        else gemm_norm_tail(c, ws, t.M, n_tile, split, t.splits, normw, fuse_kind - 1);
+        else gemm_norm_tail(c, ws, t.M, n_tile, split, t.splits, normw, fuse_kind - 1,
+                            fuse_kind == 1 ? c.tp_attn > 1 : c.tp_size > 1);
       }
     }
     if (barrier_after) {
@@ -397,7 +401,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     nstages = min(kMaxStages, ring_bytes / slot_bytes);
     pipe.stage = 0;
 
-    JF_SIMT_STAGE(SID_EMBED, stage_commit(c, ws, ip.n_commit); stage_rows_norm(c, ws, T, true, 0, c.layer[0].ln1, 0));
+    JF_SIMT_STAGE(SID_EMBED, stage_commit(c, ws, ip.n_commit); stage_rows_norm(c, ws, T, true, 0, c.layer[0].ln1, 0, 1));
     // the fused tails apply to Jacobi-sized forwards on one GPU (see gemm_stage); prefill-sized ones keep the stages
     const bool fuse_ok = c.fuse_norm != 0 && T <= kFuseRows;
     const bool fuse_o = fuse_ok && nt_h * c.splits_o <= nctas;
@@ -422,9 +426,15 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       if (fused) { t.out = c.tpart; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; }
       return t;
     };
+    // stand-alone (prefill-sized) row-split stages: which fp32 partial buffer a projection uses.  Peers read the buffers of
+    // a sharded projection, so consecutive sharded projections alternate between two of them (O = 0, down = 1); with
+    // MLP-only tensor parallelism the down projections of consecutive layers alternate and the local O uses a third.
+    const bool mlp_only = tp && c.tp_attn == 1;
+    auto which_o = [&]() { return mlp_only ? 2 : 0; };
+    auto which_d = [&](int l) { return mlp_only ? (l & 1) : 1; };
     auto task_o = [&](int l, bool fused = false) {
       GemmTask t = base_task();
-      t.W = c.layer[l].wo; t.X = c.xa; t.out = c.part_rs[0]; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
+      t.W = c.layer[l].wo; t.X = c.xa; t.out = c.part_rs[which_o()]; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
       t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
       if (fused) { t.out = c.tpart_rs[0]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; }
       return t;
@@ -441,7 +451,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     };
     auto task_down = [&](int l, bool fused = false) {
       GemmTask t = base_task();
-      t.W = c.layer[l].wd; t.X = c.xact; t.out = c.part_rs[1]; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
+      t.W = c.layer[l].wd; t.X = c.xact; t.out = c.part_rs[which_d(l)]; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
       t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
       if (fused) { t.out = c.tpart_rs[1]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; }
       return t;
@@ -469,8 +479,8 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       if (fuse_o) {
         gemm_stage(task_o(l, true), true, SID_O_FUSED, false, 1, lw.ln2);
       } else {
-        gemm_stage(task_o(l), true, SID_O, tp);
-        JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, ws, T, false, c.splits_o, lw.ln2, 0));
+        gemm_stage(task_o(l), true, SID_O, c.tp_attn > 1);
+        JF_SIMT_STAGE(SID_O_NORM, if (!(c.debug_skip & 8)) stage_rows_norm(c, ws, T, false, c.splits_o, lw.ln2, which_o(), c.tp_attn));
       }
       const __nv_bfloat16* next_norm = (l + 1 < md.layers) ? c.layer[l + 1].ln1 : c.final_norm;
       if (dflow) {
@@ -487,7 +497,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         gemm_stage(task_down(l, true), true, SID_DOWN_FUSED, false, 2, next_norm);
       } else {
         gemm_stage(task_down(l), true, SID_DOWN, tp);
-        JF_SIMT_STAGE(SID_DOWN_NORM, stage_rows_norm(c, ws, T, false, c.splits_down, next_norm, 1));
+        JF_SIMT_STAGE(SID_DOWN_NORM, stage_rows_norm(c, ws, T, false, c.splits_down, next_norm, which_d(l), c.tp_size));
       }
     }
 

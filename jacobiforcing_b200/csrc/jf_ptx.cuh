@@ -271,13 +271,13 @@ __device__ __forceinline__ ulonglong2 ld_cg_poll_u64x2(const unsigned long long*
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
-// Against a tensor-parallel peer's memory (NVLink) strong loads are served one at a time (~2 us each, measured), so
-// the peers' words are fetched with WEAK loads - they pipeline - and a failed tag check is followed by
-// fence.acq_rel.sys (system scope: the writer is another device; it also drops this SM's L1 copies) before the next
-// attempt, the same pattern grid_barrier uses for the cross-GPU flags.
-__device__ __forceinline__ ulonglong2 ld_weak_poll_u64x2(const unsigned long long* p) {
+// Words a tensor-parallel PEER writes into THIS GPU's memory (push buffers, staging buffers): the probes target local
+// memory, so they are served by the local L2 like the gpu-scope ones; system scope because the writer is another device.
+// (Loads that target a peer's memory over NVLink are a different matter: strong ones are served one at a time, ~2 us
+// each, measured - the fused path never issues them.)
+__device__ __forceinline__ ulonglong2 ld_sys_poll_u64x2(const unsigned long long* p) {
   ulonglong2 v;
-  asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long ld_cg_poll_u64(const unsigned long long* p) {

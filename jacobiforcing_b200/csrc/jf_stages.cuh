@@ -140,11 +140,12 @@ __device__ __forceinline__ float row_total_canonical(const DevCtx& c, int t, int
   return halfwarp_tree(p);
 }
 
-// SPLITS == 0: embedding lookup instead of a reduce.  TP = tensor-parallel ranks whose partial sums are added (rank order,
-// then split order, identical on every rank): rank r's slices live in peer memory reached through c.peer_part_rs.
-template <int SPLITS, int TP>
+// SPLITS == 0: embedding lookup instead of a reduce.  `ranks` = tensor-parallel ranks whose partial sums are added (rank r's
+// slices live in peer memory reached through c.peer_part_rs).  Order of the sum, identical on every rank and in the fused
+// tail: each rank's k-splits in split order, then the ranks in rank order.
+template <int SPLITS>
 __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx& w, int T, const __nv_bfloat16* normw,
-                                               int which) {
+                                               int which, int ranks) {
   const int h = c.md.h;
   const int nvec = h >> 3;
   const int nt_h = (h + 127) >> 7;
@@ -164,26 +165,28 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
         tk = tk < 0 ? 0 : (tk >= c.md.vocab_embed ? c.md.vocab_embed - 1 : tk);
         unpack8(__ldg(reinterpret_cast<const uint4*>(c.embed + (size_t)tk * h) + v), x);
       } else {
-        // every slice of this 8-column group is in flight before the first add; the sum runs in (rank, split) order
+        // every k-split slice of this 8-column group is in flight before the first add
         const uint4 rr = ld_weak(reinterpret_cast<const uint4*>(hrow) + v);
         const size_t roff = (size_t)t * c.part_splits * h;
         const size_t sstride4 = (size_t)h >> 2;
-        float4 pa[(SPLITS > 0 ? SPLITS : 1) * TP], pb[(SPLITS > 0 ? SPLITS : 1) * TP];
-#pragma unroll
-        for (int r = 0; r < TP; ++r) {
-          const float* src = (TP == 1) ? c.part_rs[which] : c.peer_part_rs[r][which];
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < ranks; ++r) {
+          const float* src = (ranks == 1) ? c.part_rs[which] : c.peer_part_rs[r][which];
           const float4* p = reinterpret_cast<const float4*>(src + roff) + v * 2;
+          float4 pa[SPLITS > 0 ? SPLITS : 1], pb[SPLITS > 0 ? SPLITS : 1];
 #pragma unroll
           for (int s2 = 0; s2 < SPLITS; ++s2) {
-            pa[r * SPLITS + s2] = ld_weak(p + s2 * sstride4);
-            pb[r * SPLITS + s2] = ld_weak(p + s2 * sstride4 + 1);
+            pa[s2] = ld_weak(p + s2 * sstride4);
+            pb[s2] = ld_weak(p + s2 * sstride4 + 1);
           }
-        }
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float sr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int s2 = 0; s2 < SPLITS * TP; ++s2) {
-          acc[0] += pa[s2].x; acc[1] += pa[s2].y; acc[2] += pa[s2].z; acc[3] += pa[s2].w;
-          acc[4] += pb[s2].x; acc[5] += pb[s2].y; acc[6] += pb[s2].z; acc[7] += pb[s2].w;
+          for (int s2 = 0; s2 < SPLITS; ++s2) {
+            sr[0] += pa[s2].x; sr[1] += pa[s2].y; sr[2] += pa[s2].z; sr[3] += pa[s2].w;
+            sr[4] += pb[s2].x; sr[5] += pb[s2].y; sr[6] += pb[s2].z; sr[7] += pb[s2].w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += sr[j];
         }
         float r[8];
         unpack8(rr, r);
@@ -212,15 +215,51 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
   }
 }
 
+// Poll N tagged slices (`stride` words apart) of one 8-column group until every word carries `tag`, then add them to acc
+// in slice order.  All 4 * N 16-byte loads are in flight before the first check.  SYS: the words are written by another
+// GPU (into THIS GPU's memory), so the probes are system-scope relaxed loads.
+template <int N, bool SYS>
+__device__ __forceinline__ void poll_slices_add(const unsigned long long* p, size_t stride, unsigned int tag, float (&acc)[8]) {
+  ulonglong2 wd[N][4];
+  const long long t0 = clock64();
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int s2 = 0; s2 < N; ++s2)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        wd[s2][k] = SYS ? ld_sys_poll_u64x2(p + s2 * stride + 2 * k) : ld_cg_poll_u64x2(p + s2 * stride + 2 * k);
+#pragma unroll
+    for (int s2 = 0; s2 < N; ++s2)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, tag) && tagged_ok(wd[s2][k].y, tag);
+    if (ok) break;
+    if (clock64() - t0 > (SYS ? JF_XSPIN_LIMIT_CYCLES : JF_SPIN_LIMIT_CYCLES)) jf_trap_timeout();
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < N; ++s2)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { acc[2 * k] += tagged_val(wd[s2][k].x); acc[2 * k + 1] += tagged_val(wd[s2][k].y); }
+}
+__device__ __forceinline__ ulonglong2 tag2(unsigned long long tg, uint32_t a, uint32_t b) {
+  return make_ulonglong2(tg | (unsigned long long)a, tg | (unsigned long long)b);
+}
+
 // The same reduce + residual + RMSNorm executed as the TAIL of a row-split GEMM (O / down projection): once every
 // k-split of n-tile `n_tile` has stored its partial sums, the CTAs of those splits share the tile's rows - row step
 // `it` (8 rows: one per half-warp) belongs to split it % SPLITS - and each owns the tile's 128 columns of its rows
 // (8 columns per lane).  The arithmetic (split order, rounding points, the canonical row statistic) is that of
 // rows_norm_impl, bit for bit.
-// TP = tensor-parallel ranks: the row-split GEMM of every rank holds SPLITS partial sums of its K shard; every rank adds
-// all TP * SPLITS of them in (rank, split) order (its own from local memory, the peers' over NVLink), so all ranks end
-// with bit-identical rows and no cross-GPU barrier separates the projection from its consumers.
-template <int SPLITS, int TP>
+// PUSH (tensor parallelism over R ranks, this GEMM's K dimension is sharded): four phases, all of them driven by tagged
+// data, none by a cross-GPU flag, fence or atomic:
+//   0. every row: add this rank's k-splits (split order) and store the sum, tagged, into the push buffer of the row's
+//      owner (row t belongs to rank t mod R; slice = this rank)                                      [reduce-scatter]
+//   1. owned rows: poll the R slices (own memory), add them in rank order, add the residual, publish the tile statistic
+//   2. owned rows: row statistic -> normalise; the finished hidden / xn columns go to the own buffers and, tagged, into
+//      every peer's staging buffer                                                                   [all-gather]
+//   3. rows owned by peers: poll the staging buffer (own memory) and copy hidden / xn into place
+// so every rank ends with bit-identical rows and the stage closes with the ordinary LOCAL grid barrier.
+template <int SPLITS, bool PUSH>
 __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerShared* ws, int T, int n_tile, int split,
                                                  const __nv_bfloat16* normw, int which) {
   const WorkerCtx w = load_wctx(ws);
@@ -233,44 +272,49 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
   const int nit = (T + 7) >> 3;
   prof_mark(c, w, 500);
   if (split >= nit) return;
+  const int R = PUSH ? c.tp_size : 1, me = PUSH ? c.tp_rank : 0;
+  const int cnt = PUSH ? ((T > me) ? (T - me + R - 1) / R : 0) : T;     // rows this rank reduces and normalises
+  const int njt = (cnt + 7) >> 3;
   const size_t sstride = (size_t)h;                        // words between the k-split slices of a row
   const unsigned long long* tsrc = c.tpart_rs[which];
   const int trow = w.wwarp * 2 + hw;                       // this half-warp's row inside a step
+  const unsigned long long tg = (unsigned long long)w.tag << 32;
   uint4 wraw = make_uint4(0u, 0u, 0u, 0u);
   if (cvalid) wraw = __ldg(reinterpret_cast<const uint4*>(normw) + v);
+  if (PUSH) {
+    // phase 0: this rank's sum over its k-splits of every row -> the owner's push buffer
+    for (int it = split; it < nit; it += SPLITS) {
+      const int t = it * 8 + trow;
+      if (t < T && cvalid) {
+        float sr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        poll_slices_add<SPLITS, false>(tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8, sstride, w.tag, sr);
+        const int owner = t % R, j = t / R;
+        unsigned long long* dst = c.push_buf[owner] + ((size_t)j * R + me) * h + (size_t)v * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<ulonglong2*>(dst + 2 * k) = tag2(tg, __float_as_uint(sr[2 * k]), __float_as_uint(sr[2 * k + 1]));
+      }
+    }
+    prof_mark(c, w, 505);
+  }
   // phase 1, per row step: poll the tagged partial sums, add the residual, store the row, publish the tile statistic
-  for (int it = split; it < nit; it += SPLITS) {
-    const int t = it * 8 + trow;
-    const bool live = t < T && cvalid;
+  for (int it = split; it < njt; it += SPLITS) {
+    const int j = it * 8 + trow;
+    const int t = me + j * R;
+    const bool live = j < cnt && cvalid;
     uint4 rr = make_uint4(0u, 0u, 0u, 0u);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (live) {
       rr = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
-#pragma unroll
-      for (int rk = 0; rk < TP; ++rk) {                     // rank order, then split order: deterministic
-        const unsigned long long* p = ((TP == 1) ? tsrc : c.peer_tpart_rs[rk][which]) +
-                                      ((size_t)t * c.part_splits) * h + (size_t)v * 8;
-        ulonglong2 wd[SPLITS][4];
-        const long long t0 = clock64();
-        for (;;) {                                          // every split's 8 words in flight, then one check
-          bool ok = true;
-#pragma unroll
-          for (int s2 = 0; s2 < SPLITS; ++s2)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              wd[s2][k] = (TP == 1) ? ld_cg_poll_u64x2(p + s2 * sstride + 2 * k) : ld_weak_poll_u64x2(p + s2 * sstride + 2 * k);
-#pragma unroll
-          for (int s2 = 0; s2 < SPLITS; ++s2)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
-          if (ok) break;
-          if (TP > 1) fence_acq_rel_sys();              // system scope (the writer is a peer GPU); drops the stale L1 copies
-          if (clock64() - t0 > (TP > 1 ? JF_XSPIN_LIMIT_CYCLES : JF_SPIN_LIMIT_CYCLES)) jf_trap_timeout();
+      if (!PUSH) {
+        poll_slices_add<SPLITS, false>(tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8, sstride, w.tag, acc);
+      } else {                                              // rank order: deterministic, identical to rows_norm_impl
+        const unsigned long long* p = c.push_buf[me] + ((size_t)j * R) * h + (size_t)v * 8;
+        if (R == 2) poll_slices_add<2, true>(p, sstride, w.tag, acc);
+        else {
+          poll_slices_add<4, true>(p, sstride, w.tag, acc);
+          if (R == 8) poll_slices_add<4, true>(p + 4 * sstride, sstride, w.tag, acc);
         }
-#pragma unroll
-        for (int s2 = 0; s2 < SPLITS; ++s2)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { acc[2 * k] += tagged_val(wd[s2][k].x); acc[2 * k + 1] += tagged_val(wd[s2][k].y); }
       }
     }
     prof_mark(c, w, 501);
@@ -280,7 +324,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     for (int e = 0; e < 8; ++e) x[e] = bf16_round(r[e] + bf16_round(acc[e]));
     if (live) reinterpret_cast<uint4*>(c.hidden + (size_t)t * h)[v] = pack8(x);
     const float tile_ss = halfwarp_tree(sumsq8(x));
-    if (l16 == 0 && t < T) publish_tile_ss(c, t, n_tile, w.tag, tile_ss);
+    if (l16 == 0 && j < cnt) publish_tile_ss(c, t, n_tile, w.tag, tile_ss);
     prof_mark(c, w, 502);
   }
   // phase 2, four row steps at a time: the statistic words of all four rows are polled together (one round trip when
@@ -288,35 +332,36 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
   // itself is read back from `hidden` (this thread's own store) in the same round trip
   float wt[8];
   unpack8(wraw, wt);
-  for (int it0 = split; it0 < nit; it0 += 4 * SPLITS) {
+  for (int it0 = split; it0 < njt; it0 += 4 * SPLITS) {
     uint4 xr[4];
     unsigned long long sw[4][MW];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int t = (it0 + j * SPLITS) * 8 + trow;
-      xr[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (t < T && cvalid) xr[j] = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
+    for (int q = 0; q < 4; ++q) {
+      const int j = (it0 + q * SPLITS) * 8 + trow;
+      const int t = me + j * R;
+      xr[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (j < cnt && cvalid) xr[q] = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
     }
     const long long t0 = clock64();
     for (;;) {
       bool ok = true;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int t = (it0 + j * SPLITS) * 8 + trow;
-        if (t < T) {
-          const unsigned long long* slots = c.row_ss + (size_t)t * kMaxHTiles;
+      for (int q = 0; q < 4; ++q) {
+        const int j = (it0 + q * SPLITS) * 8 + trow;
+        if (j < cnt) {
+          const unsigned long long* slots = c.row_ss + (size_t)(me + j * R) * kMaxHTiles;
 #pragma unroll
           for (int m = 0; m < MW; ++m)
-            if (l16 + 16 * m < nt_h) sw[j][m] = ld_relaxed_gpu_u64(slots + l16 + 16 * m);
+            if (l16 + 16 * m < nt_h) sw[q][m] = ld_relaxed_gpu_u64(slots + l16 + 16 * m);
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int t = (it0 + j * SPLITS) * 8 + trow;
-        if (t < T) {
+      for (int q = 0; q < 4; ++q) {
+        const int j = (it0 + q * SPLITS) * 8 + trow;
+        if (j < cnt) {
 #pragma unroll
           for (int m = 0; m < MW; ++m)
-            if (l16 + 16 * m < nt_h) ok = ok && tagged_ok(sw[j][m], w.tag);
+            if (l16 + 16 * m < nt_h) ok = ok && tagged_ok(sw[q][m], w.tag);
         }
       }
       if (ok) break;
@@ -324,52 +369,83 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     }
     prof_mark(c, w, 503);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int it = it0 + j * SPLITS;
-      const int t = it * 8 + trow;
-      if (it < nit) {                                       // whole warps take part in the reduction of their rows
+    for (int q = 0; q < 4; ++q) {
+      const int it = it0 + q * SPLITS;
+      const int j = it * 8 + trow;
+      const int t = me + j * R;
+      if (it < njt) {                                       // whole warps take part in the reduction of their rows
         float pj = 0.f;
-        if (t < T) {
+        if (j < cnt) {
 #pragma unroll
           for (int m = 0; m < MW; ++m)
-            if (l16 + 16 * m < nt_h) pj += tagged_val(sw[j][m]);
+            if (l16 + 16 * m < nt_h) pj += tagged_val(sw[q][m]);
         }
         const float total = halfwarp_tree(pj);
-        if (t < T && cvalid) {
+        if (j < cnt && cvalid) {
           const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
           float x[8], o[8];
-          unpack8(xr[j], x);
+          unpack8(xr[q], x);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = wt[e] * bf16_round(x[e] * rstd);
           uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(v >> 3) * c.xrows_cap + t) * 128 +
                          (((v & 7) ^ (t & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = pack8(o);
+          const uint4 on = pack8(o);
+          *reinterpret_cast<uint4*>(dst) = on;
+          if (PUSH) {                                       // the finished row -> every peer's staging buffer
+            const size_t soff = ((size_t)t * (h >> 3) + v) * 8;
+            for (int r2 = 0; r2 < R; ++r2) {
+              if (r2 == me) continue;
+              unsigned long long* sd = c.stage_buf[r2] + soff;
+              *reinterpret_cast<ulonglong2*>(sd) = tag2(tg, xr[q].x, xr[q].y);
+              *reinterpret_cast<ulonglong2*>(sd + 2) = tag2(tg, xr[q].z, xr[q].w);
+              *reinterpret_cast<ulonglong2*>(sd + 4) = tag2(tg, on.x, on.y);
+              *reinterpret_cast<ulonglong2*>(sd + 6) = tag2(tg, on.z, on.w);
+            }
+          }
         }
       }
     }
   }
   prof_mark(c, w, 504);
+  if (PUSH) {
+    // phase 3: the rows the peers own arrive, finished, in this rank's staging buffer
+    for (int it = split; it < nit; it += SPLITS) {
+      const int t = it * 8 + trow;
+      if (t < T && cvalid && (t % R) != me) {
+        const unsigned long long* sp = c.stage_buf[me] + ((size_t)t * (h >> 3) + v) * 8;
+        ulonglong2 wd[4];
+        const long long t0 = clock64();
+        for (;;) {
+          bool ok = true;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) wd[k] = ld_sys_poll_u64x2(sp + 2 * k);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[k].x, w.tag) && tagged_ok(wd[k].y, w.tag);
+          if (ok) break;
+          if (clock64() - t0 > JF_XSPIN_LIMIT_CYCLES) jf_trap_timeout();
+        }
+        const uint4 hv = make_uint4((uint32_t)wd[0].x, (uint32_t)wd[0].y, (uint32_t)wd[1].x, (uint32_t)wd[1].y);
+        const uint4 xv = make_uint4((uint32_t)wd[2].x, (uint32_t)wd[2].y, (uint32_t)wd[3].x, (uint32_t)wd[3].y);
+        reinterpret_cast<uint4*>(c.hidden + (size_t)t * h)[v] = hv;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(c.xn) + ((size_t)(v >> 3) * c.xrows_cap + t) * 128 +
+                       (((v & 7) ^ (t & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = xv;
+      }
+    }
+    prof_mark(c, w, 506);
+  }
 }
 
+// push = this projection's K dimension is sharded over the tensor-parallel ranks
 __device__ __forceinline__ void gemm_norm_tail(const DevCtx& c, const WorkerShared* w, int T, int n_tile, int split,
-                                            int splits, const __nv_bfloat16* normw, int which) {
-#define JF_TAIL_CASE(S, TPN) case S: gemm_norm_tail_impl<S, TPN>(c, w, T, n_tile, split, normw, which); break;
-  if (c.tp_size == 1) {
-    switch (splits) {
-      JF_TAIL_CASE(1, 1) JF_TAIL_CASE(2, 1) JF_TAIL_CASE(3, 1) JF_TAIL_CASE(4, 1) JF_TAIL_CASE(5, 1) JF_TAIL_CASE(6, 1)
-      JF_TAIL_CASE(7, 1)
-      default: gemm_norm_tail_impl<8, 1>(c, w, T, n_tile, split, normw, which); break;
-    }
-  } else if (c.tp_size == 2) {                 // splits are capped at 4 (tp 2) / 2 (tp 4) when the engine is created
-    switch (splits) {
-      JF_TAIL_CASE(1, 2) JF_TAIL_CASE(2, 2) JF_TAIL_CASE(3, 2)
-      default: gemm_norm_tail_impl<4, 2>(c, w, T, n_tile, split, normw, which); break;
-    }
-  } else {
-    switch (splits) {
-      JF_TAIL_CASE(1, 4)
-      default: gemm_norm_tail_impl<2, 4>(c, w, T, n_tile, split, normw, which); break;
-    }
+                                            int splits, const __nv_bfloat16* normw, int which, bool push) {
+#define JF_TAIL_CASE(S) case S: if (push) gemm_norm_tail_impl<S, true>(c, w, T, n_tile, split, normw, which); \
+                                else gemm_norm_tail_impl<S, false>(c, w, T, n_tile, split, normw, which); break;
+  switch (splits) {
+    JF_TAIL_CASE(1) JF_TAIL_CASE(2) JF_TAIL_CASE(3) JF_TAIL_CASE(4) JF_TAIL_CASE(5) JF_TAIL_CASE(6) JF_TAIL_CASE(7)
+    default: if (push) gemm_norm_tail_impl<8, true>(c, w, T, n_tile, split, normw, which);
+             else gemm_norm_tail_impl<8, false>(c, w, T, n_tile, split, normw, which);
+             break;
   }
 #undef JF_TAIL_CASE
 }
@@ -433,32 +509,24 @@ __device__ __forceinline__ void gu_swiglu_tail(const DevCtx& c, const WorkerShar
   switch (splits) {
     case 2: gu_swiglu_tail_impl<2>(c, ws, T, n_tile, split); break;
     case 3: gu_swiglu_tail_impl<3>(c, ws, T, n_tile, split); break;
-    default: gu_swiglu_tail_impl<4>(c, ws, T, n_tile, split); break;
+    case 4: gu_swiglu_tail_impl<4>(c, ws, T, n_tile, split); break;
+    case 5: gu_swiglu_tail_impl<5>(c, ws, T, n_tile, split); break;
+    case 6: gu_swiglu_tail_impl<6>(c, ws, T, n_tile, split); break;
+    case 7: gu_swiglu_tail_impl<7>(c, ws, T, n_tile, split); break;
+    default: gu_swiglu_tail_impl<8>(c, ws, T, n_tile, split); break;
   }
 }
 
-// which: 0 = after the O projection, 1 = after the down projection (selects the row-split partial buffer)
+// which: the row-split partial buffer to reduce (0 / 1 / 2, see DevCtx::part_rs); ranks: tensor-parallel ranks that hold
+// partial sums of this projection (1 = local)
 __device__ __noinline__ void stage_rows_norm(const DevCtx& c, const WorkerShared* ws, int T, bool embed, int splits,
-                                             const __nv_bfloat16* normw, int which) {
+                                             const __nv_bfloat16* normw, int which, int ranks) {
   const WorkerCtx w = load_wctx(ws);
-  if (embed) { rows_norm_impl<0, 1>(c, w, T, normw, which); return; }
-#define JF_NORM_CASE(S, TPN) case S: rows_norm_impl<S, TPN>(c, w, T, normw, which); break;
-  if (c.tp_size == 1) {
-    switch (splits) {
-      JF_NORM_CASE(1, 1) JF_NORM_CASE(2, 1) JF_NORM_CASE(3, 1) JF_NORM_CASE(4, 1) JF_NORM_CASE(5, 1) JF_NORM_CASE(6, 1)
-      JF_NORM_CASE(7, 1)
-      default: rows_norm_impl<8, 1>(c, w, T, normw, which); break;
-    }
-  } else if (c.tp_size == 2) {
-    switch (splits) {
-      JF_NORM_CASE(1, 2) JF_NORM_CASE(2, 2) JF_NORM_CASE(3, 2)
-      default: rows_norm_impl<4, 2>(c, w, T, normw, which); break;
-    }
-  } else {                       // tp_size == 4 (creation rejects other sizes; splits are capped at 2 for tp 4)
-    switch (splits) {
-      JF_NORM_CASE(1, 4)
-      default: rows_norm_impl<2, 4>(c, w, T, normw, which); break;
-    }
+  if (embed) { rows_norm_impl<0>(c, w, T, normw, which, 1); return; }
+#define JF_NORM_CASE(S) case S: rows_norm_impl<S>(c, w, T, normw, which, ranks); break;
+  switch (splits) {
+    JF_NORM_CASE(1) JF_NORM_CASE(2) JF_NORM_CASE(3) JF_NORM_CASE(4) JF_NORM_CASE(5) JF_NORM_CASE(6) JF_NORM_CASE(7)
+    default: rows_norm_impl<8>(c, w, T, normw, which, ranks); break;
   }
 #undef JF_NORM_CASE
 }

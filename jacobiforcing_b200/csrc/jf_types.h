@@ -105,8 +105,9 @@ struct alignas(16) DevCtx {
   unsigned long long* tpart;         // [kFuseRopeRows][part_splits][part_n] tagged {stage tag, fp32} partial sums of the fused QKV stage
   unsigned long long* tpart_rs[2];   // [kFuseRows][part_splits][h] the same for the fused O / down stages
   unsigned long long* tgu;           // [T_cap][splits_gu][2][inter] tagged gate / up partial sums (split-K gate/up)
-  float* part_rs[2];                 // [T_cap][part_splits][h]: partials of the row-split GEMMs (0 = O, 1 = down); with
+  float* part_rs[3];                 // [T_cap][part_splits][h]: partials of the row-split GEMMs (0 = O, 1 = down); with
                                      // tensor parallelism the peers read them over NVLink, hence double-buffered
+                                     // (MLP-only tensor parallelism: down alternates 0 / 1 by layer, the local O uses 2)
   __nv_bfloat16* qbuf;               // [T_cap][q_dim] rotated queries
   float* attn_o;                     // [attn_slots_cap][n_q][d] unnormalised partial outputs
   float* attn_ml;                    // [attn_slots_cap][n_q][2] (running max, running sum)
@@ -142,11 +143,21 @@ struct alignas(16) DevCtx {
   int* trace;                        // optional forward trace: {iter, seq, ctx, B, L, tokens...}*
   int trace_cap;
   int* trace_len;
-  // ---- tensor parallelism: every rank runs the same kernel on its shard; row-split partial sums and argmax keys are
-  // read straight out of the peers' memory (CUDA IPC mappings), cross-GPU barriers are flags in peer memory
+  // ---- tensor parallelism: every rank runs the same kernel on its shard and talks to its peers through mapped peer
+  // memory (CUDA IPC over NVLink; plain pointers when several ranks share one device).  Fused (Jacobi-sized) forwards
+  // exchange nothing but TAGGED DATA - no cross-GPU flag, fence or atomic: a row-split projection reduce-scatters by
+  // push (rank r adds its own k-splits and stores the sum of row t into the push buffer of the row's OWNER, t mod
+  // ranks), the owner adds the ranks in rank order, applies residual + RMSNorm and pushes the finished row into every
+  // peer's staging buffer (all-gather by push), from where each rank copies it into its own hidden / xn before its
+  // LOCAL grid barrier.  Prefill-sized forwards: partial sums stay local, peers read them after a flag barrier.
   int tp_rank, tp_size;
-  const float* peer_part_rs[kMaxTP][2];
-  const unsigned long long* peer_tpart_rs[kMaxTP][2];   // the peers' tagged partial buffers (fused tails under tensor parallelism)
+  int tp_attn;                                // ranks the attention block (QKV / O) is sharded over: tp_size, or 1 when
+                                              // attention is replicated on every rank (MLP-only tensor parallelism)
+  int push_rows_cap;                          // owned rows a push buffer holds (>= ceil(kFuseRows / ranks))
+  unsigned long long* push_buf[kMaxTP];       // rank r's push buffer [push_rows_cap][tp_size][h] of tagged partial sums
+  unsigned long long* stage_buf[kMaxTP];      // rank r's staging buffer [kFuseRows][h / 8][8] of tagged finished rows:
+                                              // per 8-column group, words 0-3 = hidden, 4-7 = xn (two bf16 per word)
+  const float* peer_part_rs[kMaxTP][3];       // the peers' fp32 partial buffers (stand-alone reduce stage, prefill)
   const unsigned long long* peer_keys[kMaxTP];
   unsigned long long* peer_xflag[kMaxTP];     // rank r's flag array (this rank writes element [tp_rank])
   unsigned long long* xflag;                  // own flag array [kMaxTP]

@@ -74,7 +74,8 @@ class ModelRunner:
                                 num_kv_pages=config.num_kvcache_blocks, max_pages_per_seq=self.max_pages_per_seq,
                                 gen_capacity=config.max_model_len + 1024 + 64, max_calls=1024,
                                 trace_capacity=1 << 20, tp_rank=(self.rank if self.world_size > 1 else 0),
-                                tp_size=self.world_size, tp_group=tp_group)
+                                tp_size=self.world_size, tp_group=tp_group,
+                                tp_shard_attention=config.tp_shard_attention)
         self.rt.free_pages = []                            # pages are owned by the scheduler's BlockManager
         if config.state_dict is not None:
             self.rt.load_state_dict(config.state_dict)

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _cabi
 from .policy import MODES, POLICY_ERRORS, STOP_REASONS, PolicyKnobs, draw_prefill_draft, mt_state_words
-from .tp import check_divisibility, shard_tensor
+from .tp import LocalTPGroup, check_divisibility, shard_tensor
 
 PAGE = 256
 
@@ -54,7 +54,11 @@ class JacobiRuntime:
     def __init__(self, hf_config, *, device: int = 0, max_rows: int = 1024, max_seqs: int = 8,
                  num_kv_pages: int = 64, max_pages_per_seq: int = 8, attn_chunk: int = 64, attn_slots: int = 0,
                  gen_capacity: int = 4096, max_calls: int = 256, trace_capacity: int = 0,
-                 tp_rank: int = 0, tp_size: int = 1, tp_group=None):
+                 tp_rank: int = 0, tp_size: int = 1, tp_group=None, tp_shard_attention: bool = False,
+                 num_ctas: int = 0):
+        """tp_group: a torch.distributed group (one process per GPU) or a tp.LocalTPGroup (one thread per rank in this
+        process).  tp_shard_attention: False = MLP-only tensor parallelism (attention replicated, one exchange per
+        block, any tp in {2,4,8}); True = heads sharded too (reference layout; heads must divide)."""
         self.lib = _cabi.load()
         g = (lambda k, d=None: hf_config[k] if isinstance(hf_config, dict) else getattr(hf_config, k, d))
         heads = int(g("num_attention_heads"))
@@ -68,10 +72,12 @@ class JacobiRuntime:
             hidden, int(g("num_hidden_layers")), heads, int(g("num_key_value_heads")), int(head_dim),
             int(g("intermediate_size")), int(g("vocab_size")), int(bool(g("tie_word_embeddings", False))),
             int(g("max_position_embeddings")), float(g("rms_norm_eps", 1e-6)), float(theta))
-        check_divisibility(hf_config, tp_size)
+        self.tp_shard_attention = bool(tp_shard_attention) and tp_size > 1
+        check_divisibility(hf_config, tp_size, self.tp_shard_attention)
         self.tp_rank, self.tp_size = tp_rank, tp_size
         self.runtime_cfg = _cabi.RuntimeCfg(device, max_rows, max_seqs, num_kv_pages, max_pages_per_seq, attn_chunk,
-                                            attn_slots, gen_capacity, max_calls, trace_capacity, tp_rank, tp_size)
+                                            attn_slots, gen_capacity, max_calls, trace_capacity, tp_rank, tp_size,
+                                            tp_size if self.tp_shard_attention else 1, num_ctas)
         self.vocab = int(g("vocab_size"))
         self.vocab_local = self.vocab // tp_size
         self.hidden = hidden
@@ -95,13 +101,23 @@ class JacobiRuntime:
         inside the kernel, whose cross-GPU waits are bounded (a rank that is seconds late - GC, tokenizer, page faults -
         would otherwise trip its peers' watchdog)."""
         if self.tp_size > 1:
+            if isinstance(self._tp_group, LocalTPGroup):
+                self._tp_group.barrier()
+                return
             import torch.distributed as dist
             if dist.is_initialized():
                 dist.barrier(group=self._tp_group)
 
     def _connect_peers(self, group) -> None:
         """Exchange the CUDA IPC handles of the activation arenas (torch.distributed is only the transport) so the
-        kernel can read peers' partial sums / argmax keys and signal barriers over NVLink."""
+        kernel can write partial sums / finished rows into the peers' memory and read their argmax keys over NVLink."""
+        if isinstance(group, LocalTPGroup):
+            group.handles[self.tp_rank] = self.h.value
+            group.barrier()
+            arr = (C.c_void_p * self.tp_size)(*group.handles)
+            _cabi.check(self.lib.jf_tp_attach_local(self.h, arr), self.h)
+            group.barrier()
+            return
         import torch.distributed as dist
         mine = (C.c_ubyte * 64)()
         _cabi.check(self.lib.jf_tp_export(self.h, mine), self.h)
@@ -177,7 +193,7 @@ class JacobiRuntime:
         import torch
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t)
-        t = shard_tensor(name, t.detach(), self.tp_rank, self.tp_size).contiguous()
+        t = shard_tensor(name, t.detach(), self.tp_rank, self.tp_size, self.tp_shard_attention).contiguous()
         if t.is_cuda:
             # the library copies on its own stream: the producer kernels on torch's stream must have finished
             torch.cuda.current_stream(t.device).synchronize()

@@ -8,12 +8,17 @@ from typing import Tuple
 
 COLUMN_PARALLEL = ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "mlp.gate_proj", "mlp.up_proj")
 ROW_PARALLEL = ("self_attn.o_proj", "mlp.down_proj")
+SUPPORTED_TP = (1, 2, 4, 8)
 
 
-def shard_dim(name: str) -> Tuple[int, bool]:
-    """(dimension to narrow or -1, applies_to_bias)."""
+def shard_dim(name: str, shard_attention: bool = True) -> Tuple[int, bool]:
+    """(dimension to narrow or -1, applies_to_bias).  shard_attention=False: MLP-only tensor parallelism - the attention
+    block (q/k/v/o) is replicated on every rank, only gate/up/down and the LM head are sharded (SURVEY 8(e) option A:
+    one exchange per transformer block, no head-divisibility constraint)."""
     if name == "lm_head.weight":
         return 0, False
+    if not shard_attention and "self_attn." in name:
+        return -1, False
     for key in COLUMN_PARALLEL:
         if key in name:
             return 0, True                      # output features: rows of the weight, and the bias
@@ -23,11 +28,11 @@ def shard_dim(name: str) -> Tuple[int, bool]:
     return -1, False
 
 
-def shard_tensor(name: str, t, tp_rank: int, tp_size: int):
+def shard_tensor(name: str, t, tp_rank: int, tp_size: int, shard_attention: bool = True):
     """This rank's slice of an HF tensor (a view; the caller makes it contiguous)."""
     if tp_size == 1:
         return t
-    dim, _ = shard_dim(name)
+    dim, _ = shard_dim(name, shard_attention)
     if dim < 0 or (t.dim() == 1 and dim == 1):
         return t
     n = t.shape[dim]
@@ -37,11 +42,32 @@ def shard_tensor(name: str, t, tp_rank: int, tp_size: int):
     return t.narrow(dim, tp_rank * per, per)
 
 
-def check_divisibility(cfg, tp_size: int) -> None:
-    """The reference asserts head divisibility (inference_engine/models/qwen3.py:31,34)."""
+def check_divisibility(cfg, tp_size: int, shard_attention: bool = True) -> None:
+    """The reference asserts head divisibility (inference_engine/models/qwen3.py:31,34); with the attention block
+    replicated (shard_attention=False) only the MLP width and the vocabulary have to divide."""
     g = (lambda k: cfg[k] if isinstance(cfg, dict) else getattr(cfg, k))
-    for key in ("num_attention_heads", "num_key_value_heads", "intermediate_size", "vocab_size"):
+    keys = ("intermediate_size", "vocab_size")
+    if shard_attention:
+        keys = ("num_attention_heads", "num_key_value_heads") + keys
+    for key in keys:
         if int(g(key)) % tp_size:
             raise ValueError(f"{key}={g(key)} is not divisible by tensor_parallel_size={tp_size}")
-    if tp_size not in (1, 2, 4):
-        raise NotImplementedError("tensor_parallel_size must be 1, 2 or 4 on this build")
+    if tp_size not in SUPPORTED_TP:
+        raise NotImplementedError("tensor_parallel_size must be 1, 2, 4 or 8 on this build")
+    if tp_size > 1 and (int(g("intermediate_size")) // tp_size) % 64:
+        raise ValueError(f"intermediate_size / tensor_parallel_size = {int(g('intermediate_size')) // tp_size} must be a "
+                         "multiple of 64")
+
+
+class LocalTPGroup:
+    """Rendezvous of tensor-parallel ranks that live in ONE process, one host thread per rank (ranks on several devices
+    with peer access, or sharing one device whose SMs they split): what torch.distributed provides between processes."""
+
+    def __init__(self, size: int):
+        import threading
+        self.size = size
+        self.handles = [None] * size
+        self._barrier = threading.Barrier(size)
+
+    def barrier(self) -> None:
+        self._barrier.wait()

@@ -274,7 +274,7 @@ def test_error_mapping(pair):
         hf_generate(rt, [prompt], n=8, max_new_tokens=16, mode="multiblock", K=2, r=0.2, pad=None)
     rt.free_pages = list(range(rt.runtime_cfg.num_kv_pages - 1, -1, -1))
     with pytest.raises(RuntimeError):
-        rt.forward([1] * 300, [(0, 300, 0, 0)], [rt.new_sequence()], 0, 8)      # more rows than max_rows
+        rt.forward([1] * 1100, [(0, 1100, 0, 0)], [rt.new_sequence()], 0, 8)    # more rows than max_rows
 
 
 # ---------------------------------------------------------------------------------------------------------------

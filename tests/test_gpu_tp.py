@@ -1,5 +1,6 @@
-"""Tensor parallelism on real GPUs (needs >= 2 B200 with NVLink peer access; skipped otherwise): one process per GPU,
-the persistent kernel on every rank reading the peers' row-split partial sums and argmax keys over NVLink.
+"""Tensor parallelism on real GPUs (needs >= 2 B200 with NVLink peer access; skipped otherwise - the same kernels are
+covered on one GPU by tests/test_gpu_tp_virtual.py): one process per GPU, the persistent kernel on every rank pushing
+its row-split partial sums / finished rows into the peers' memory and reading their argmax keys over NVLink.
 Checks: both ranks return identical ids / iteration counts; the gathered logits match the single-GPU engine and the HF
 fp32 oracle within the bf16 tolerance; Jacobi == AR on the sharded engine; ids equal the single-GPU ids up to near-ties
 (the cross-rank sum changes the fp32 summation order)."""
@@ -22,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, shard_attn=False, skew=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -40,7 +41,7 @@ def _worker(rank, world, port, ret):
         cos, sin = rope_tables(float(cfg.rope_theta), cfg.hidden_size // cfg.num_attention_heads,
                                cfg.max_position_embeddings)
         kw = dict(device=rank, max_rows=256, max_seqs=4, num_kv_pages=16, max_pages_per_seq=4)
-        rt = JacobiRuntime(cfg, tp_rank=rank, tp_size=world, **kw)
+        rt = JacobiRuntime(cfg, tp_rank=rank, tp_size=world, tp_shard_attention=shard_attn, **kw)
         rt.load_state_dict(sd)
         rt.set_rope_tables(cos.numpy(), sin.numpy())
         g = torch.Generator().manual_seed(1)
@@ -61,9 +62,14 @@ def _worker(rank, world, port, ret):
         rt.release(seq)
         prompt = torch.randint(0, cfg.vocab_size, (24,), generator=g).tolist()
         runs = {}
-        for mode, n in (("single", 1), ("single", 8), ("multiblock", 8)):
+        for rep, (mode, n) in enumerate((("single", 1), ("single", 8), ("multiblock", 8)) * (4 if skew else 1)):
+            if skew and rank == rep % world:
+                import time
+                time.sleep(0.05 * (1 + rep % 3))       # host skew between the ranks' launches
             seqs, results, run = hf_generate(rt, [prompt], n=n, max_new_tokens=40, mode=mode, pad=0,
                                              rngs=[random.Random(2)])
+            if (mode, n) in runs:
+                assert runs[(mode, n)] == (results[0].tokens[:40], results[0].iters, run["forwards"]), "not reproducible"
             runs[(mode, n)] = (results[0].tokens[:40], results[0].iters, run["forwards"])
             for s in seqs:
                 rt.release(s)
@@ -94,21 +100,22 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_tp2_matches_single_gpu_and_oracle():
+@pytest.mark.parametrize("world,shard_attn,skew", [(2, False, True), (2, True, False), (4, False, False), (8, False, False)])
+def test_tp_matches_single_gpu_and_oracle(world, shard_attn, skew):
     import torch.multiprocessing as mp
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     port = _free_port()
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret, shard_attn, skew)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(600)
         assert p.exitcode == 0, "a tensor-parallel rank failed"
-    r0, r1 = ret[0], ret[1]
-    print("TP2 rank0:", {k: v for k, v in r0.items() if k not in ("tokens", "tokens_tp1")})
+    r0, r1 = ret[0], ret[world - 1]
+    print(f"TP{world} rank0:", {k: v for k, v in r0.items() if k not in ("tokens", "tokens_tp1")})
     assert r0["max_err"] <= 2.5e-2 and r0["mean_err"] <= 4e-3
     assert r0["greedy_same_on_ranks"] and r0["fused_argmax_ok"]
     assert r0["runs_same_on_ranks"] and r1["runs_same_on_ranks"]
