@@ -21,7 +21,9 @@ class LLMEngine:
         self._exited = False
         self.model_runner = ModelRunner(config, 0, [])
         self.tokenizer = None
-        tok_path = tokenizer_path or model
+        from ..config import _resolve_checkpoint_dir
+        # a training output directory is resolved to its latest checkpoint-N, like config.model
+        tok_path = _resolve_checkpoint_dir(tokenizer_path) if tokenizer_path else config.model
         if tok_path is not None:
             try:
                 from transformers import AutoTokenizer

@@ -124,7 +124,7 @@ class ModelRunner:
             prompt = list(seq.token_ids)
             draft = [self._rng.choice(prompt) for _ in range(L)]          # :797 random prompt tokens
             self._reserve(seq, len(prompt) + L)
-            h = self._handle(seq, 0)
+            h = self._handle(seq, seq.num_cached_tokens)                  # > 0: leading pages came from the prefix cache
             first, drafted, _ = self.rt.prefill(h, prompt, draft)         # argmax(logits[P-1 : P+L-1]) (:906-918)
             seq._prefill_draft = list(drafted)
             seq._first_correct = first
@@ -236,7 +236,7 @@ class ModelRunner:
             for seq in seqs:
                 prompt = list(seq.token_ids)
                 self._reserve(seq, len(prompt) + 1)
-                first, _, _ = self.rt.prefill(self._handle(seq, 0), prompt, [])
+                first, _, _ = self.rt.prefill(self._handle(seq, seq.num_cached_tokens), prompt, [])
                 seq.num_cached_tokens = len(prompt)
                 tokens.append(int(first))
             return tokens

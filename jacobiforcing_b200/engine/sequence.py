@@ -77,6 +77,15 @@ class Sequence:
     def num_blocks(self) -> int:
         return -(-self.num_tokens // self.block_size)
 
+    @property
+    def num_cached_blocks(self) -> int:
+        return self.num_cached_tokens // self.block_size
+
+    def block(self, i: int) -> List[int]:
+        """Token ids of page i (the last one may be partial)."""
+        assert 0 <= i < self.num_blocks
+        return self.token_ids[i * self.block_size:(i + 1) * self.block_size]
+
     # ---- growth ------------------------------------------------------------------------------------------------
     def append_token(self, token_id) -> None:
         if isinstance(token_id, (list, tuple)):

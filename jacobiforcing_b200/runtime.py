@@ -282,20 +282,21 @@ class JacobiRuntime:
     def prefill(self, seq: SeqHandle, prompt: Sequence[int], draft: Sequence[int]):
         """Forward prompt ++ draft, commit the prompt's KV, return (first_correct_token, prefill_drafted_n_gram) =
         argmax(logits[-n-1:-1]).  Long prompts are processed in chunks of max_rows rows; logits are computed for the
-        last n+1 rows only."""
+        last n+1 rows only.  seq.ctx > 0: the first seq.ctx prompt tokens are already in the sequence's pages (prefix
+        cache hit, engine/block_manager.py) and are skipped - all but the last prompt token, whose logits are needed."""
         prompt = [int(t) for t in prompt]
         draft = [int(t) for t in draft]
         P, n = len(prompt), len(draft)
-        if seq.ctx != 0:
-            raise ValueError("prefill needs a fresh sequence")
         if P < 1:
             raise ValueError("empty prompt")
+        if seq.ctx < 0 or seq.ctx > P:
+            raise ValueError("cached prefix longer than the prompt")
         row = prompt + draft
         total = len(row)
         self.ensure_capacity(seq, total)
         want_from = P - 1                      # first row whose argmax is needed
         out: List[int] = []
-        start = 0
+        start = min(seq.ctx, P - 1)
         ms = 0.0
         while start < total:
             end = min(total, start + self.max_rows)
@@ -311,6 +312,7 @@ class JacobiRuntime:
                 lm_rows = T - lm_row0
             res = self.forward(toks, [(0, T, 0, start)], [seq], lm_row0, lm_rows, commits)
             ms += res["ms"]
+            self.stats["prefill_rows"] = self.stats.get("prefill_rows", 0) + T
             if end > want_from:
                 out.extend(int(t) for t in res["greedy"][lm0:T])
             start = end

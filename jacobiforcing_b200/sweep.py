@@ -172,7 +172,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     model_dir = _resolve_checkpoint_dir(args.model_name)
     hf = AutoConfig.from_pretrained(model_dir)
     tokenizer = None
-    tok_dir = args.tokenizer_name or model_dir
+    tok_dir = _resolve_checkpoint_dir(args.tokenizer_name) if args.tokenizer_name else model_dir
     try:
         from transformers import AutoTokenizer
         tokenizer = AutoTokenizer.from_pretrained(tok_dir, use_fast=True)

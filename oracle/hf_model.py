@@ -150,6 +150,20 @@ def teacher_forced_logits(model, ids: Sequence[int]) -> torch.Tensor:
     return model(input_ids=t, use_cache=False).logits[0].float()
 
 
+def bf16_copy(model):
+    """A bf16 copy of an fp32 oracle model, the dtype the reference runs in.  A COPY on purpose: `model.to(bfloat16)`
+    converts in place and also rounds the rotary embedding's `inv_freq` buffer, which a later `.to(float32)` does not
+    restore - the "fp32 oracle" would silently keep bf16-rounded rotary frequencies (error grows with the position).
+    The copy keeps the fp32 inv_freq, as a model loaded with torch_dtype=bfloat16 does."""
+    import copy
+    m = copy.deepcopy(model).to(torch.bfloat16)
+    src = dict(model.named_buffers())
+    for name, buf in m.named_buffers():
+        if name.endswith("inv_freq") and name in src:
+            buf.data = src[name].detach().clone().float()
+    return m.eval()
+
+
 @torch.no_grad()
 def greedy_ar(model, prompt: Sequence[int], n_new: int) -> List[int]:
     """HF greedy decoding, the property the reference's own tests pin Jacobi against

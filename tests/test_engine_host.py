@@ -178,3 +178,80 @@ def test_can_append_predicates():
     s.extend_tokens([1])
     assert not bm.can_append(s)                                # len % 256 == 1 and nothing free
     assert bm.can_append(s, need_tokens=256) and not bm.can_append(s, need_tokens=258)
+
+
+# ---- prefix cache (reference: inference_engine/engine/block_manager.py:71-97 hash chain, :135-168 allocate) ------------
+def _seq(tokens, **kw):
+    from jacobiforcing_b200.engine.sequence import Sequence
+    from jacobiforcing_b200.sampling_params import SamplingParams
+    return Sequence(list(tokens), SamplingParams(temperature=0.0, **kw))
+
+
+def test_prefix_cache_shares_full_pages_and_verifies_tokens():
+    from jacobiforcing_b200.engine.block_manager import BlockManager
+    bm = BlockManager(16, 256)
+    base = list(range(600))                       # 2 full pages + 88 tokens
+    a = _seq(base)
+    bm.allocate(a)
+    assert a.num_cached_tokens == 0 and len(a.block_table) == 3
+    b = _seq(base[:512] + [7] * 50)               # same first two pages, different tail
+    bm.allocate(b)
+    assert b.num_cached_tokens == 512 and b.block_table[:2] == a.block_table[:2] and b.block_table[2] != a.block_table[2]
+    assert bm.blocks[a.block_table[0]].ref_count == 2
+    c = _seq(base[:256] + [9] * 300)              # only the first page matches; the chain stops at the first miss
+    bm.allocate(c)
+    assert c.num_cached_tokens == 256 and c.block_table[0] == a.block_table[0] and c.block_table[1] != a.block_table[1]
+    d = _seq([5] + base[1:600])                   # differs in the first token: nothing shared
+    bm.allocate(d)
+    assert d.num_cached_tokens == 0 and not set(d.block_table) & set(a.block_table)
+    # a shared page is freed only with its last user, and keeps its identity while it sits on the free list
+    shared = a.block_table[0]
+    for s in (a, b, c):
+        s.num_cached_tokens = len(s)
+    bm.deallocate(a); bm.deallocate(b)
+    assert shared in bm.used_block_ids
+    bm.deallocate(c)
+    assert shared not in bm.used_block_ids
+    e = _seq(base)
+    bm.allocate(e)
+    assert e.num_cached_tokens == 512 and e.block_table[0] == shared      # revived from the free list
+    assert bm.stats["prefix_hit_tokens"] == 512 + 256 + 512
+
+
+def test_prefix_cache_forgets_a_page_that_is_handed_out_again():
+    from jacobiforcing_b200.engine.block_manager import BlockManager
+    bm = BlockManager(3, 256)
+    a = _seq(list(range(300)))
+    bm.allocate(a)
+    a.num_cached_tokens = 300
+    bm.deallocate(a)
+    b = _seq([1] * 700)                           # needs all three pages: the cached one is recycled
+    bm.allocate(b)
+    b.num_cached_tokens = 0
+    bm.deallocate(b)
+    c = _seq(list(range(300)))
+    bm.allocate(c)
+    assert c.num_cached_tokens == 0               # the hash entry died with the page's reuse
+
+
+def test_generated_pages_become_shareable_when_the_sequence_is_released():
+    from jacobiforcing_b200.engine.block_manager import BlockManager
+    bm = BlockManager(8, 256)
+    a = _seq(list(range(100)))
+    bm.allocate(a)
+    a.extend_tokens(list(range(1000, 1000 + 500)))        # decode grew it to 600 tokens, all committed but the last
+    bm.ensure(a, 600)
+    a.num_cached_tokens = 600
+    toks = list(a.token_ids)
+    bm.deallocate(a)
+    b = _seq(toks[:520])
+    bm.allocate(b)
+    assert b.num_cached_tokens == 512
+
+
+def test_disabled_prefix_cache_never_shares():
+    from jacobiforcing_b200.engine.block_manager import BlockManager
+    bm = BlockManager(8, 256, enable_prefix_cache=False)
+    a, b = _seq(list(range(600))), _seq(list(range(600)))
+    bm.allocate(a); bm.allocate(b)
+    assert b.num_cached_tokens == 0 and not set(a.block_table) & set(b.block_table)

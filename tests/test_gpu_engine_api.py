@@ -164,3 +164,35 @@ def test_streaming_and_profile_drivers():
     assert rows[0]["token_ids"][:40] == res[0].tokens[:40]
     assert rows[0]["calls"] == res[0].calls and rows[0]["total_iterations"] == res[0].total_iterations
     rt.close()
+
+
+def test_prefix_cache_reuse_skips_cached_pages_and_keeps_ids(llm):
+    """Prefill prefix cache (reference: engine/block_manager.py:135-168): a request whose leading full pages were
+    committed by an earlier request shares them, its prefill forwards only the remainder, and its output is identical
+    (greedy, Jacobi and autoregressive)."""
+    from jacobiforcing_b200 import SamplingParams
+    g = torch.Generator().manual_seed(11)
+    shared = torch.randint(0, 1000, (600,), generator=g).tolist()            # two full 256-token pages + 88
+    p1, p2 = shared + [3, 1, 4], shared[:560] + [2, 7, 1, 8]
+    bm = llm.scheduler.block_manager
+    for strategy in ("jacobi", "autoregressive"):
+        sp = SamplingParams(temperature=0.0, max_tokens=24, decode_strategy=strategy, jacobi_block_len=8, ignore_eos=True)
+        reset(llm)
+        bm.hash_to_block_id.clear()                                          # cold cache
+        for b in bm.blocks:
+            b.hash, b.token_ids = -1, []
+        rows0 = llm.model_runner.rt.stats.get("prefill_rows", 0)
+        cold = llm.generate([p2], sp, use_tqdm=False)[0]["token_ids"]
+        rows_cold = llm.model_runner.rt.stats["prefill_rows"] - rows0
+        reset(llm)
+        bm.hash_to_block_id.clear()
+        for b in bm.blocks:
+            b.hash, b.token_ids = -1, []
+        llm.generate([p1], sp, use_tqdm=False)                               # commits the shared pages
+        hits0 = bm.stats["prefix_hit_tokens"]
+        rows0 = llm.model_runner.rt.stats["prefill_rows"]
+        warm = llm.generate([p2], sp, use_tqdm=False)[0]["token_ids"]
+        rows_warm = llm.model_runner.rt.stats["prefill_rows"] - rows0
+        assert bm.stats["prefix_hit_tokens"] - hits0 == 512
+        assert rows_warm == rows_cold - 512, (rows_warm, rows_cold)
+        assert warm == cold, f"{strategy}: prefix-cache hit changed the output"

@@ -40,7 +40,7 @@ def _ids(model, n, seed=1):
 
 @pytest.mark.parametrize("rows", [32, 72, 256])
 def test_7b_width_logits_vs_hf_fp32(pair7b, rows):
-    from oracle.hf_model import teacher_forced_logits
+    from oracle.hf_model import bf16_copy, teacher_forced_logits
     model, rt = pair7b
     ids = _ids(model, rows)
     seq = rt.new_sequence()
@@ -48,9 +48,9 @@ def test_7b_width_logits_vs_hf_fp32(pair7b, rows):
     res = rt.forward(ids, [(0, rows, 0, 0)], [seq], 0, rows, want_logits=True)
     rt.release(seq)
     ref = teacher_forced_logits(model, ids).numpy()
-    m16 = model.to(torch.bfloat16)
+    m16 = bf16_copy(model)                          # a copy: .to() in place would round the rotary inv_freq buffer
     ref16 = teacher_forced_logits(m16, ids).numpy()
-    model.to(torch.float32)                         # weights are bf16-rounded already: the round trip is exact
+    del m16
     err = np.abs(res["logits"] - ref)
     err16 = np.abs(ref16 - ref)
     print(f"[7b-width rows={rows}] device vs fp32: max {err.max():.4g} mean {err.mean():.4g}; "
@@ -59,9 +59,12 @@ def test_7b_width_logits_vs_hf_fp32(pair7b, rows):
     assert err.max() <= max(LOGIT_MAX_TOL, 1.5 * err16.max())
     dev16 = torch.from_numpy(res["logits"]).to(torch.bfloat16).float()
     assert (res["greedy"] == dev16.argmax(-1).numpy()).all()
-    # the device argmax equals the fp32 oracle's wherever the oracle's top-2 margin is not a near-tie
+    # the device argmax equals the fp32 oracle's wherever the oracle's top-2 margin is decided: wider than a near-tie AND
+    # wider than what the reference's own dtype can flip at that row (twice the HF bf16 forward's largest error there -
+    # at |logit| ~ 7 one bf16 ulp is 0.03, so a fixed 3e-2 margin is not a decided position at these widths)
     top2 = torch.from_numpy(ref).topk(2, dim=-1).values
-    decided = (top2[:, 0] - top2[:, 1]).numpy() >= NEAR_TIE
+    decided = (top2[:, 0] - top2[:, 1]).numpy() >= np.maximum(NEAR_TIE, 2.0 * err16.max(axis=1))
+    assert decided.sum() >= rows // 2
     assert (res["greedy"][decided] == ref.argmax(-1)[decided]).all()
 
 

@@ -25,14 +25,11 @@ pytestmark = pytest.mark.gpu
 LOGIT_MAX_TOL, LOGIT_MEAN_TOL, NEAR_TIE = 2.5e-2, 4e-3, 3e-2
 
 
-def _rank_main(rank, tp, group, model_name, shard_attn, num_ctas, out, errors):
+def _rank_main(rank, tp, group, cfg, sd, shard_attn, num_ctas, out, errors):
     try:
         from jacobiforcing_b200.runtime import JacobiRuntime, hf_generate
-        from oracle.hf_model import build_model, rope_tables, state_dict_bf16
+        from oracle.hf_model import rope_tables
         from tests.test_gpu_parity import _oracle_on_device
-        model = build_model(model_name, seed=0, dtype=torch.float32)
-        sd = state_dict_bf16(model)
-        cfg = model.config
         cos, sin = rope_tables(float(cfg.rope_theta), cfg.hidden_size // cfg.num_attention_heads,
                                cfg.max_position_embeddings)
         rt = JacobiRuntime(cfg, device=0, max_rows=512, max_seqs=4, num_kv_pages=16, max_pages_per_seq=4,
@@ -87,7 +84,11 @@ def test_virtual_ranks_match_oracle_and_single_engine(model_name, tp, shard_attn
     num_ctas = (sms - 4) // tp                      # co-resident persistent kernels: leave a few SMs free
     group = LocalTPGroup(tp)
     out, errors = {}, []
-    threads = [threading.Thread(target=_rank_main, args=(r, tp, group, model_name, shard_attn, num_ctas, out, errors))
+    model, rt1 = make_pair(model_name)              # the oracle model (bf16-rounded weights) and the single engine
+    from oracle.hf_model import state_dict_bf16
+    sd = state_dict_bf16(model)                     # built here: transformers' lazy imports are not thread-safe
+    import tests.test_gpu_parity  # noqa: F401
+    threads = [threading.Thread(target=_rank_main, args=(r, tp, group, model.config, sd, shard_attn, num_ctas, out, errors))
                for r in range(tp)]
     for t in threads:
         t.start()
@@ -95,7 +96,8 @@ def test_virtual_ranks_match_oracle_and_single_engine(model_name, tp, shard_attn
         t.join(900)
     assert not errors, errors
     assert len(out) == tp
-    model, rt1 = make_pair(model_name)              # the oracle model (bf16-rounded weights) and the single engine
+    from oracle.hf_model import bf16_copy
+    m16 = bf16_copy(model)
     r0 = out[0]
     for rows, (ids, lm0, _, greedy0, hidden0) in r0["fwd"].items():
         logits = np.concatenate([out[r]["fwd"][rows][2] for r in range(tp)], axis=1)
@@ -104,8 +106,11 @@ def test_virtual_ranks_match_oracle_and_single_engine(model_name, tp, shard_attn
             assert (out[r]["fwd"][rows][4] == hidden0).all(), "ranks hold different hidden states"
         ref = teacher_forced_logits(model, ids).numpy()[lm0:]
         err = np.abs(logits - ref)
-        print(f"[tp{tp} {model_name} attn_sharded={shard_attn} rows={rows}] max {err.max():.4g} mean {err.mean():.4g}")
-        assert err.max() <= LOGIT_MAX_TOL and err.mean() <= LOGIT_MEAN_TOL
+        err16 = np.abs(teacher_forced_logits(m16, ids).numpy()[lm0:] - ref)   # what the reference's own dtype achieves
+        print(f"[tp{tp} {model_name} attn_sharded={shard_attn} rows={rows}] max {err.max():.4g} mean {err.mean():.4g} "
+              f"(HF bf16: max {err16.max():.4g} mean {err16.mean():.4g})")
+        assert err.max() <= max(LOGIT_MAX_TOL, 1.5 * err16.max())
+        assert err.mean() <= max(LOGIT_MEAN_TOL, 1.5 * err16.mean() + 1e-4)
         dev16 = torch.from_numpy(logits).to(torch.bfloat16).float()
         assert greedy0 == dev16.argmax(-1).tolist()
     for r in range(1, tp):
