@@ -60,10 +60,17 @@ typedef struct {
 /* Greedy Jacobi policy knobs (field order = struct jf::PolicyKnobs, csrc/jf_policy.h).  mode: 0 = HF single block
  * (modeling/cllm2_qwen2_modeling_kv_terminate_on_eos_improved.py:140-276), 1 = HF multiblock + rejection recycling
  * (modeling/..._multiblock_lookahead_unified.py:230-740), 2 = engine fixed-length policy
- * (inference_engine/engine/jacobi_decoding.py:303-445). */
+ * (inference_engine/engine/jacobi_decoding.py:303-445), 3 = engine non-greedy policy
+ * (inference_engine/engine/jacobi_decoding_nongreedy.py:300-470). */
 typedef struct {
   int32_t mode, n, K, spawn_threshold, pool_size, eos, pad, max_iteration_count, max_new_tokens, max_calls;
   int32_t lookahead_min_acc, vocab;
+  /* mode 3 only (non-greedy Jacobi, rejection-sampling verify: engine/jacobi_decoding_nongreedy.py:300-355): float bits of
+   * the temperature (> 0), the 64-bit key of the counter-based generator behind every random draw, and an offset added
+   * to the forward index in its counters (consecutive runs may share a key). */
+  int32_t temp_bits;
+  uint32_t seed_lo, seed_hi;
+  int32_t rng_offset;
 } jf_policy_knobs;
 
 /* replaces ModelRunner.__init__ (engine/model_runner.py:155-291): device, buffers, KV cache */

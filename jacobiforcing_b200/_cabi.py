@@ -34,7 +34,8 @@ class RuntimeCfg(C.Structure):
 class PolicyKnobsC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "mode", "n", "K", "spawn_threshold", "pool_size", "eos", "pad", "max_iteration_count", "max_new_tokens",
-        "max_calls", "lookahead_min_acc", "vocab")]
+        "max_calls", "lookahead_min_acc", "vocab", "temp_bits")] + [("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32),
+                                                                     ("rng_offset", C.c_int32)]
 
 
 _lib = None

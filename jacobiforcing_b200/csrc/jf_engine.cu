@@ -15,7 +15,7 @@
 using namespace jf;
 
 static_assert(sizeof(jf_policy_knobs) == sizeof(PolicyKnobs), "jf_policy_knobs must mirror jf::PolicyKnobs");
-static_assert(sizeof(DevCtx) % 16 == 0 && sizeof(DevCtx) <= 4864, "DevCtx is staged in shared memory");
+static_assert(sizeof(DevCtx) % 16 == 0 && sizeof(DevCtx) <= 4992, "DevCtx is staged in shared memory");
 
 static thread_local std::string g_create_error;
 
@@ -306,6 +306,11 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     const char* e5 = getenv("JF_FUSE_NORM");
     c.fuse_norm = e5 ? atoi(e5) : 1;
   }
+  ALLOC(c.ng_prop, c.T_cap, h->bytes_act);
+  ALLOC(c.ng_gumbel, c.T_cap, h->bytes_act);
+  ALLOC(c.ng_px, c.T_cap, h->bytes_act);
+  ALLOC(c.ng_bonus, c.T_cap, h->bytes_act);
+  ALLOC(c.ng_ms, (size_t)h->num_ctas * c.T_cap, h->bytes_act);
   ALLOC(c.seq_state, c.S_cap, h->bytes_act);
   ALLOC(c.seq_slot, c.S_cap, h->bytes_act);
   ALLOC(c.knobs, c.S_cap, h->bytes_act);
@@ -871,11 +876,17 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
   PolicyKnobs kn;
   memcpy(&kn, knobs, sizeof(kn));
   if (kn.n < 1 || kn.n > kNMax) { h->err = "block length n outside [1, 128]"; return JF_ERR_INVALID; }
-  if (kn.mode == MODE_ENGINE && kn.n < 2) { h->err = "Jacobi draft length L must be >= 2"; return JF_ERR_INVALID; }
+  if ((kn.mode == MODE_ENGINE || kn.mode == MODE_ENGINE_NG) && kn.n < 2) { h->err = "Jacobi draft length L must be >= 2"; return JF_ERR_INVALID; }
+  float ng_temp = 0.f;
+  if (kn.mode == MODE_ENGINE_NG) {
+    memcpy(&ng_temp, &kn.temp_bits, 4);
+    if (!(ng_temp > 0.f) || !std::isfinite(ng_temp)) { h->err = "non-greedy Jacobi needs a finite temperature > 0"; return JF_ERR_INVALID; }
+    if (c.tp_size > 1) { h->err = "non-greedy Jacobi is not available under tensor parallelism on this build"; return JF_ERR_UNSUPPORTED; }
+  }
   if (kn.mode == MODE_HF_MULTI && (kn.K < 1 || kn.K > 2)) { h->err = "device multiblock policy supports K in {1, 2}"; return JF_ERR_UNSUPPORTED; }
   if (kn.pool_size < 0 || kn.pool_size > kPoolMax) { h->err = "n_gram_pool_size outside [0, 16]"; return JF_ERR_INVALID; }
-  if (kn.mode < 0 || kn.mode > 2) { h->err = "unknown policy mode"; return JF_ERR_INVALID; }
-  if (kn.mode != MODE_ENGINE && !first_call_tokens) { h->err = "first_call_tokens required"; return JF_ERR_INVALID; }
+  if (kn.mode < 0 || kn.mode > 3) { h->err = "unknown policy mode"; return JF_ERR_INVALID; }
+  if ((kn.mode == MODE_HF_SINGLE || kn.mode == MODE_HF_MULTI) && !first_call_tokens) { h->err = "first_call_tokens required"; return JF_ERR_INVALID; }
   if (kn.max_calls > c.iters_cap) kn.max_calls = c.iters_cap;
   kn.vocab = h->md.vocab;
   const int n = kn.n;
@@ -944,9 +955,21 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
   TRYC(cudaMemsetAsync(c.iters_log, 0, (size_t)c.S_cap * c.iters_cap * 4, h->stream));
   TRYC(cudaMemsetAsync(c.hdr, 0, sizeof(PlanHdr), h->stream));
   TRYC(cudaMemsetAsync(c.trace_len, 0, 16, h->stream));
-  if (c.n_seqs != n_seqs) {
-    c.n_seqs = n_seqs;
-    TRYC(cudaMemcpyAsync(h->dctx, &h->hctx, sizeof(DevCtx), cudaMemcpyHostToDevice, h->stream));
+  {
+    const int ng = kn.mode == MODE_ENGINE_NG ? 1 : 0;
+    const float inv_t = ng ? 1.0f / ng_temp : 1.0f;
+    if (c.n_seqs != n_seqs || c.ng_mode != ng || (ng && (c.ng_inv_temp != inv_t || c.ng_seed_lo != kn.seed_lo ||
+                                                         c.ng_seed_hi != kn.seed_hi || c.ng_rng_offset != kn.rng_offset))) {
+      c.n_seqs = n_seqs;
+      c.ng_mode = ng; c.ng_inv_temp = inv_t; c.ng_seed_lo = kn.seed_lo; c.ng_seed_hi = kn.seed_hi; c.ng_rng_offset = kn.rng_offset;
+      TRYC(cudaMemcpyAsync(h->dctx, &h->hctx, sizeof(DevCtx), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (ng) {           // accumulators of the sampling epilogue start clean (the policy stage re-arms them after every forward)
+      std::vector<float> ninf(c.T_cap, -INFINITY);
+      TRYC(cudaMemcpyAsync(c.ng_prop, ninf.data(), (size_t)c.T_cap * 4, cudaMemcpyHostToDevice, h->stream));
+      TRYC(cudaMemsetAsync(c.ng_gumbel, 0, (size_t)c.T_cap * 8, h->stream));
+      TRYC(cudaStreamSynchronize(h->stream));
+    }
   }
   TRYC(cudaStreamSynchronize(h->stream));
   float ms = 0.f;

@@ -20,6 +20,7 @@
 #pragma once
 #include "jf_ptx.cuh"
 #include "jf_sched.h"
+#include "jf_policy.h"
 
 namespace jf {
 
@@ -42,7 +43,11 @@ enum GemmEpilogue : int {
   EPI_SWIGLU_TAGGED = 4, // split-K gate/up: both accumulators as tagged fp32 partial sums; the fused tail adds the splits
                          // and applies SwiGLU (used when the gate/up tiles alone would leave SMs idle: tensor parallelism)
   EPI_ARGMAX      = 2,   // LM head: bf16-rounded logits, running (max, lowest index) per row -> atomicMax of packed keys
+  EPI_SAMPLE      = 5,   // LM head of the non-greedy path: the argmax keys plus, per row, everything the rejection-sampling
+                         // verify needs from softmax(logits / T) - its normaliser (running max, sum of exponentials), the
+                         // scaled logit of the drafted token and a Gumbel-max sample that excludes it - in the same pass
 };
+constexpr int kNgRows = 128;   // rows one EPI_SAMPLE task may carry (four running statistics per row live in smem)
 
 struct GemmTask {
   const __nv_bfloat16* W;    // packed weight tiles [n_tiles (x2 for SWIGLU: gate tiles then up tiles)][k_chunks][128x64 sw128]
@@ -61,6 +66,17 @@ struct GemmTask {
   int out_rows_cap;          // SWIGLU: xrows_cap of the destination packed buffer
   int index_offset;          // ARGMAX: added to the local feature index (vocabulary slice of this rank)
   unsigned int tag;          // PARTIAL_TAGGED: stage tag stored with every partial sum
+  // ---- SAMPLE
+  float inv_temp;            // 1 / temperature
+  unsigned int seed_lo, seed_hi;
+  int fwd;                   // forward index that enters the random counters
+  const int* tok;            // [rows] tokens of the forward in flight: row m verifies tok[m + 1] when both rows belong to
+  const int* row_group;      // the same group
+  int rows_total;            // T of the forward
+  float* ng_prop;            // [rows] logit / T of the drafted token (written by the one thread that owns it)
+  unsigned long long* ng_gumbel;   // [rows] packed (logit / T + Gumbel noise, ~index) keys, atomicMax
+  float2* ng_ms;             // [nctas][ms_stride] per-CTA (running max, sum of exp) of logit / T
+  int ms_stride;
 };
 
 struct GemmSmem {
@@ -277,6 +293,23 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
     for (int m = lane; m < t.M; m += 32) gs->best[q * kArgmaxRows + m] = 0ull;
     __syncwarp();
   }
+  // EPI_SAMPLE shared-memory state (aliases the attention tile buffer like `best`): per epilogue warp and row the running
+  // argmax key, Gumbel key and (max, sum) pair; per row the drafted token the row verifies (-1: none)
+  unsigned long long* ng_best = gs->best;                                     // [4][kNgRows]
+  unsigned long long* ng_gbest = gs->best + 4 * kNgRows;                      // [4][kNgRows]
+  float2* ng_msw = reinterpret_cast<float2*>(gs->best + 8 * kNgRows);         // [4][kNgRows]
+  int* ng_prop_tok = reinterpret_cast<int*>(gs->best + 12 * kNgRows);         // [kNgRows]
+  if (t.epilogue == EPI_SAMPLE) {
+    for (int m = lane; m < t.M; m += 32) {
+      ng_best[q * kNgRows + m] = 0ull; ng_gbest[q * kNgRows + m] = 0ull;
+      ng_msw[q * kNgRows + m] = make_float2(-INFINITY, 0.f);
+      if (q == 0) {
+        const int r = t.x_row0 + m;
+        ng_prop_tok[m] = (r + 1 < t.rows_total && t.row_group[r + 1] == t.row_group[r]) ? t.tok[r + 1] : -1;
+      }
+    }
+    named_bar_sync(1, kWorkerThreads);           // kBarWorkers: the four epilogue warps read warp 0's drafted-token table
+  }
   for (int u = cta; u < units; u += nctas) {
     const UnitRange r = unit_range(t, u);
     const int n = r.n_tile * kTileN + feat_in_tile;
@@ -360,6 +393,63 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
             }
           }
         }
+      } else if (t.epilogue == EPI_SAMPLE) {
+        // Non-greedy verify (reference: engine/jacobi_decoding_nongreedy.py:300-355 over _build_target_probs :110-123):
+        // p = softmax(bf16 logits / T).  One pass over the vocabulary tile gives, per row, the tile's argmax key, its
+        // (max, sum exp) pair, the scaled logit of the drafted token if this thread owns it, and the tile's best
+        // Gumbel-perturbed score among the OTHER tokens: argmax_v (logit_v / T + G_v), v != drafted, is a draw from p
+        // conditioned on != drafted - the residual distribution of the delta proposal (:134-153) - without logits in HBM.
+        const bool valid = n < t.N;
+        const int vglob = n + t.index_offset;
+        for (int c0 = 0; c0 < mpad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          unsigned long long mine_a = 0ull, mine_g = 0ull;
+          float mine_m = -INFINITY, mine_s = 0.f;
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const int row4 = t.x_row0 + m0 + c0 + j4;                        // multiple of 4
+            const Philox4 rnd = philox4x32_10((unsigned int)vglob, (unsigned int)(row4 >> 2), (unsigned int)t.fwd, RNG_GUMBEL,
+                                              t.seed_lo, t.seed_hi);
+            const unsigned int rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 + jj;
+              const int mloc = m0 + c0 + j;
+              const float val = bf16_round(__uint_as_float(v[j]));
+              const float sc = val * t.inv_temp;
+              const int prop = (c0 + j < mlive) ? ng_prop_tok[mloc] : -1;
+              if (valid && c0 + j < mlive && vglob == prop) t.ng_prop[t.x_row0 + mloc] = sc;
+              unsigned long long ka = valid ? argmax_key(val, vglob) : 0ull;
+              const float gum = -__logf(-__logf(u01_open(rw[jj])));
+              unsigned long long kg = (valid && vglob != prop) ? argmax_key(sc + gum, vglob) : 0ull;
+              float mx = valid ? sc : -INFINITY;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                const unsigned long long oa = __shfl_xor_sync(0xffffffffu, ka, o);
+                const unsigned long long og = __shfl_xor_sync(0xffffffffu, kg, o);
+                ka = oa > ka ? oa : ka;
+                kg = og > kg ? og : kg;
+              }
+              float ex = valid ? __expf(sc - mx) : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
+              if (lane == j) { mine_a = ka; mine_g = kg; mine_m = mx; mine_s = ex; }
+            }
+          }
+          const int m = m0 + c0 + lane;
+          if (lane < 16 && c0 + lane < mlive) {
+            if (mine_a > ng_best[q * kNgRows + m]) ng_best[q * kNgRows + m] = mine_a;
+            if (mine_g > ng_gbest[q * kNgRows + m]) ng_gbest[q * kNgRows + m] = mine_g;
+            const float2 old = ng_msw[q * kNgRows + m];
+            const float nm = fmaxf(old.x, mine_m);
+            if (nm > -INFINITY)
+              ng_msw[q * kNgRows + m] = make_float2(nm, old.y * __expf(old.x - nm) + mine_s * __expf(mine_m - nm));
+          }
+          __syncwarp();
+        }
       } else {  // EPI_ARGMAX
         // bf16-rounded logits (reference: lm_head output is bf16, then .float(); modeling/..._unified.py:463).
         // Each warp reduces its 32 vocab rows with shuffles and folds the winner into its running best in smem.
@@ -397,6 +487,28 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
       const unsigned long long k = gs->best[q * kArgmaxRows + m];
       if (k != 0ull) atomicMax(&keys[t.x_row0 + m], k);
     }
+  }
+  if (t.epilogue == EPI_SAMPLE) {
+    __syncwarp();
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(t.out);
+    for (int m = lane; m < t.M; m += 32) {
+      const unsigned long long ka = ng_best[q * kNgRows + m], kg = ng_gbest[q * kNgRows + m];
+      if (ka != 0ull) atomicMax(&keys[t.x_row0 + m], ka);
+      if (kg != 0ull) atomicMax(&t.ng_gumbel[t.x_row0 + m], kg);
+    }
+    named_bar_sync(1, kWorkerThreads);           // every epilogue warp's (max, sum) pairs are final
+    if (cta < units)
+      for (int m = (q * 32 + lane); m < t.M; m += kWorkerThreads) {
+        float2 acc = ng_msw[m];
+#pragma unroll
+        for (int w2 = 1; w2 < 4; ++w2) {
+          const float2 o = ng_msw[w2 * kNgRows + m];
+          const float nm = fmaxf(acc.x, o.x);
+          if (nm > -INFINITY) acc = make_float2(nm, acc.y * __expf(acc.x - nm) + o.y * __expf(o.x - nm));
+        }
+        t.ng_ms[(size_t)cta * t.ms_stride + t.x_row0 + m] = acc;
+      }
+    named_bar_sync(1, kWorkerThreads);           // before a following task re-initialises the tables
   }
 }
 

@@ -123,6 +123,29 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
     // are separated from this point by that forward's cross-GPU barriers
     for (int t = w.wtid; t < c.T_cap; t += kWorkerThreads) c.argmax_keys[(size_t)(kbuf ^ 1) * c.T_cap + t] = 0ull;
   }
+  if (!first && c.ng_mode) {
+    // non-greedy verify inputs: merge the CTAs' (max, sum exp) pairs of every row, turn the drafted token's scaled logit
+    // into its probability, decode the residual sample, and reset the accumulators for the next forward
+    const int parts = min((int)gridDim.x, (c.md.vocab + kTileN - 1) / kTileN);
+    for (int t = w.wtid; t < Tprev; t += kWorkerThreads) {
+      float M = -INFINITY, S = 0.f;
+      for (int p0 = 0; p0 < parts; p0 += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (p0 + i < parts) ? ld_weak(&c.ng_ms[(size_t)(p0 + i) * c.T_cap + t]) : make_float2(-INFINITY, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float nm = fmaxf(M, v[i].x);
+          if (nm > -INFINITY) { S = S * __expf(M - nm) + v[i].y * __expf(v[i].x - nm); M = nm; }
+        }
+      }
+      const float lp = ld_weak(&c.ng_prop[t]);
+      c.ng_px[t] = (S > 0.f && lp > -INFINITY) ? __expf(lp - M) / S : 0.f;
+      c.ng_bonus[t] = argmax_key_index(ld_weak(&c.ng_gumbel[t]));
+      c.ng_prop[t] = -INFINITY;
+      c.ng_gumbel[t] = 0ull;
+    }
+  }
   __threadfence_block();
   workers_sync();
   if (w.lane == 0) {
@@ -138,6 +161,9 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
       bool more;
       if (kn.mode == MODE_ENGINE)
         more = eng_advance(st, kn, src, greedy, c.gen + (size_t)s * c.gen_cap, c.gen_cap);
+      else if (kn.mode == MODE_ENGINE_NG)
+        more = eng_ng_advance(st, kn, src, greedy, c.ng_px + sl.row0, c.ng_bonus + sl.row0, sl.row0,
+                              first ? 0 : ld_weak(&hdr->iter), c.gen + (size_t)s * c.gen_cap, c.gen_cap);
       else
         more = hf_advance(st, kn, src, greedy, sl.L, c.gen + (size_t)s * c.gen_cap, c.gen_cap,
                           c.iters_log + (size_t)s * c.iters_cap, c.iters_cap);
@@ -203,9 +229,10 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
     hdr->want_logits = 0;
     if (err) hdr->error = err;
     int nl = 0;
-    for (int r = 0; r < T && nl < kMaxLmTasks; r += kArgmaxRows) {
+    const int lm_step = c.ng_mode ? kNgRows : kArgmaxRows;
+    for (int r = 0; r < T && nl < kMaxLmTasks; r += lm_step) {
       hdr->lm_row0[nl] = r;
-      hdr->lm_rows[nl] = min(kArgmaxRows, T - r);
+      hdr->lm_rows[nl] = min(lm_step, T - r);
       ++nl;
     }
     hdr->n_lm_tasks = nl;
@@ -462,6 +489,13 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       t.n_tiles = nt_v; t.k_chunks = kc_h; t.splits = 1; t.index_offset = md.vocab_offset;
       t.M = ld_weak(&hdr->lm_rows[i]); t.x_row0 = ld_weak(&hdr->lm_row0[i]);
       t.N = md.vocab; t.epilogue = EPI_ARGMAX;
+      if (c.ng_mode && run_mode == RUN_JACOBI) {
+        t.epilogue = EPI_SAMPLE;
+        t.inv_temp = c.ng_inv_temp; t.seed_lo = c.ng_seed_lo; t.seed_hi = c.ng_seed_hi;
+        t.fwd = ld_weak(&hdr->iter) + c.ng_rng_offset;
+        t.tok = c.tok; t.row_group = c.row_group; t.rows_total = T;
+        t.ng_prop = c.ng_prop; t.ng_gumbel = c.ng_gumbel; t.ng_ms = c.ng_ms; t.ms_stride = c.T_cap;
+      }
       return t;
     };
 

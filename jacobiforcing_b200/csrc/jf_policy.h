@@ -8,6 +8,8 @@
 //                  (candidates :62-91, committed_len :264-271, build_out_and_spans :317-377, pool concat :387-411)
 //   driver         JacobiForcing/jacobi_forcing_inference_MR_humaneval.py:152-240
 //   engine policy  inference_engine/engine/jacobi_decoding.py:303-445 (fixed length L, draft[0] = cached seed)
+//   non-greedy     inference_engine/engine/jacobi_decoding_nongreedy.py:300-355 (accept draft token x with probability
+//                  p(x); on the first rejection commit a token drawn from p conditioned on != x), :385-470 (loop, next draft)
 // `num_blocks`, `active_blocks` and the block-list length are three separate things, exactly as in the reference
 // (SURVEY.md finding 5 / Appendix A).
 #pragma once
@@ -28,7 +30,7 @@ constexpr int kBlocksMax    = 4;     // block-list capacity (K <= 2 needs 2; hea
 constexpr int kPoolEntryMax = kBlocksMax * kNMax;
 constexpr int kOutColsMax   = kBlocksMax * kNMax;
 
-enum PolicyMode : int { MODE_HF_SINGLE = 0, MODE_HF_MULTI = 1, MODE_ENGINE = 2 };
+enum PolicyMode : int { MODE_HF_SINGLE = 0, MODE_HF_MULTI = 1, MODE_ENGINE = 2, MODE_ENGINE_NG = 3 };
 enum StopReason : int { STOP_NONE = 0, STOP_EOS = 1, STOP_MAX_NEW = 2, STOP_MAX_CALLS = 3, STOP_MAX_ITERS = 4,
                         STOP_ERROR = 5 };
 enum PolicyError : int { PERR_NONE = 0, PERR_BROADCAST = 1, PERR_NO_PAD = 2, PERR_BLOCKS = 3, PERR_PROMOTE_LEN = 4,
@@ -47,6 +49,10 @@ struct PolicyKnobs {
   int max_calls;
   int lookahead_min_acc;         // smallest total_acc with total_acc / n >= lookahead_start_ratio (host, double precision)
   int vocab;
+  // ---- non-greedy engine mode (MODE_ENGINE_NG): rejection-sampling verify, jacobi_decoding_nongreedy.py:300-355
+  int temp_bits;               // float bits of the sampling temperature (> 0)
+  unsigned int seed_lo, seed_hi;   // key of the counter-based generator (Philox4x32-10) behind every random draw
+  int rng_offset;              // added to the forward index in the counters (lets consecutive runs share a key)
 };
 
 struct MBlock {
@@ -635,6 +641,102 @@ JF_HD inline bool eng_advance(SeqState& s, const PolicyKnobs& kn, const DraftSou
   s.iters += 1;
   s.total_iters += 1;
   q[0] = gen[s.gen_len - 1];                                        // :197-199
+  for (int j = 0; j < L; ++j) s.out_rows[0][j] = q[j];
+  s.B_out = 1;
+  s.L_out = L;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Counter-based random numbers (Philox4x32-10, Salmon et al. 2011): every draw of the non-greedy path is a pure function
+// of (key, counter), so the device, the host harness and the Python oracle produce the same stream without shared state.
+// The reference draws from torch's global CUDA generator (jacobi_decoding_nongreedy.py:322, :128-131), which is neither
+// seeded nor reproducible across batch compositions; only the DISTRIBUTION of its draws is part of its behaviour.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Philox4 { unsigned int x, y, z, w; };
+JF_HD inline Philox4 philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3, unsigned int k0,
+                                   unsigned int k1) {
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+    const unsigned int n0 = (unsigned int)(p1 >> 32) ^ c1 ^ k0;
+    const unsigned int n1 = (unsigned int)p1;
+    const unsigned int n2 = (unsigned int)(p0 >> 32) ^ c3 ^ k1;
+    const unsigned int n3 = (unsigned int)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+enum RngStream : unsigned int { RNG_GUMBEL = 1u, RNG_ACCEPT = 2u };
+// 24-bit uniforms: [0, 1) for the accept test (u < p), (0, 1) for the Gumbel noise -log(-log(u))
+JF_HD inline float u01_closed_open(unsigned int x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+JF_HD inline float u01_open(unsigned int x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform of the accept test of in-flight row `row` (global row index of the forward) of forward `fwd`
+JF_HD inline float ng_accept_uniform(const PolicyKnobs& kn, int row, int fwd) {
+  return u01_closed_open(philox4x32_10((unsigned int)row, 0u, (unsigned int)(fwd + kn.rng_offset), RNG_ACCEPT, kn.seed_lo,
+                                       kn.seed_hi).x);
+}
+
+// Non-greedy engine policy: one call = one Jacobi iteration of JacobiDecoderNonGreedy._generate_single (:385-470).
+// Per in-flight row t (0 <= t < L-1, verifying draft[t+1]) the forward supplies, besides the argmax `greedy[t]`:
+//   px[t]     target probability of the drafted token, softmax(logits[t] / T)[draft[t+1]]
+//   bonus[t]  a token drawn from softmax(logits[t] / T) conditioned on != draft[t+1]  (:134-153; the residual of the
+//             delta proposal).  Both come out of the LM-head epilogue; only the accept uniforms are drawn here.
+JF_HD inline bool eng_ng_advance(SeqState& s, const PolicyKnobs& kn, const DraftSource& src, const int* greedy,
+                                 const float* px, const int* bonus, int row0, int fwd, int* gen, int gen_cap) {
+  const int L = kn.n;
+  MBlock& b0 = s.blk[0];
+  int* q = b0.draft[0];
+  s.commit_n = 0;
+  s.commit_row = 0;
+  if (L <= 1) { s.finished = 1; s.stop_reason = STOP_ERROR; return false; }
+  if (greedy != nullptr && s.in_call) {
+    // verify (:316-347): sequential accept / reject along the block
+    int committed = 0;
+    bool eos_reached = false;
+    for (int t = 0; t < L - 1; ++t) {
+      const int proposed = q[t + 1];
+      const float u = ng_accept_uniform(kn, row0 + t, fwd);
+      int tok = proposed;
+      const bool accept = u < px[t];
+      if (!accept) tok = bonus[t];
+      if (s.gen_len < gen_cap) gen[s.gen_len++] = tok;
+      ++committed;
+      if (kn.eos >= 0 && tok == kn.eos) eos_reached = true;
+      if (!accept || eos_reached) break;
+    }
+    s.total_new += committed;
+    const int new_ctx = s.gen_len - 1;                       // the last committed token is the next seed (recomputed)
+    s.commit_n = new_ctx - s.ctx;
+    s.ctx = new_ctx;
+    if (eos_reached) { s.finished = 1; s.stop_reason = STOP_EOS; s.eos_seen = 1; return false; }
+    if (s.total_new >= kn.max_new_tokens) { s.finished = 1; s.stop_reason = STOP_MAX_NEW; return false; }
+    // next draft (:446-466): seed + greedy fill from the current logits + random padding
+    const int acc_len = 1 + committed;
+    int d[kNMax];
+    int dl = 0;
+    d[dl++] = gen[s.gen_len - 1];
+    if (acc_len < L) {
+      for (int j = acc_len - 1; j < L - 1 && dl < L; ++j) d[dl++] = greedy[j];
+    } else {
+      d[dl++] = greedy[L - 2];
+    }
+    while (dl < L) d[dl++] = eng_next_pad(s, kn, src);
+    for (int j = 0; j < L; ++j) q[j] = d[j];
+  } else if (!s.in_call) {
+    q[0] = gen[s.gen_len - 1];                                // _init_draft (:216-236): seed + random tokens
+    int dl = 1;
+    if (src.first_call_tokens != nullptr)
+      for (int j = 0; j < L - 1; ++j) q[dl++] = src.first_call_tokens[j];
+    while (dl < L) q[dl++] = eng_next_pad(s, kn, src);
+    s.in_call = 1;
+    s.ctx = s.gen_len - 1;
+  }
+  if (s.error != PERR_NONE) { s.finished = 1; s.stop_reason = STOP_ERROR; return false; }
+  if (s.iters >= kn.max_iteration_count) { s.finished = 1; s.stop_reason = STOP_MAX_ITERS; return false; }
+  s.iters += 1;
+  s.total_iters += 1;
+  q[0] = gen[s.gen_len - 1];
   for (int j = 0; j < L; ++j) s.out_rows[0][j] = q[j];
   s.B_out = 1;
   s.L_out = L;

@@ -140,6 +140,16 @@ struct alignas(16) DevCtx {
   int* iters_log;                    // [S_cap][iters_cap]
   int iters_cap;
   int n_seqs;
+  // ---- non-greedy verify (MODE_ENGINE_NG; reference: engine/jacobi_decoding_nongreedy.py:300-355)
+  int ng_mode;                       // 1: the LM head runs EPI_SAMPLE and the policy stage the rejection-sampling verify
+  float ng_inv_temp;                 // 1 / temperature
+  unsigned int ng_seed_lo, ng_seed_hi;
+  int ng_rng_offset;
+  float* ng_prop;                    // [T_cap] logit / T of the drafted token of every row (-inf: outside the vocabulary)
+  unsigned long long* ng_gumbel;     // [T_cap] best Gumbel-perturbed key among the other tokens
+  float2* ng_ms;                     // [nctas][T_cap] per-CTA (max, sum exp) of logit / T
+  float* ng_px;                      // [T_cap] merged by the policy stage: probability of the drafted token
+  int* ng_bonus;                     // [T_cap] and the residual sample
   int* trace;                        // optional forward trace: {iter, seq, ctx, B, L, tokens...}*
   int trace_cap;
   int* trace_len;

@@ -8,11 +8,12 @@ choices the reference's driver makes between calls (JacobiForcing/jacobi_forcing
 from __future__ import annotations
 
 import math
+import struct
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
-MODE_HF_SINGLE, MODE_HF_MULTI, MODE_ENGINE = 0, 1, 2
-MODES = {"single": MODE_HF_SINGLE, "multiblock": MODE_HF_MULTI, "engine": MODE_ENGINE}
+MODE_HF_SINGLE, MODE_HF_MULTI, MODE_ENGINE, MODE_ENGINE_NG = 0, 1, 2, 3
+MODES = {"single": MODE_HF_SINGLE, "multiblock": MODE_HF_MULTI, "engine": MODE_ENGINE, "engine_nongreedy": MODE_ENGINE_NG}
 STOP_REASONS = {0: "", 1: "eos", 2: "max_new_tokens", 3: "max_calls", 4: "max_iterations", 5: "error",
                 }
 POLICY_ERRORS = {0: "", 1: "reference would fail to broadcast draft rows against greedy rows",
@@ -36,12 +37,18 @@ class PolicyKnobs:
     max_new_tokens: int = 512
     max_calls: int = 1024
     vocab: int = 0
+    # non-greedy engine mode: sampling temperature, 64-bit key of the counter-based generator, counter offset
+    temperature: float = 0.0
+    seed: int = 0
+    rng_offset: int = 0
 
     def validate(self) -> None:
         if not (1 <= self.n <= N_MAX):
             raise ValueError(f"block length n={self.n} outside [1, {N_MAX}]")
-        if self.mode == MODE_ENGINE and self.n < 2:
+        if self.mode in (MODE_ENGINE, MODE_ENGINE_NG) and self.n < 2:
             raise ValueError("Jacobi draft length L must be >= 2")          # jacobi_decoding.py:316-317
+        if self.mode == MODE_ENGINE_NG and not self.temperature > 0.0:
+            raise ValueError("non-greedy Jacobi decoding needs temperature > 0")
         if self.mode == MODE_HF_MULTI:
             if not (1 <= self.K <= 2):
                 raise NotImplementedError("K >= 3 relies on the reference's block-list drift (SURVEY.md finding 5); "
@@ -56,7 +63,9 @@ class PolicyKnobs:
         lsr_min = next((a for a in range(0, 2 * N_MAX + 1) if a / n >= self.lookahead_start_ratio), 1 << 30)
         return [self.mode, n, self.K, spawn, self.n_gram_pool_size,
                 -1 if self.eos is None else int(self.eos), -1 if self.pad is None else int(self.pad),
-                self.max_iteration_count, self.max_new_tokens, self.max_calls, lsr_min, self.vocab]
+                self.max_iteration_count, self.max_new_tokens, self.max_calls, lsr_min, self.vocab,
+                struct.unpack("<i", struct.pack("<f", float(self.temperature)))[0],
+                int(self.seed) & 0xFFFFFFFF, (int(self.seed) >> 32) & 0xFFFFFFFF, int(self.rng_offset)]
 
 
 def mt_state_words(rng) -> List[int]:

@@ -53,6 +53,46 @@ int jf_policy_replay(const int* knobs_i /*12 ints in PolicyKnobs order*/, const 
   return rc;
 }
 
+// Non-greedy engine policy (MODE_ENGINE_NG): forward f supplies px / bonus / greedy for its L-1 verify rows (row0 = 0);
+// rows_out[f][L] receives the draft the policy asked to forward.  Returns the number of forwards consumed (<= nfw).
+int jf_policy_replay_ng(const int* knobs_i, const int* prompt, int prompt_len, int ctx0, const int* pad_stream,
+                        int pad_stream_len, int nfw, const float* px_flat, const int* bonus_flat, const int* greedy_flat,
+                        int* rows_out, int* ctx_out, int* gen_out, int gen_cap, int* result /*[8]*/) {
+  PolicyKnobs kn;
+  std::memcpy(&kn, knobs_i, sizeof(PolicyKnobs));
+  SeqState* s = (SeqState*)std::calloc(1, sizeof(SeqState));
+  seq_state_init(*s, prompt_len, ctx0, 0);
+  for (int i = 0; i < prompt_len && i < gen_cap; ++i) gen_out[i] = prompt[i];
+  DraftSource src{nullptr, nullptr, 0, pad_stream, pad_stream_len};
+  const int L = kn.n;
+  int f = 0;
+  while (true) {
+    const bool have = f > 0;
+    const bool more = eng_ng_advance(*s, kn, src, have ? greedy_flat + (size_t)(f - 1) * (L - 1) : nullptr,
+                                     have ? px_flat + (size_t)(f - 1) * (L - 1) : nullptr,
+                                     have ? bonus_flat + (size_t)(f - 1) * (L - 1) : nullptr, 0, f - 1, gen_out, gen_cap);
+    if (!more || f >= nfw) break;
+    for (int j = 0; j < L; ++j) rows_out[(size_t)f * L + j] = s->out_rows[0][j];
+    ctx_out[f] = s->ctx;
+    ++f;
+  }
+  result[0] = s->gen_len; result[1] = s->calls; result[2] = s->stop_reason; result[3] = s->total_new;
+  result[4] = s->error; result[5] = f; result[6] = s->total_iters; result[7] = s->ctx;
+  std::free(s);
+  return f;
+}
+
+void jf_philox(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3, unsigned int k0, unsigned int k1,
+               unsigned int* out4) {
+  const Philox4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
+  out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+float jf_ng_accept_uniform(const int* knobs_i, int row, int fwd) {
+  PolicyKnobs kn;
+  std::memcpy(&kn, knobs_i, sizeof(PolicyKnobs));
+  return ng_accept_uniform(kn, row, fwd);
+}
+
 int jf_policy_state_bytes() { return (int)sizeof(SeqState); }
 int jf_policy_knob_ints() { return (int)(sizeof(PolicyKnobs) / sizeof(int)); }
 
