@@ -162,6 +162,13 @@ class ModelRunner:
             knobs = PolicyKnobs(mode=MODES["engine"], n=L, eos=eos, pad=pad,
                                 max_iteration_count=int(s0.jacobi_max_iterations), max_new_tokens=remaining, vocab=V)
             n_pad = knobs.max_iteration_count * (L - 1) + L
+        elif mode == "engine_nongreedy":
+            # rejection-sampling verify (jacobi_decoding_nongreedy.py:300-355): every random draw of the call comes from
+            # a counter-based generator keyed by a fresh 64-bit seed out of this runner's seeded RNG
+            knobs = PolicyKnobs(mode=MODES["engine_nongreedy"], n=L, eos=eos, pad=pad,
+                                max_iteration_count=int(s0.jacobi_max_iterations), max_new_tokens=remaining, vocab=V,
+                                temperature=float(s0.temperature), seed=self._rng.getrandbits(64))
+            n_pad = min(knobs.max_iteration_count, remaining + 1) * (L - 1) + L
         else:
             n_calls = (remaining + L - 1) // L + 3
             knobs = PolicyKnobs(mode=MODES["multiblock"], n=L, K=int(s0.jacobi_max_blocks),
@@ -174,7 +181,11 @@ class ModelRunner:
             S = len(seq)
             self._reserve(seq, S + remaining + 3 * L + 1)
             draft = getattr(seq, "_prefill_draft", None)
-            if mode == "engine":
+            if mode == "engine_nongreedy":
+                handles.append(self._handle(seq, S - 1))
+                fcs.append(0)                                                 # the non-greedy decoder never reads the
+                pads.append([self._rng.randrange(V) for _ in range(n_pad)])  # prefill draft: seed + random (:216-236)
+            elif mode == "engine":
                 handles.append(self._handle(seq, S - 1))
                 fcs.append(0)
                 fcts.append((list(draft) + [0] * L)[:L] if draft else
@@ -190,7 +201,7 @@ class ModelRunner:
                     fcts.append([int(seq._first_correct)] + [self._rng.choice(seq.token_ids) for _ in range(L - 1)])
                 chs.append(mt_state_words(random.Random(self._rng.getrandbits(64))))
             seq._prefill_draft = None
-        results, run = self.rt.jacobi_run(handles, knobs, fcs, fcts, rng_states=(chs or None),
+        results, run = self.rt.jacobi_run(handles, knobs, fcs, (fcts or None), rng_states=(chs or None),
                                           pad_stream=(pads or None), want_trace=True)
         out = []
         st = self.jacobi_decoder.stats
@@ -217,7 +228,7 @@ class ModelRunner:
         for i, s in enumerate(seqs):                                          # group-by-L (jacobi_decoding.py:500-515)
             key = (int(s.jacobi_block_len), int(s.jacobi_max_iterations), int(s.max_tokens) - s.num_completion_tokens,
                    int(s.jacobi_max_blocks), float(s.jacobi_spawn_ratio), int(s.jacobi_n_gram_pool_size),
-                   float(s.jacobi_lookahead_start_ratio))
+                   float(s.jacobi_lookahead_start_ratio), float(s.temperature))
             groups.setdefault(key, []).append(i)
         out: List[Optional[List[int]]] = [None] * len(seqs)
         for idxs in groups.values():
@@ -230,7 +241,8 @@ class ModelRunner:
 
     def _run_autoregressive(self, seqs: List[Sequence], is_prefill: bool) -> List[int]:
         if any(s.temperature > 0 for s in seqs):
-            raise NotImplementedError("sampling (temperature > 0) is outside the greedy hot path of this build")
+            raise NotImplementedError("autoregressive sampling (temperature > 0): use decode_strategy='jacobi', whose "
+                                      "non-greedy verify samples from the same distribution")
         tokens = []
         if is_prefill:
             for seq in seqs:
@@ -271,9 +283,18 @@ class ModelRunner:
                 f"Mixed decode strategies in same batch not supported. Got {len(jac)} Jacobi, {len(mb)} multiblock "
                 f"and {len(ar)} autoregressive sequences.")
         if jac or mb:
-            if any(getattr(s, "jacobi_on_policy", False) or s.temperature > 0 for s in seqs):
-                raise NotImplementedError("non-greedy / on-policy Jacobi decoding is outside the greedy hot path")
+            if any(getattr(s, "jacobi_on_policy", False) for s in seqs):
+                raise NotImplementedError("on-policy rollout records (jacobi_decoding_nongreedy_on_policy.py) are not "
+                                          "part of this build")
+            temps = [float(s.temperature) for s in seqs]
+            nongreedy = all(t > 0.0 for t in temps)
+            if not nongreedy and any(t > 0.0 for t in temps):                 # model_runner.py:331-373
+                raise NotImplementedError("Mixed greedy / non-greedy temperatures in one batch are not supported")
+            if nongreedy and mb:
+                raise NotImplementedError("the multiblock strategy is greedy only")
+            if nongreedy and self.world_size > 1:
+                raise NotImplementedError("non-greedy Jacobi decoding is not available under tensor parallelism")
             if is_prefill:
                 return self._jacobi_prefill_with_drafting(seqs)
-            return self._run_jacobi(seqs, "engine" if jac else "multiblock")
+            return self._run_jacobi(seqs, "engine_nongreedy" if nongreedy else ("engine" if jac else "multiblock"))
         return self._run_autoregressive(seqs, is_prefill)

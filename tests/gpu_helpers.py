@@ -87,11 +87,13 @@ class DeviceEngineForward:
     """forward_step callback of oracle.jacobi_policy.engine_fixed_len on the device forward: draft[0] is the last
     committed token at position S-1; what the policy accepted of the previous draft is committed lazily."""
 
-    def __init__(self, rt: JacobiRuntime, seq):
+    def __init__(self, rt: JacobiRuntime, seq, want_logits: bool = False):
         self.rt, self.seq = rt, seq
         self.cached = seq.ctx          # tokens physically in the cache
         self.last_base = None
         self.n_forwards = 0
+        self.want_logits = want_logits
+        self.last_logits = None        # fp32 [L, V] of the last forward (want_logits)
 
     def __call__(self, token_ids, draft):
         S = len(token_ids)
@@ -100,7 +102,8 @@ class DeviceEngineForward:
             self.rt.commit_rows([self.seq], [(p - self.last_base, 0, p) for p in range(self.last_base, base)])
         L = len(draft)
         self.rt.ensure_capacity(self.seq, base + L)
-        res = self.rt.forward(list(draft), [(0, L, 0, base)], [self.seq], 0, L)
+        res = self.rt.forward(list(draft), [(0, L, 0, base)], [self.seq], 0, L, want_logits=self.want_logits)
         self.last_base = base
         self.n_forwards += 1
+        self.last_logits = res["logits"]
         return [int(t) for t in res["greedy"][:L - 1]]
