@@ -35,6 +35,9 @@ SHAPES = {
     "qwen2.5-coder-7b": dict(hidden_size=3584, num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4,
                              head_dim=128, intermediate_size=18944, vocab_size=152064, tie_word_embeddings=False,
                              rope_theta=1e6, max_position_embeddings=32768, rms_norm_eps=1e-6),
+    "qwen2.5-math-7b": dict(hidden_size=3584, num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4,
+                            head_dim=128, intermediate_size=18944, vocab_size=152064, tie_word_embeddings=False,
+                            rope_theta=1e4, max_position_embeddings=4096, rms_norm_eps=1e-6),
     "qwen2-0.5b": dict(hidden_size=896, num_hidden_layers=24, num_attention_heads=14, num_key_value_heads=2,
                        head_dim=64, intermediate_size=4864, vocab_size=151936, tie_word_embeddings=True,
                        rope_theta=1e6, max_position_embeddings=32768, rms_norm_eps=1e-6),
@@ -267,7 +270,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     rows_cap = min(max(rows_cap, 64), 4096)
     pages = (P + G + 3 * n + 255) // 256 + 1
     rt = JacobiRuntime(cfg, device=local_rank, max_rows=rows_cap, max_seqs=B, num_kv_pages=pages * B,
-                       max_pages_per_seq=pages, gen_capacity=P + G + 4 * n + 8, max_calls=G // n + 8,
+                       max_pages_per_seq=pages, attn_chunk=args.attn_chunk, gen_capacity=P + G + 4 * n + 8,
+                       max_calls=G // n + 8,
                        tp_rank=tp_rank, tp_size=tp, tp_group=tp_group, tp_shard_attention=args.tp_shard_attention)
     load_random_weights(rt, cfg, seed=1234 + group_id, device=device)
 
@@ -434,6 +438,7 @@ def main():
     ap.add_argument("--gen", type=int, default=512)
     ap.add_argument("--ref-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn-chunk", type=int, default=64, help="keys per attention work unit (multiple of 64)")
     ap.add_argument("--tp", type=int, default=0, help="tensor-parallel group size (1, 2, 4, 8); default (0) = all N GPUs in one group")
     ap.add_argument("--replicas", action="store_true", help="N independent engines instead of tensor parallelism")
     ap.add_argument("--tp-shard-attention", action="store_true", help="shard the attention block too (heads must divide tp)")

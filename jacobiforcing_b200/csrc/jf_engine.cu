@@ -237,6 +237,7 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     if (const char* e = getenv("JF_DOWN_SPLITS")) c.splits_down = std::max(1, std::min(c.splits_down, atoi(e)));
   }
   c.tp_rank = tpr; c.tp_size = tp; c.tp_attn = tpa;
+  c.fuse_rows = std::min(rt.max_rows, tp > 1 ? kFuseRowsTP : kFuseRows);
   h->max_splits = std::max(c.splits_qkv, std::max(c.splits_o, c.splits_down));
 
   int rc = JF_OK;
@@ -333,16 +334,16 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   if (tp > 1 && tpa == 1) ALLOC(c.part_rs[2], (size_t)c.T_cap * c.part_splits * md.h, h->bytes_act);
   if (tp > 1) {
     unsigned long long *pb = nullptr, *sb = nullptr;
-    c.push_rows_cap = (kFuseRows + tp - 1) / tp + 8;
+    c.push_rows_cap = (c.fuse_rows + tp - 1) / tp + 8;
     ALLOC(pb, (size_t)c.push_rows_cap * tp * md.h, h->bytes_act);
-    ALLOC(sb, (size_t)kFuseRows * md.h, h->bytes_act);              // [rows][h / 8][8] words
+    ALLOC(sb, (size_t)c.fuse_rows * md.h, h->bytes_act);              // [rows][h / 8][8] words
     c.push_buf[tpr] = pb; c.stage_buf[tpr] = sb;
   }
   ALLOC(c.tpart, (size_t)kFuseRopeRows * c.part_splits * c.part_n, h->bytes_act);
   c.tgu = nullptr;
   if (c.splits_gu > 1) ALLOC(c.tgu, (size_t)c.T_cap * c.splits_gu * 2 * md.inter, h->bytes_act);
-  ALLOC(c.tpart_rs[0], (size_t)kFuseRows * c.part_splits * md.h, h->bytes_act);
-  ALLOC(c.tpart_rs[1], (size_t)kFuseRows * c.part_splits * md.h, h->bytes_act);
+  ALLOC(c.tpart_rs[0], (size_t)c.fuse_rows * c.part_splits * md.h, h->bytes_act);
+  ALLOC(c.tpart_rs[1], (size_t)c.fuse_rows * c.part_splits * md.h, h->bytes_act);
   ALLOC(c.attn_ml, (size_t)c.attn_slots_cap * md.n_q * 2, h->bytes_act);
   ALLOC(c.attn_o, (size_t)c.attn_slots_cap * md.n_q * md.d, h->bytes_act);
   ALLOC(c.xact, (size_t)kc_i * c.xrows_cap * 64, h->bytes_act);
@@ -723,12 +724,12 @@ static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float
     DevCtx& c = h->hctx;
     JF_CUDA(h, cudaMemsetAsync(c.row_ss, 0, (size_t)c.T_cap * kMaxHTiles * 8, h->stream));
     JF_CUDA(h, cudaMemsetAsync(c.tpart, 0, (size_t)kFuseRopeRows * c.part_splits * c.part_n * 8, h->stream));
-    JF_CUDA(h, cudaMemsetAsync(c.tpart_rs[0], 0, (size_t)kFuseRows * c.part_splits * h->md.h * 8, h->stream));
-    JF_CUDA(h, cudaMemsetAsync(c.tpart_rs[1], 0, (size_t)kFuseRows * c.part_splits * h->md.h * 8, h->stream));
+    JF_CUDA(h, cudaMemsetAsync(c.tpart_rs[0], 0, (size_t)c.fuse_rows * c.part_splits * h->md.h * 8, h->stream));
+    JF_CUDA(h, cudaMemsetAsync(c.tpart_rs[1], 0, (size_t)c.fuse_rows * c.part_splits * h->md.h * 8, h->stream));
     if (c.tgu) JF_CUDA(h, cudaMemsetAsync(c.tgu, 0, (size_t)c.T_cap * c.splits_gu * 2 * h->md.inter * 8, h->stream));
     if (c.tp_size > 1) {
       JF_CUDA(h, cudaMemsetAsync(c.push_buf[c.tp_rank], 0, (size_t)c.push_rows_cap * c.tp_size * h->md.h * 8, h->stream));
-      JF_CUDA(h, cudaMemsetAsync(c.stage_buf[c.tp_rank], 0, (size_t)kFuseRows * h->md.h * 8, h->stream));
+      JF_CUDA(h, cudaMemsetAsync(c.stage_buf[c.tp_rank], 0, (size_t)c.fuse_rows * h->md.h * 8, h->stream));
     }
     c.tag_base = 0u;
   }

@@ -430,7 +430,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
 
     JF_SIMT_STAGE(SID_EMBED, stage_commit(c, ws, ip.n_commit); stage_rows_norm(c, ws, T, true, 0, c.layer[0].ln1, 0, 1));
     // the fused tails apply to Jacobi-sized forwards on one GPU (see gemm_stage); prefill-sized ones keep the stages
-    const bool fuse_ok = c.fuse_norm != 0 && T <= kFuseRows;
+    const bool fuse_ok = c.fuse_norm != 0 && T <= c.fuse_rows;
     const bool fuse_o = fuse_ok && nt_h * c.splits_o <= nctas;
     const bool fuse_d = fuse_ok && nt_h * c.splits_down <= nctas;
     // split-K gate/up is a property of the engine (set when it is created), never of the forward: every forward must

@@ -14,7 +14,9 @@ constexpr int kQTokPerUnit = 64;     // query tokens one attention unit covers
 constexpr int kMaxHTiles   = 64;     // 128-column tiles of a hidden row (h <= 8192)
 constexpr int kMaxTilesPerKind = 128; // arrival counters per fused GEMM kind (O, down, QKV)
 constexpr int kFuseRopeRows = 64;    // forwards of at most this many rows run the fused QKV + rotary tail
-constexpr int kFuseRows    = 320;    // row capacity of the tagged partial buffers of the fused O / down tails
+constexpr int kFuseRows    = 320;    // default row capacity of the tagged partial buffers of the fused O / down tails (one GPU)
+constexpr int kFuseRowsTP  = 2048;   // under tensor parallelism: the fused tails exchange ~1/ranks of what the stand-alone
+                                     // stage pulls over NVLink, so batched / prefill-sized forwards stay fused too
 constexpr int kMaxTP       = 8;      // tensor-parallel ranks whose buffers one kernel may address (NVLink peers)
 
 struct ModelDims {
@@ -103,7 +105,7 @@ struct alignas(16) DevCtx {
                                      // rows of a forward share a few 2 MB pages (TLB reach matters: see DESIGN.md)
   int part_splits, part_n;
   unsigned long long* tpart;         // [kFuseRopeRows][part_splits][part_n] tagged {stage tag, fp32} partial sums of the fused QKV stage
-  unsigned long long* tpart_rs[2];   // [kFuseRows][part_splits][h] the same for the fused O / down stages
+  unsigned long long* tpart_rs[2];   // [fuse_rows][part_splits][h] the same for the fused O / down stages
   unsigned long long* tgu;           // [T_cap][splits_gu][2][inter] tagged gate / up partial sums (split-K gate/up)
   float* part_rs[3];                 // [T_cap][part_splits][h]: partials of the row-split GEMMs (0 = O, 1 = down); with
                                      // tensor parallelism the peers read them over NVLink, hence double-buffered
@@ -163,9 +165,10 @@ struct alignas(16) DevCtx {
   int tp_rank, tp_size;
   int tp_attn;                                // ranks the attention block (QKV / O) is sharded over: tp_size, or 1 when
                                               // attention is replicated on every rank (MLP-only tensor parallelism)
-  int push_rows_cap;                          // owned rows a push buffer holds (>= ceil(kFuseRows / ranks))
+  int fuse_rows;                              // forwards of at most this many rows run the fused O / down tails
+  int push_rows_cap;                          // owned rows a push buffer holds (>= ceil(fuse_rows / ranks))
   unsigned long long* push_buf[kMaxTP];       // rank r's push buffer [push_rows_cap][tp_size][h] of tagged partial sums
-  unsigned long long* stage_buf[kMaxTP];      // rank r's staging buffer [kFuseRows][h / 8][8] of tagged finished rows:
+  unsigned long long* stage_buf[kMaxTP];      // rank r's staging buffer [fuse_rows][h / 8][8] of tagged finished rows:
                                               // per 8-column group, words 0-3 = hidden, 4-7 = xn (two bf16 per word)
   const float* peer_part_rs[kMaxTP][3];       // the peers' fp32 partial buffers (stand-alone reduce stage, prefill)
   const unsigned long long* peer_keys[kMaxTP];
