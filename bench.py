@@ -253,6 +253,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # headline.  --tp T < N: N / T groups with independent sequence batches; --replicas: N independent engines (how the
     # reference's own sweep uses several GPUs, scripts/inference/scanning_hyperparameter_jacobi_decoding_mr.sh:31-45).
     tp = 1 if args.replicas else (args.tp if args.tp > 0 else world)
+    divides = cfg["num_key_value_heads"] % tp == 0 and cfg["num_attention_heads"] % tp == 0
+    args.tp_shard_attention = tp > 1 and (args.tp_attn == "shard" or (args.tp_attn == "auto" and divides))
     if world % tp or tp not in (1, 2, 4, 8) or (args.tp_shard_attention and cfg["num_key_value_heads"] % tp):
         raise SystemExit(f"--tp {tp} does not fit {world} GPUs / {cfg['num_key_value_heads']} KV heads")
     groups = world // tp
@@ -441,7 +443,9 @@ def main():
     ap.add_argument("--attn-chunk", type=int, default=64, help="keys per attention work unit (multiple of 64)")
     ap.add_argument("--tp", type=int, default=0, help="tensor-parallel group size (1, 2, 4, 8); default (0) = all N GPUs in one group")
     ap.add_argument("--replicas", action="store_true", help="N independent engines instead of tensor parallelism")
-    ap.add_argument("--tp-shard-attention", action="store_true", help="shard the attention block too (heads must divide tp)")
+    ap.add_argument("--tp-attn", default="auto", choices=["auto", "shard", "replicate"],
+                    help="attention block under tensor parallelism: sharded by heads (must divide tp), replicated on "
+                         "every rank (MLP-only TP, one exchange per block), or auto = shard when the heads divide")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                  # timing rule: at least three warm-up steps

@@ -36,9 +36,10 @@ class Config:
     jacobi_multiblock_enabled: bool = False                # serve "jacobi_multiblock_rejection_recycling" on device
     draft_seed: int = 0                                    # seeds every random draft token (reference: unseeded RNGs)
     device: int = 0
-    tp_shard_attention: bool = False                       # False: MLP-only tensor parallelism (attention replicated on
+    tp_shard_attention: Optional[bool] = None              # True: heads sharded like the reference (heads must divide tp);
+                                                           # False: MLP-only tensor parallelism (attention replicated on
                                                            # every rank: one exchange per block, any tp in {2,4,8});
-                                                           # True: heads sharded like the reference (heads must divide)
+                                                           # None: shard when the heads divide, else replicate
 
     def __post_init__(self):
         self.model = _resolve_checkpoint_dir(self.model)

@@ -54,11 +54,12 @@ class JacobiRuntime:
     def __init__(self, hf_config, *, device: int = 0, max_rows: int = 1024, max_seqs: int = 8,
                  num_kv_pages: int = 64, max_pages_per_seq: int = 8, attn_chunk: int = 64, attn_slots: int = 0,
                  gen_capacity: int = 4096, max_calls: int = 256, trace_capacity: int = 0,
-                 tp_rank: int = 0, tp_size: int = 1, tp_group=None, tp_shard_attention: bool = False,
+                 tp_rank: int = 0, tp_size: int = 1, tp_group=None, tp_shard_attention: Optional[bool] = None,
                  num_ctas: int = 0):
         """tp_group: a torch.distributed group (one process per GPU) or a tp.LocalTPGroup (one thread per rank in this
-        process).  tp_shard_attention: False = MLP-only tensor parallelism (attention replicated, one exchange per
-        block, any tp in {2,4,8}); True = heads sharded too (reference layout; heads must divide)."""
+        process).  tp_shard_attention: True = heads sharded too (the reference's layout; q and kv heads must divide tp);
+        False = MLP-only tensor parallelism (attention replicated, ONE exchange per block, any tp in {2,4,8});
+        None = shard when the heads divide (measured faster at every batch size), else replicate."""
         self.lib = _cabi.load()
         g = (lambda k, d=None: hf_config[k] if isinstance(hf_config, dict) else getattr(hf_config, k, d))
         heads = int(g("num_attention_heads"))
@@ -72,6 +73,8 @@ class JacobiRuntime:
             hidden, int(g("num_hidden_layers")), heads, int(g("num_key_value_heads")), int(head_dim),
             int(g("intermediate_size")), int(g("vocab_size")), int(bool(g("tie_word_embeddings", False))),
             int(g("max_position_embeddings")), float(g("rms_norm_eps", 1e-6)), float(theta))
+        if tp_shard_attention is None:
+            tp_shard_attention = heads % tp_size == 0 and int(g("num_key_value_heads")) % tp_size == 0
         self.tp_shard_attention = bool(tp_shard_attention) and tp_size > 1
         check_divisibility(hf_config, tp_size, self.tp_shard_attention)
         self.tp_rank, self.tp_size = tp_rank, tp_size

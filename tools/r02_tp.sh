@@ -7,5 +7,5 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 timeout 600 $TR bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_tp$N.err | tail -1 > gpurun_out/r02_bench_n${N}_tp$N.json; head -c 700 gpurun_out/r02_bench_n${N}_tp$N.json; echo
 timeout 600 $TR tools/stage_profile.py --gen 64 --out gpurun_out/stage_profile_tp$N.json > gpurun_out/r02_stage_profile_tp$N.txt 2>&1; tail -14 gpurun_out/r02_stage_profile_tp$N.txt
 if [ "$N" -le 4 ]; then
-timeout 600 $TR bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline --tp-shard-attention 2>gpurun_out/bench_tp${N}sa.err | tail -1 > gpurun_out/r02_bench_n${N}_tp${N}_shardattn.json; head -c 400 gpurun_out/r02_bench_n${N}_tp${N}_shardattn.json; echo
+timeout 600 $TR bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline --tp-attn shard 2>gpurun_out/bench_tp${N}sa.err | tail -1 > gpurun_out/r02_bench_n${N}_tp${N}_shardattn.json; head -c 400 gpurun_out/r02_bench_n${N}_tp${N}_shardattn.json; echo
 fi

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--prompt", type=int, default=512)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--mode", default="single")
-    ap.add_argument("--shard-attention", action="store_true")
+    ap.add_argument("--tp-attn", default="auto", choices=["auto", "shard", "replicate"])
     ap.add_argument("--attn-chunk", type=int, default=64)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "stage_profile.json"))
     a = ap.parse_args()
@@ -40,7 +40,7 @@ def main():
     pages = (a.prompt + a.gen + 3 * a.n + 255) // 256 + 1
     rt = JacobiRuntime(cfg, device=rank, max_rows=max(a.prompt + a.n, 64, a.batch * a.n * 5), max_seqs=a.batch,
                        num_kv_pages=pages * a.batch, max_pages_per_seq=pages, attn_chunk=a.attn_chunk, gen_capacity=a.prompt + a.gen + 4 * a.n + 8,
-                       tp_rank=rank, tp_size=world, tp_group=group, tp_shard_attention=a.shard_attention)
+                       tp_rank=rank, tp_size=world, tp_group=group, tp_shard_attention={'auto': None, 'shard': True, 'replicate': False}[a.tp_attn])
     bench.load_random_weights(rt, cfg, 1234, f"cuda:{rank}")
     g = torch.Generator().manual_seed(1)
     prompts = [torch.randint(0, cfg["vocab_size"], (a.prompt,), generator=g).tolist() for _ in range(a.batch)]
