@@ -86,6 +86,7 @@ struct GemmSmem {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad_;
+  long long t_acc_full;       // developer aid: clock of the first accumulator hand-over of the last GEMM stage
   unsigned long long* best;   // [4][kArgmaxRows] EPI_ARGMAX running best key per epilogue warp and row (aliases
                               // the attention tile buffer: the LM head never overlaps an attention stage)
 };
@@ -318,6 +319,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
       const int mlive = min(t.M - m0, rows_mma);
       const int mpad = round_up16(mlive);
       mbar_wait(&gs->acc_full[acc.buf], acc.phase);
+      if (threadIdx.x == 64 && u == cta && mt == 0) gs->t_acc_full = clock64();
       AccState acc2 = acc;
       if (wide) { acc2.advance(); mbar_wait(&gs->acc_full[acc2.buf], acc2.phase); }
       tc_fence_after();

@@ -316,7 +316,14 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     } else {
       w.tag = c.tag_base + bs.epoch + 1u;
       ws->tag = w.tag;
+      prof_mark(c, w, 600);
       gemm_epilogue(t, gs, cta, nctas, acc);
+      if (w.prof_on && w.wtid == 0 && c.prof_marks != nullptr) {
+        int* cnt = reinterpret_cast<int*>(w.red) + 4;
+        const int n = *cnt;
+        // developer aid: 600 = epilogue entered, 601 = first accumulator handed over, 602 = epilogue done
+        if (n + 4 <= 8192) { c.prof_marks[n] = 601; c.prof_marks[n + 1] = gs->t_acc_full; c.prof_marks[n + 2] = 602; c.prof_marks[n + 3] = clock64(); *cnt = n + 4; }
+      }
       if (fuse_kind == 5) {
         // gate/up -> down without a grid barrier: publish this tile to the k-splits of the down projection that read it
         fence_proxy_async_all();                        // the tile is read by bulk copies (async proxy) of other CTAs
