@@ -40,6 +40,7 @@ struct jf_engine {
   uint8_t* arena_base[3] = {nullptr, nullptr, nullptr};
   size_t arena_off[3] = {0, 0, 0};
   int64_t launches = 0;
+  int* dbg_host = nullptr;
   // weight bookkeeping
   std::vector<uint32_t> seen_layer;  // W_* / B_* bits per layer (jf_finalize_weights refuses a partial checkpoint)
   int seen_global = 0;
@@ -280,7 +281,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   ALLOC(c.xa, (size_t)kc_q * c.xrows_cap * 64, h->bytes_act);
   ALLOC(c.qbuf, (size_t)c.T_cap * md.q_dim, h->bytes_act);
   c.attn_slots_cap = rt.attn_slots; c.attn_chunk = rt.attn_chunk;
-  c.attn_hsplit = md.n_rep >= 4 ? 2 : 1;
+  c.attn_hsplit = 0;                                  // per forward (pick_attn_hsplit); JF_ATTN_HSPLIT fixes it
+  if (const char* eh = getenv("JF_ATTN_HSPLIT")) c.attn_hsplit = std::max(0, std::min(md.n_rep, atoi(eh)));
   ALLOC(c.argmax_keys, (size_t)2 * c.T_cap, h->bytes_act);
   ALLOC(c.xflag, kMaxTP, h->bytes_act);
   ALLOC(c.row_ss, (size_t)c.T_cap * kMaxHTiles, h->bytes_act);
@@ -304,6 +306,17 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     c.fuse_rope = e6 ? atoi(e6) : 1;
     const char* e8 = getenv("JF_DATAFLOW_GD");
     c.dataflow_gd = e8 ? atoi(e8) : 1;
+    if (getenv("JF_DEBUG_HOSTBUF") && h->arena_mode == 2) {
+      int* hb = nullptr;
+      cudaHostAlloc(&hb, 4096 * sizeof(int), cudaHostAllocMapped);
+      memset(hb, 0, 4096 * sizeof(int));
+      int* db = nullptr;
+      cudaHostGetDevicePointer(&db, hb, 0);
+      c.dbg = db;
+      h->dbg_host = hb;
+    }
+    const char* e10 = getenv("JF_ATTN_TC");
+    c.attn_tc = e10 ? atoi(e10) : 0;
     const char* e5 = getenv("JF_FUSE_NORM");
     c.fuse_norm = e5 ? atoi(e5) : 1;
   }
@@ -746,7 +759,18 @@ static int launch_persistent(jf_engine* h, int run_mode, int max_forwards, float
                                          (size_t)smem_total, h->stream));
   ++h->launches;
   JF_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-  JF_CUDA(h, cudaStreamSynchronize(h->stream));
+  {
+    cudaError_t e_ = cudaStreamSynchronize(h->stream);
+    if (e_ != cudaSuccess) {
+      if (h->dbg_host) {
+        fprintf(stderr, "[jf debug] progress words:");
+        for (int i = 0; i < 64; ++i) fprintf(stderr, " %d", h->dbg_host[i]);
+        fprintf(stderr, "\n");
+      }
+      h->err = std::string("cudaStreamSynchronize(h->stream): ") + cudaGetErrorString(e_);
+      return JF_ERR_CUDA;
+    }
+  }
   if (elapsed_ms) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -780,6 +804,13 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
   std::vector<int> row_group(T, -1), row_pos(T, 0);
   std::vector<int2> row_attn(T);
   int units = 0, slots = 0;
+  int base_units = 0;
+  for (int g = 0; g < G; ++g) {
+    const int len = groups[4 * g + 1], ctx = groups[4 * g + 3];
+    if (len >= 1 && ctx >= 0)
+      base_units += md.n_kv * ((ctx + len + c.attn_chunk - 1) / c.attn_chunk) * ((len + kQTokPerUnit - 1) / kQTokPerUnit);
+  }
+  const int hsplit = pick_attn_hsplit(base_units, h->num_ctas, md.n_rep, c.attn_hsplit);
   for (int g = 0; g < G; ++g) {
     Group& gr = hg[g];
     gr.row0 = groups[4 * g]; gr.len = groups[4 * g + 1]; gr.seq = groups[4 * g + 2]; gr.ctx = groups[4 * g + 3];
@@ -788,7 +819,7 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
     gr.nchunks = (gr.ctx + gr.len + c.attn_chunk - 1) / c.attn_chunk;
     gr.qsplit = (gr.len + kQTokPerUnit - 1) / kQTokPerUnit;
     gr.unit0 = units; gr.slot0 = slots;
-    units += md.n_kv * gr.nchunks * gr.qsplit * c.attn_hsplit;
+    units += md.n_kv * gr.nchunks * gr.qsplit * hsplit;
     slots += gr.len * gr.nchunks;
     for (int i = 0; i < gr.len; ++i) {
       if (row_group[gr.row0 + i] != -1) { h->err = "groups overlap"; return JF_ERR_INVALID; }
@@ -803,6 +834,7 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
   memset(&hdr, 0, sizeof(hdr));
   hdr.T = T; hdr.G = G; hdr.done = 0; hdr.n_commit = 0; hdr.n_commit_after = n_commit; hdr.attn_units = units;
   hdr.attn_slots = slots;
+  hdr.attn_hsplit = hsplit;
   hdr.n_lm_tasks = 0;
   for (int r = 0; r < lm_rows; r += kArgmaxRows) {
     if (hdr.n_lm_tasks >= kMaxLmTasks) { h->err = "too many LM rows"; return JF_ERR_CAPACITY; }
@@ -833,6 +865,11 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
   JF_CUDA(h, cudaStreamSynchronize(h->stream));     // the host vectors above go out of scope
   int rc = launch_persistent(h, RUN_PLAN, 1, elapsed_ms);
   if (rc != JF_OK) return rc;
+  {
+    int dev_err = 0;
+    JF_CUDA(h, cudaMemcpy(&dev_err, reinterpret_cast<const uint8_t*>(c.hdr) + offsetof(PlanHdr, error), 4, cudaMemcpyDeviceToHost));
+    if (dev_err != 0) { h->err = "device-side error " + std::to_string(dev_err) + " during the forward"; return JF_ERR_CUDA; }
+  }
   if (greedy) JF_CUDA(h, cudaMemcpy(greedy, c.greedy, (size_t)T * 4, cudaMemcpyDeviceToHost));
   if (logits && lm_rows > 0) JF_CUDA(h, cudaMemcpy(logits, c.logits, (size_t)lm_rows * md.vocab * 4, cudaMemcpyDeviceToHost));
   if (hidden) JF_CUDA(h, cudaMemcpy(hidden, c.hidden, (size_t)T * md.h * 2, cudaMemcpyDeviceToHost));

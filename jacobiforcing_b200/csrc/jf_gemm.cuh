@@ -86,6 +86,7 @@ struct GemmSmem {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad_;
+  uint64_t attn_bar;          // completion of the attention stage's MMAs (tcgen05 attention)
   long long t_acc_full;       // developer aid: clock of the first accumulator hand-over of the last GEMM stage
   unsigned long long* best;   // [4][kArgmaxRows] EPI_ARGMAX running best key per epilogue warp and row (aliases
                               // the attention tile buffer: the LM head never overlaps an attention stage)
@@ -131,6 +132,7 @@ __device__ __forceinline__ void gemm_setup(GemmSmem* gs) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < nstages; ++i) { mbar_init(&gs->full[i], 2); mbar_init(&gs->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&gs->acc_full[i], 1); mbar_init(&gs->acc_empty[i], kWorkerThreads); }
+    mbar_init(&gs->attn_bar, 1);
     fence_mbar_init();
   }
   if (warp == kWarpMMA) tmem_alloc(&gs->tmem_base, 512);
@@ -335,7 +337,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int m = t.x_row0 + m0 + c0 + j;
-            if (nvalid && c0 + j < mlive) out[(size_t)m * t.out_row_stride + n] = __uint_as_float(v[j]);
+            st_pred_f32(out + (size_t)m * t.out_row_stride + n, __uint_as_float(v[j]), nvalid && c0 + j < mlive);
           }
         }
       } else if (t.epilogue == EPI_PARTIAL_TAGGED) {
@@ -349,7 +351,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int m = t.x_row0 + m0 + c0 + j;
-            if (nvalid && c0 + j < mlive) out[(size_t)m * t.out_row_stride + n] = tg | (unsigned long long)v[j];
+            st_pred_u64(out + (size_t)m * t.out_row_stride + n, tg | (unsigned long long)v[j], nvalid && c0 + j < mlive);
           }
         }
       } else if (t.epilogue == EPI_SWIGLU_TAGGED) {
@@ -365,10 +367,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int m = t.x_row0 + m0 + c0 + j;
-            if (nvalid && c0 + j < mlive) {
-              out[(size_t)m * t.out_row_stride + n] = tg | (unsigned long long)g[j];
-              out[(size_t)m * t.out_row_stride + t.N + n] = tg | (unsigned long long)up[j];
-            }
+            const bool live = nvalid && c0 + j < mlive;
+            st_pred_u64(out + (size_t)m * t.out_row_stride + n, tg | (unsigned long long)g[j], live);
+            st_pred_u64(out + (size_t)m * t.out_row_stride + t.N + n, tg | (unsigned long long)up[j], live);
           }
         }
       } else if (t.epilogue == EPI_SWIGLU_BF16) {
@@ -386,13 +387,12 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int m = t.x_row0 + m0 + c0 + j;
-            if (nvalid && c0 + j < mlive) {
-              const float gf = bf16_round(__uint_as_float(g[j]));
-              const float uf = bf16_round(__uint_as_float(up[j]));
-              const float s = bf16_round(gf / (1.f + __expf(-gf)));
-              *reinterpret_cast<__nv_bfloat16*>(dst + ((size_t)kc * t.out_rows_cap) * 128 + sw128_offset(m, c)) =
-                  __float2bfloat16_rn(s * uf);
-            }
+            const float gf = bf16_round(__uint_as_float(g[j]));
+            const float uf = bf16_round(__uint_as_float(up[j]));
+            const float s = bf16_round(gf / (1.f + __expf(-gf)));
+            const __nv_bfloat16 ob = __float2bfloat16_rn(s * uf);
+            st_pred_u16(dst + ((size_t)kc * t.out_rows_cap) * 128 + sw128_offset(m, c), *reinterpret_cast<const unsigned short*>(&ob),
+                        nvalid && c0 + j < mlive);
           }
         }
       } else if (t.epilogue == EPI_SAMPLE) {

@@ -181,6 +181,13 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
     const int iter_done = first ? 0 : ld_weak(&hdr->iter) + 1;
     int T = 0, G = 0, nc = 0, units = 0, slots = 0, err = 0;
     const int CH = c.attn_chunk;
+    int base_units = 0;
+    for (int s = 0; s < c.n_seqs; ++s) {
+      const SeqState& st = c.seq_state[s];
+      if (!c.seq_slot[s].active || iter_done >= max_forwards) continue;
+      base_units += st.B_out * c.md.n_kv * ((st.ctx + st.L_out + CH - 1) / CH) * ((st.L_out + kQTokPerUnit - 1) / kQTokPerUnit);
+    }
+    const int hsplit = pick_attn_hsplit(base_units, (int)gridDim.x, c.md.n_rep, c.attn_hsplit);
     for (int s = 0; s < c.n_seqs; ++s) {
       SeqState& st = c.seq_state[s];
       SeqSlot& sl = c.seq_slot[s];
@@ -208,7 +215,7 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
         Group& g = c.groups[G];
         g.row0 = T + i * L; g.len = L; g.seq = s; g.ctx = st.ctx;
         g.nchunks = nchunks; g.qsplit = qsplit; g.unit0 = units; g.slot0 = slots;
-        units += c.md.n_kv * nchunks * qsplit * c.attn_hsplit;
+        units += c.md.n_kv * nchunks * qsplit * hsplit;
         slots += L * nchunks;
         ++G;
       }
@@ -224,7 +231,7 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
       T += B * L;
     }
     hdr->rows_total = (first ? 0 : ld_weak(&hdr->rows_total)) + T;
-    hdr->T = T; hdr->G = G; hdr->n_commit = nc; hdr->attn_units = units; hdr->attn_slots = slots;
+    hdr->T = T; hdr->G = G; hdr->n_commit = nc; hdr->attn_units = units; hdr->attn_slots = slots; hdr->attn_hsplit = hsplit;
     hdr->iter = iter_done;
     hdr->want_logits = 0;
     if (err) hdr->error = err;
@@ -266,7 +273,7 @@ enum StageId : int { SID_NONE = 0, SID_EMBED = 1, SID_QKV = 2, SID_ROPE = 3, SID
                      SID_O_FUSED = 13, SID_DOWN_FUSED = 14, SID_QKV_FUSED = 15, SID_GU_DOWN_FUSED = 16 };
 
 struct IterPlan {
-  int T, G, done, n_commit, attn_units, n_lm, want_logits;
+  int T, G, done, n_commit, attn_units, n_lm, want_logits, hsplit;
 };
 
 template <int ROLE>
@@ -374,6 +381,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     ip.T = ld_weak(&hdr->T); ip.G = ld_weak(&hdr->G); ip.done = ld_weak(&hdr->done);
     ip.n_commit = ld_weak(&hdr->n_commit); ip.attn_units = ld_weak(&hdr->attn_units);
     ip.n_lm = ld_weak(&hdr->n_lm_tasks); ip.want_logits = ld_weak(&hdr->want_logits);
+    ip.hsplit = max(1, ld_weak(&hdr->attn_hsplit));
     if (ip.done) {
       if (ROLE == ROLE_WORKER) {
         if (prof_slot != nullptr && w.wtid == 0) {
@@ -508,14 +516,14 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
 
     for (int l = 0; l < md.layers; ++l) {
       const LayerW& lw = c.layer[l];
-      if (ROLE == ROLE_WORKER) attention_prefetch(c, ws, l, ip.G, ip.attn_units);
+      if (ROLE == ROLE_WORKER) attention_prefetch(c, ws, l, ip.G, ip.attn_units, ip.hsplit);
       if (fuse_q) {
         gemm_stage(task_qkv(l, true), true, SID_QKV_FUSED, false, 3, nullptr, l);
       } else {
         gemm_stage(task_qkv(l), true, SID_QKV);
         JF_SIMT_STAGE_X(false, SID_ROPE, if (!(c.debug_skip & 1)) stage_qkv_rope(c, ws, T, l));
       }
-      JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) stage_attention(c, ws, l, ip.G, ip.attn_units));
+      JF_SIMT_STAGE_X(false, SID_ATTN, if (!(c.debug_skip & 2)) stage_attention(c, ws, l, ip.G, ip.attn_units, ip.hsplit));
       JF_SIMT_STAGE(SID_COMBINE, if (!(c.debug_skip & 4)) stage_attn_combine(c, ws, T));
       if (fuse_o) {
         gemm_stage(task_o(l, true), true, SID_O_FUSED, false, 1, lw.ln2);
@@ -594,7 +602,10 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   static_assert(sizeof(WorkerShared) <= 24 * sizeof(float), "WorkerShared must fit red[8..31]");
   WorkerShared* ws = reinterpret_cast<WorkerShared*>(red + 8);      // red[8..31]
-  if (threadIdx.x == 0) { ws->red = red; ws->attn_smem = attn; ws->prof_on = 0; ws->tag = 0u; ws->plan = plan; ws->plan_ok = 0; }
+  if (threadIdx.x == 0) {
+    ws->red = red; ws->attn_smem = attn; ws->prof_on = 0; ws->tag = 0u; ws->plan = plan; ws->plan_ok = 0;
+    ws->tmem_base = gs->tmem_base; ws->attn_phase = 0u; ws->attn_bar = &gs->attn_bar;
+  }
   __syncthreads();
 
   if (warp == kWarpW) {

@@ -46,6 +46,9 @@ struct WorkerShared {
   unsigned int tag;
   PlanCache* plan;     // shared-memory plan cache
   int plan_ok;         // 1: the forward in flight fits the cache and it is filled
+  uint32_t tmem_base;  // tensor memory of the CTA (free between the GEMM stages: the attention stage borrows it)
+  uint32_t attn_phase; // parity of the attention MMA barrier
+  uint64_t* attn_bar;
 };
 __device__ __forceinline__ WorkerCtx load_wctx(const WorkerShared* ws) {
   WorkerCtx w;
@@ -712,7 +715,7 @@ __device__ __noinline__ void qkv_rope_tail(const DevCtx& c, const WorkerShared* 
 // ---------------------------------------------------------------------------------------------------------------
 template <int D>
 __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx& w, int layer, const Group& grp, int g_kvh, int chunk,
-                               int qs, int hs, bool prefetched) {
+                               int qs, int hs, bool prefetched, int hsplit) {
   constexpr int LDS = D + 8;                  // padded smem row (bf16 elements) -> conflict-free fragment loads
   constexpr int VPR = D / 8;                  // 16-byte chunks per row
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem);
@@ -726,7 +729,7 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
   const int q0 = qs * kQTokPerUnit;
   const int qn = min(kQTokPerUnit, len - q0);
   const int ntt = (qn + 15) >> 4;
-  const int hp = (md.n_rep + c.attn_hsplit - 1) / c.attn_hsplit;      // q heads of this kv head handled by one unit
+  const int hp = (md.n_rep + hsplit - 1) / hsplit;      // q heads of this kv head handled by one unit
   const int j_lo = hs * hp, j_hi = min(md.n_rep, j_lo + hp);
   const int tiles = max(0, j_hi - j_lo) * ntt;
   const int nsub = (key_hi - key_lo + kAttnSub - 1) / kAttnSub;
@@ -939,9 +942,8 @@ __device__ __forceinline__ Group load_group(const DevCtx& c, int g) {
 }
 
 struct AttnUnitId { Group grp; int kvh, hs, chunk, qs; };
-__device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, const WorkerCtx& w, int u, int G) {
+__device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, const WorkerCtx& w, int u, int G, int hsplit) {
   AttnUnitId id;
-  const int hsplit = c.attn_hsplit;
   int g = 0;
   id.grp = w.plan ? w.plan->groups[0] : load_group(c, 0);
   while (g + 1 < G) {                                   // groups are few; linear scan over unit ranges
@@ -958,14 +960,220 @@ __device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, const Wo
   return id;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// tcgen05 attention: the same unit (group, kv head, 64-key chunk, query split, head split) on the 5th-gen tensor cores.
+//   S = Q K^T   A = the unit's (head, query row) pairs, up to 128 per tile, staged in TENSOR MEMORY straight from registers
+//               (lane = pair, 32-bit column j = dims 2j, 2j+1); B = the K chunk in shared memory, K-major SWIZZLE_128B
+//   softmax     one thread per pair reads its 64 scores with tcgen05.ld: scale, causal mask, max, exp, sum - no shuffles
+//   O = P V     A = P (bf16) written back to tensor memory with tcgen05.st; B = the V chunk, the SAME [key][dim] rows in
+//               shared memory read as an MN-major operand (no transposed copy of V anywhere)
+// The accumulators live in the tensor memory the GEMM stages use, idle while this stage runs.  K and V tiles are two
+// 64-dim blocks of [64 keys][128 B] each, 16-byte chunk c of key r at chunk position c ^ (r & 7); they fill the attention
+// buffer of the mma.sync path (1024-byte aligned inside it).  Results are written exactly like the mma.sync path writes them
+// (unnormalised fp32 partial outputs + (max, sum) per pair and chunk), so the combine stage is shared.
+// Rows of a result depend only on that row's query and the chunk's keys, and chunks are aligned to absolute key positions:
+// Jacobi, autoregressive and prefill forwards still agree bit for bit.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kTcQ = 0, kTcS = 64, kTcP = 128, kTcO = 256;     // tensor-memory columns: Q (D/2), S (64), P (32), O (D)
+
+template <int D>
+__device__ __forceinline__ uint32_t tc_kv_base(const WorkerCtx& w) {
+  return (smem_u32(w.attn_smem) + 1023u) & ~1023u;
+}
+// K (kv = 0) / V (kv = 1) tile address of 16-byte chunk `v` (8 dims) of key row `jr`
+template <int D>
+__device__ __forceinline__ uint32_t tc_kv_addr(uint32_t base, int kv, int jr, int v) {
+  constexpr uint32_t kTile = 64u * D * 2u;                               // bytes of one K or V tile
+  return base + (uint32_t)kv * kTile + (uint32_t)(v >> 3) * 8192u + (uint32_t)jr * 128u + (uint32_t)(((v & 7) ^ (jr & 7)) << 4);
+}
+__device__ __forceinline__ void cp_async_16_saddr(uint32_t saddr, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
+#define JF_DBG(slot, val) do { if (c.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) { c.dbg[(int)(threadIdx.x >> 5) * 8 + (slot)] = (val); __threadfence_system(); } } while (0)
+// bounded wait on the attention MMA barrier: a timeout is recorded in the plan header (the host turns it into an error)
+// instead of trapping, so a wrong descriptor shows up as a diagnosable failure rather than a dead context
+__device__ __forceinline__ bool attn_bar_wait(const DevCtx& c, uint64_t* bar, uint32_t phase, int code) {
+  if (mbar_try_wait(bar, phase)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, phase)) {
+    if (clock64() - t0 > 400000000LL) {                      // ~0.2 s
+      if ((threadIdx.x & 31) == 0) atomicMax(&c.hdr->error, code);
+      return false;
+    }
+  }
+  return true;
+}
+
+template <int D>
+__device__ __forceinline__ void attention_unit_tc(const DevCtx& c, const WorkerCtx& w, const WorkerShared* ws, uint32_t& phase,
+                                                  int layer, const Group& grp, int g_kvh, int chunk, int qs, int hs,
+                                                  bool prefetched, int hsplit) {
+  constexpr int VPR = D / 8;                  // 16-byte chunks per K / V row
+  const ModelDims& md = c.md;
+  const int ctx = grp.ctx, len = grp.len, row0 = grp.row0;
+  const int nkeys = ctx + len;
+  const int key_lo = chunk * kAttnSub;
+  const int q0 = qs * kQTokPerUnit;
+  const int qn = min(kQTokPerUnit, len - q0);
+  const int hp = (md.n_rep + hsplit - 1) / hsplit;
+  const int j_lo = hs * hp, j_hi = min(md.n_rep, j_lo + hp);
+  const int nheads = j_hi - j_lo;
+  if (nheads <= 0 || qn <= 0) return;
+  if (key_lo > ctx + q0 + qn - 1) return;                     // no key of this chunk is visible to any query of the unit
+  const int pairs = nheads * qn;
+  const int ntiles = (pairs + 127) >> 7;
+  const uint32_t base = tc_kv_base<D>(w);
+  const uint32_t tm = ws->tmem_base;
+  const int q = (int)(threadIdx.x >> 5) & 3;                 // TMEM lane quarter of this warp
+  const int lane_tm = q * 32 + w.lane;                       // TMEM lane = pair index inside a tile
+  const uint32_t tq = tm + ((uint32_t)(q * 32) << 16);
+  const float scale = rsqrtf((float)D);
+  const int* bt = c.block_tables + (size_t)grp.seq * c.max_pages_per_seq;
+  // K / V chunk -> shared memory (16-byte asynchronous copies; rows past the last key are zero-filled: 0 * P = 0)
+  if (!prefetched) workers_sync();                           // previous readers (MMAs of the previous unit) are done
+  {
+    const __nv_bfloat16* cbase[2] = {nullptr, nullptr};
+    const bool need_committed = key_lo < ctx && !prefetched;
+    if (need_committed) {
+      const int page = ld_weak(bt + (key_lo / kPage));
+      cbase[0] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 0, page, g_kvh, key_lo % kPage);
+      cbase[1] = c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 1, page, g_kvh, key_lo % kPage);
+    }
+    const __nv_bfloat16* sbase[2] = {c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, row0, g_kvh),
+                                     c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, row0, g_kvh)};
+    const size_t srow = (size_t)md.n_kv * D;
+#pragma unroll 4
+    for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
+      const int kv = idx / (kAttnSub * VPR);
+      const int rem = idx - kv * (kAttnSub * VPR);
+      const int jr = rem / VPR, v = rem - jr * VPR;
+      const int pos = key_lo + jr;
+      const __nv_bfloat16* src = sbase[kv];
+      uint32_t nbytes = 0;
+      if (pos < ctx) {
+        if (prefetched) continue;                            // committed rows were fetched during the QKV stage
+        src = cbase[kv] + (size_t)jr * D + v * 8; nbytes = 16;
+      } else if (pos < nkeys) { src = sbase[kv] + (size_t)(pos - ctx) * srow + v * 8; nbytes = 16; }
+      cp_async_16_saddr(tc_kv_addr<D>(base, kv, jr, v), src, nbytes);
+    }
+    cp_async_commit();
+  }
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int p = tile * 128 + lane_tm;                      // this thread's pair
+    const bool pvalid = p < pairs;
+    const int hl = pvalid ? p / qn : 0;
+    const int i = q0 + (pvalid ? p - hl * qn : 0);           // query row inside the group
+    const int head = g_kvh * md.n_rep + j_lo + hl;
+    // queries: registers -> tensor memory (invalid pairs: zeros)
+    {
+      const uint4* qsrc = reinterpret_cast<const uint4*>(c.qbuf + (size_t)(row0 + i) * md.q_dim + (size_t)head * D);
+#pragma unroll
+      for (int c16 = 0; c16 < D / 32; ++c16) {               // 16 columns = 32 dims = 4 x 16 bytes
+        uint32_t v[16];
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          uint4 u = make_uint4(0u, 0u, 0u, 0u);
+          if (pvalid) u = ld_weak(qsrc + c16 * 4 + k4);
+          v[4 * k4] = u.x; v[4 * k4 + 1] = u.y; v[4 * k4 + 2] = u.z; v[4 * k4 + 3] = u.w;
+        }
+        tmem_st16(tq + kTcQ + c16 * 16, v);
+      }
+      tmem_st_wait();
+    }
+    if (tile == 0) cp_async_wait_all();
+    fence_proxy_async_smem();                                // K / V written by this thread's copies -> async proxy (MMA)
+    tc_fence_before();
+    workers_sync();
+    if (w.wtid == 0) {                                       // S = Q K^T : M = 128 pairs, N = 64 keys, K = D dims
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, kAttnSub);
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk)
+        if (!(c.debug_skip & 65536)) umma_bf16_ts(tm + kTcS, tm + kTcQ + kk * 8, umma_desc_sw128(base + (uint32_t)(kk >> 2) * 8192u + (uint32_t)(kk & 3) * 32u),
+                     idesc, kk > 0 ? 1u : 0u);
+      umma_commit(ws->attn_bar);
+    }
+    attn_bar_wait(c, ws->attn_bar, phase, 1001);
+    phase ^= 1u;
+    tc_fence_after();
+    // softmax of this pair's row: 64 scores in registers
+    float m_run = -INFINITY, l_run = 0.f;
+    {
+      uint32_t sv[64];
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) tmem_ld16(tq + kTcS + c16 * 16, *reinterpret_cast<uint32_t(*)[16]>(&sv[c16 * 16]));
+      tmem_ld_wait();
+      const int qpos = ctx + i;
+      const int kvis = min(qpos - key_lo + 1, nkeys - key_lo);      // visible keys of the chunk: columns [0, kvis)
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        const float sc = (k < kvis) ? __uint_as_float(sv[k]) * scale : -INFINITY;
+        sv[k] = __float_as_uint(sc);
+        m_run = fmaxf(m_run, sc);
+      }
+      const float mu = (m_run == -INFINITY) ? 0.f : m_run;
+      uint32_t pk[32];
+#pragma unroll
+      for (int k = 0; k < 64; k += 2) {
+        const float e0 = __expf(__uint_as_float(sv[k]) - mu), e1 = __expf(__uint_as_float(sv[k + 1]) - mu);
+        l_run += e0 + e1;
+        pk[k >> 1] = pack_bf16x2(e0, e1);
+      }
+      tmem_st16(tq + kTcP, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+      tmem_st16(tq + kTcP + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    workers_sync();
+    if (w.wtid == 0) {                                       // O = P V : M = 128 pairs, N = D dims, K = 64 keys
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16_bmn(128, D);
+      constexpr uint32_t kTile = 64u * D * 2u;
+#pragma unroll
+      for (int kk = 0; kk < kAttnSub / 16; ++kk)
+        if (!(c.debug_skip & 131072)) umma_bf16_ts(tm + kTcO, tm + kTcP + kk * 8, umma_desc_sw128_mn(base + kTile + (uint32_t)kk * 2048u, 8192u, 1024u),
+                     idesc, kk > 0 ? 1u : 0u);
+      umma_commit(ws->attn_bar);
+    }
+    attn_bar_wait(c, ws->attn_bar, phase, 1002);
+    phase ^= 1u;
+    tc_fence_after();
+    // unnormalised partial output + (max, sum) of this pair and chunk (tcgen05.ld is warp-collective: every lane loads,
+    // only the lanes that hold a live pair store)
+    {
+      const bool live = pvalid && key_lo <= ctx + i;
+      const size_t sh = live ? ((size_t)(grp.slot0 + i * grp.nchunks + chunk) * md.n_q + head) : 0;
+      float* op = c.attn_o + sh * D;
+#pragma unroll
+      for (int c16 = 0; c16 < D / 16; ++c16) {
+        uint32_t ov[16];
+        tmem_ld16(tq + kTcO + c16 * 16, ov);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            *reinterpret_cast<float4*>(op + c16 * 16 + k4 * 4) =
+                make_float4(__uint_as_float(ov[4 * k4]), __uint_as_float(ov[4 * k4 + 1]), __uint_as_float(ov[4 * k4 + 2]),
+                            __uint_as_float(ov[4 * k4 + 3]));
+        }
+      }
+      if (live) *reinterpret_cast<float2*>(c.attn_ml + sh * 2) = make_float2(m_run, l_run);
+    }
+    tc_fence_before();                                       // the next tile / unit overwrites Q, S, P, O
+    if (tile + 1 < ntiles) workers_sync();
+  }
+}
+
 // Issued by the workers at the START of the layer's QKV GEMM stage: the committed K/V rows of the first 64-key
 // sub-tile of the unit this CTA will run in the attention stage do not depend on this layer's projections, so their
 // HBM latency hides behind the QKV GEMM and the rope stage.  attention_unit(prefetched = true) then only adds the
 // in-flight rows.  (The tile buffer is free: the previous attention stage and LM head ended grid barriers ago.)
-__device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerShared* ws, int layer, int G, int units) {
+__device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerShared* ws, int layer, int G, int units, int hsplit) {
   const WorkerCtx w = load_wctx(ws);
   if (w.cta >= units || !c.attn_prefetch) return;
-  const AttnUnitId id = decode_attn_unit(c, w, w.cta, G);
+  const AttnUnitId id = decode_attn_unit(c, w, w.cta, G, hsplit);
   const ModelDims& md = c.md;
   const int D = md.d, LDS = D + 8, VPR = D >> 3;
   const int ctx = id.grp.ctx;
@@ -977,24 +1185,49 @@ __device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerSha
   const __nv_bfloat16* cbase[2] = {c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 0, page, id.kvh, k0 % kPage),
                                    c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 1, page, id.kvh, k0 % kPage)};
   const int nrow = min(kAttnSub, ctx - k0);
+  const bool tc = c.attn_tc != 0 && c.attn_chunk == kAttnSub;
+  const uint32_t tbase = (smem_u32(w.attn_smem) + 1023u) & ~1023u;
   for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
     const int kv = idx / (kAttnSub * VPR);
     const int rem = idx - kv * (kAttnSub * VPR);
     const int jr = rem / VPR, v = rem - jr * VPR;
-    if (jr < nrow) cp_async_16((kv ? Vs : Ks) + jr * LDS + v * 8, cbase[kv] + (size_t)jr * D + v * 8, 16);
+    if (jr >= nrow) continue;
+    if (tc) {
+      const uint32_t dst = (D == 128) ? tc_kv_addr<128>(tbase, kv, jr, v) : tc_kv_addr<64>(tbase, kv, jr, v);
+      cp_async_16_saddr(dst, cbase[kv] + (size_t)jr * D + v * 8, 16);
+    } else {
+      cp_async_16((kv ? Vs : Ks) + jr * LDS + v * 8, cbase[kv] + (size_t)jr * D + v * 8, 16);
+    }
   }
   cp_async_commit();
 }
 
-__device__ __noinline__ void stage_attention(const DevCtx& c, const WorkerShared* ws, int layer, int G, int units) {
+__device__ __noinline__ void stage_attention_tc(const DevCtx& c, WorkerShared* ws, int layer, int G, int units, int hsplit) {
+  const WorkerCtx w = load_wctx(ws);
+  uint32_t phase = ws->attn_phase;
+  for (int u = w.cta; u < units; u += w.nctas) {
+    prof_mark(c, w, 398);
+    const AttnUnitId id = decode_attn_unit(c, w, u, G, hsplit);
+    const bool pf = c.attn_prefetch && u == w.cta;
+    prof_mark(c, w, 399);
+    if (c.md.d == 128) attention_unit_tc<128>(c, w, ws, phase, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf, hsplit);
+    else attention_unit_tc<64>(c, w, ws, phase, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf, hsplit);
+    prof_mark(c, w, 403);
+  }
+  workers_sync();
+  if (w.wtid == 0) ws->attn_phase = phase;
+}
+
+__device__ __noinline__ void stage_attention(const DevCtx& c, WorkerShared* ws, int layer, int G, int units, int hsplit) {
+  if (c.attn_tc != 0 && c.attn_chunk == kAttnSub) { stage_attention_tc(c, ws, layer, G, units, hsplit); return; }
   const WorkerCtx w = load_wctx(ws);
   for (int u = w.cta; u < units; u += w.nctas) {
     prof_mark(c, w, 398);
-    const AttnUnitId id = decode_attn_unit(c, w, u, G);
+    const AttnUnitId id = decode_attn_unit(c, w, u, G, hsplit);
     const bool pf = c.attn_prefetch && u == w.cta;
     prof_mark(c, w, 399);
-    if (c.md.d == 128) attention_unit<128>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf);
-    else attention_unit<64>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf);
+    if (c.md.d == 128) attention_unit<128>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf, hsplit);
+    else attention_unit<64>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf, hsplit);
   }
 }
 

@@ -68,6 +68,7 @@ struct PlanHdr {
   int want_logits;           // plan mode: also write fp32 logits of LM task 0
   int n_commit_after;        // plan mode: commit entries to apply once the forward is done
   int rows_total;            // sum of T over the forwards of this launch
+  int attn_hsplit;           // attention units per kv head along its q heads, chosen per forward (pick_attn_hsplit)
 };
 
 struct SeqSlot {             // per-sequence bookkeeping owned by the policy stage
@@ -115,7 +116,7 @@ struct alignas(16) DevCtx {
   float* attn_ml;                    // [attn_slots_cap][n_q][2] (running max, running sum)
   int attn_slots_cap;
   int attn_chunk;                    // keys per attention unit (multiple of kAttnSub)
-  int attn_hsplit;                   // attention units per kv head along its q heads (2 when n_rep >= 4)
+  int attn_hsplit;                   // > 0: fixed attention units per kv head along its q heads; 0: chosen per forward
   unsigned long long* argmax_keys;   // [2][T_cap] packed (value, ~index) keys, double-buffered by forward parity
   unsigned long long* row_ss;        // [T_cap][kMaxHTiles] per-tile {stage tag, sum of squares} words of the row being normalised
   unsigned int tag_base;             // stage tag = tag_base + barriers passed + 1: a 32-bit count of all stages this engine
@@ -191,9 +192,22 @@ struct alignas(16) DevCtx {
   int debug_skip;                    // timing experiments only: bit s = skip the body of SIMT stage s (results invalid)
   int w_evict_first;                 // 1: weight tiles are streamed with the L2 evict_first hint (see jf_ptx.cuh)
   int attn_prefetch;                 // 1: committed K/V of each CTA's first attention unit is fetched during the QKV GEMM
+  volatile int* dbg;                 // developer aid: host-mapped progress words (survive a trapped launch)
+  int attn_tc;                       // 1: attention on the tcgen05 tensor cores (TMEM-staged Q / P, MN-major V); 0: mma.sync
 };
 
 enum RunMode : int { RUN_PLAN = 0, RUN_JACOBI = 1 };
+
+// Attention units per kv head along its query heads for a forward whose units number `base_units` without any head split:
+// the stage is latency-bound, so small forwards spread the heads of a kv head over up to four units (more SMs, shorter
+// units) and large ones keep them together (the K / V chunk is loaded once per kv head).  Results do not depend on it.
+__host__ __device__ inline int pick_attn_hsplit(int base_units, int nctas, int n_rep, int fixed) {
+  if (fixed > 0) return fixed < n_rep ? fixed : (n_rep > 0 ? n_rep : 1);
+  const int cap = nctas + nctas / 2;
+  if (n_rep >= 4 && base_units * 4 <= cap) return 4;
+  if (n_rep >= 2 && base_units * 2 <= cap) return 2;
+  return 1;
+}
 
 __host__ __device__ inline size_t kv_cache_offset(const ModelDims& md, int num_pages, int layer, int kv, int page,
                                                   int kvh, int slot) {

@@ -96,8 +96,16 @@ def test_mixed_strategies_and_sampling_rejected(llm):
     for s in list(llm.scheduler.running):
         llm.scheduler.block_manager.deallocate(s)
     reset(llm)
+    # mixed greedy / non-greedy temperatures in one batch (reference: model_runner.py:331-373), and sampling on the plain
+    # autoregressive path (served by the non-greedy Jacobi verify instead)
+    with pytest.raises(NotImplementedError, match="Mixed greedy"):
+        llm.generate(p, [SamplingParams(temperature=0.8, decode_strategy="jacobi", jacobi_block_len=8),
+                         SamplingParams(temperature=0.0, decode_strategy="jacobi", jacobi_block_len=8)], use_tqdm=False)
+    for s in list(llm.scheduler.running):
+        llm.scheduler.block_manager.deallocate(s)
+    reset(llm)
     with pytest.raises(NotImplementedError):
-        llm.generate(p[:1], SamplingParams(temperature=0.8, decode_strategy="jacobi", jacobi_block_len=8), use_tqdm=False)
+        llm.generate(p[:1], SamplingParams(temperature=0.8, decode_strategy="autoregressive"), use_tqdm=False)
     for s in list(llm.scheduler.running):
         llm.scheduler.block_manager.deallocate(s)
     reset(llm)
