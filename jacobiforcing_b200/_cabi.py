@@ -45,11 +45,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("JF_LIB_PATH", LIB_PATH)           # developer aid: A/B an older build of the library
+    if not os.path.exists(path):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64p, i32p, fp = C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_float)
     lib.jf_create.argtypes = [C.POINTER(ModelCfg), C.POINTER(RuntimeCfg), C.POINTER(vp)]
     lib.jf_destroy.argtypes = [vp]
@@ -68,11 +69,12 @@ def load() -> C.CDLL:
     lib.jf_profile_read.argtypes = [vp, i64p, i32, i32p, i32p]
     lib.jf_tp_export.argtypes = [vp, vp]
     lib.jf_tp_import.argtypes = [vp, vp]
-    lib.jf_tp_attach_local.argtypes = [vp, C.POINTER(vp)]
+    if hasattr(lib, "jf_tp_attach_local"):
+        lib.jf_tp_attach_local.argtypes = [vp, C.POINTER(vp)]
     lib.jf_launch_count.argtypes = [vp]
     lib.jf_launch_count.restype = C.c_int64
     for name in EXPORTS:
-        if name not in ("jf_last_error", "jf_launch_count"):
+        if name not in ("jf_last_error", "jf_launch_count") and hasattr(lib, name):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

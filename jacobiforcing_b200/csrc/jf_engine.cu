@@ -804,13 +804,15 @@ extern "C" int jf_forward(jf_handle h, int32_t T, const int32_t* tokens, int32_t
   std::vector<int> row_group(T, -1), row_pos(T, 0);
   std::vector<int2> row_attn(T);
   int units = 0, slots = 0;
-  int base_units = 0;
+  int base_units = 0, max_len = 1;
   for (int g = 0; g < G; ++g) {
     const int len = groups[4 * g + 1], ctx = groups[4 * g + 3];
-    if (len >= 1 && ctx >= 0)
+    if (len >= 1 && ctx >= 0) {
       base_units += md.n_kv * ((ctx + len + c.attn_chunk - 1) / c.attn_chunk) * ((len + kQTokPerUnit - 1) / kQTokPerUnit);
+      max_len = std::max(max_len, len);
+    }
   }
-  const int hsplit = pick_attn_hsplit(base_units, h->num_ctas, md.n_rep, c.attn_hsplit);
+  const int hsplit = pick_attn_hsplit(base_units, h->num_ctas, md.n_rep, max_len, c.attn_hsplit);
   for (int g = 0; g < G; ++g) {
     Group& gr = hg[g];
     gr.row0 = groups[4 * g]; gr.len = groups[4 * g + 1]; gr.seq = groups[4 * g + 2]; gr.ctx = groups[4 * g + 3];

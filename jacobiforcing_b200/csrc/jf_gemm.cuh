@@ -66,17 +66,11 @@ struct GemmTask {
   int out_rows_cap;          // SWIGLU: xrows_cap of the destination packed buffer
   int index_offset;          // ARGMAX: added to the local feature index (vocabulary slice of this rank)
   unsigned int tag;          // PARTIAL_TAGGED: stage tag stored with every partial sum
-  // ---- SAMPLE
-  float inv_temp;            // 1 / temperature
-  unsigned int seed_lo, seed_hi;
+  // ---- SAMPLE: everything else the sampling epilogue needs (temperature, generator key, row tables, accumulators) is read
+  // from the kernel context, so the task stays small (it is rebuilt by every role at every stage)
+  const DevCtx* sample_ctx;
   int fwd;                   // forward index that enters the random counters
-  const int* tok;            // [rows] tokens of the forward in flight: row m verifies tok[m + 1] when both rows belong to
-  const int* row_group;      // the same group
   int rows_total;            // T of the forward
-  float* ng_prop;            // [rows] logit / T of the drafted token (written by the one thread that owns it)
-  unsigned long long* ng_gumbel;   // [rows] packed (logit / T + Gumbel noise, ~index) keys, atomicMax
-  float2* ng_ms;             // [nctas][ms_stride] per-CTA (running max, sum of exp) of logit / T
-  int ms_stride;
 };
 
 struct GemmSmem {
@@ -308,7 +302,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
       ng_msw[q * kNgRows + m] = make_float2(-INFINITY, 0.f);
       if (q == 0) {
         const int r = t.x_row0 + m;
-        ng_prop_tok[m] = (r + 1 < t.rows_total && t.row_group[r + 1] == t.row_group[r]) ? t.tok[r + 1] : -1;
+        ng_prop_tok[m] = (r + 1 < t.rows_total && t.sample_ctx->row_group[r + 1] == t.sample_ctx->row_group[r])
+                             ? t.sample_ctx->tok[r + 1] : -1;
       }
     }
     named_bar_sync(1, kWorkerThreads);           // kBarWorkers: the four epilogue warps read warp 0's drafted-token table
@@ -403,6 +398,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
         // conditioned on != drafted - the residual distribution of the delta proposal (:134-153) - without logits in HBM.
         const bool valid = n < t.N;
         const int vglob = n + t.index_offset;
+        const DevCtx& sc = *t.sample_ctx;
+        const float inv_temp = sc.ng_inv_temp;
+        const unsigned int seed_lo = sc.ng_seed_lo, seed_hi = sc.ng_seed_hi;
+        float* ng_prop = sc.ng_prop;
         for (int c0 = 0; c0 < mpad; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
@@ -413,20 +412,20 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
           for (int j4 = 0; j4 < 16; j4 += 4) {
             const int row4 = t.x_row0 + m0 + c0 + j4;                        // multiple of 4
             const Philox4 rnd = philox4x32_10((unsigned int)vglob, (unsigned int)(row4 >> 2), (unsigned int)t.fwd, RNG_GUMBEL,
-                                              t.seed_lo, t.seed_hi);
+                                              seed_lo, seed_hi);
             const unsigned int rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int j = j4 + jj;
               const int mloc = m0 + c0 + j;
               const float val = bf16_round(__uint_as_float(v[j]));
-              const float sc = val * t.inv_temp;
+              const float scv = val * inv_temp;
               const int prop = (c0 + j < mlive) ? ng_prop_tok[mloc] : -1;
-              if (valid && c0 + j < mlive && vglob == prop) t.ng_prop[t.x_row0 + mloc] = sc;
+              if (valid && c0 + j < mlive && vglob == prop) ng_prop[t.x_row0 + mloc] = scv;
               unsigned long long ka = valid ? argmax_key(val, vglob) : 0ull;
               const float gum = -__logf(-__logf(u01_open(rw[jj])));
-              unsigned long long kg = (valid && vglob != prop) ? argmax_key(sc + gum, vglob) : 0ull;
-              float mx = valid ? sc : -INFINITY;
+              unsigned long long kg = (valid && vglob != prop) ? argmax_key(scv + gum, vglob) : 0ull;
+              float mx = valid ? scv : -INFINITY;
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) {
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -435,7 +434,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
                 ka = oa > ka ? oa : ka;
                 kg = og > kg ? og : kg;
               }
-              float ex = valid ? __expf(sc - mx) : 0.f;
+              float ex = valid ? __expf(scv - mx) : 0.f;
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
               if (lane == j) { mine_a = ka; mine_g = kg; mine_m = mx; mine_s = ex; }
@@ -496,7 +495,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
     for (int m = lane; m < t.M; m += 32) {
       const unsigned long long ka = ng_best[q * kNgRows + m], kg = ng_gbest[q * kNgRows + m];
       if (ka != 0ull) atomicMax(&keys[t.x_row0 + m], ka);
-      if (kg != 0ull) atomicMax(&t.ng_gumbel[t.x_row0 + m], kg);
+      if (kg != 0ull) atomicMax(&t.sample_ctx->ng_gumbel[t.x_row0 + m], kg);
     }
     named_bar_sync(1, kWorkerThreads);           // every epilogue warp's (max, sum) pairs are final
     if (cta < units)
@@ -508,7 +507,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
           const float nm = fmaxf(acc.x, o.x);
           if (nm > -INFINITY) acc = make_float2(nm, acc.y * __expf(acc.x - nm) + o.y * __expf(o.x - nm));
         }
-        t.ng_ms[(size_t)cta * t.ms_stride + t.x_row0 + m] = acc;
+        t.sample_ctx->ng_ms[(size_t)cta * t.sample_ctx->T_cap + t.x_row0 + m] = acc;
       }
     named_bar_sync(1, kWorkerThreads);           // before a following task re-initialises the tables
   }

@@ -181,13 +181,14 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
     const int iter_done = first ? 0 : ld_weak(&hdr->iter) + 1;
     int T = 0, G = 0, nc = 0, units = 0, slots = 0, err = 0;
     const int CH = c.attn_chunk;
-    int base_units = 0;
+    int base_units = 0, max_len = 1;
     for (int s = 0; s < c.n_seqs; ++s) {
       const SeqState& st = c.seq_state[s];
       if (!c.seq_slot[s].active || iter_done >= max_forwards) continue;
       base_units += st.B_out * c.md.n_kv * ((st.ctx + st.L_out + CH - 1) / CH) * ((st.L_out + kQTokPerUnit - 1) / kQTokPerUnit);
+      max_len = max(max_len, st.L_out);
     }
-    const int hsplit = pick_attn_hsplit(base_units, (int)gridDim.x, c.md.n_rep, c.attn_hsplit);
+    const int hsplit = pick_attn_hsplit(base_units, (int)gridDim.x, c.md.n_rep, max_len, c.attn_hsplit);
     for (int s = 0; s < c.n_seqs; ++s) {
       SeqState& st = c.seq_state[s];
       SeqSlot& sl = c.seq_slot[s];
@@ -506,10 +507,9 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       t.N = md.vocab; t.epilogue = EPI_ARGMAX;
       if (c.ng_mode && run_mode == RUN_JACOBI) {
         t.epilogue = EPI_SAMPLE;
-        t.inv_temp = c.ng_inv_temp; t.seed_lo = c.ng_seed_lo; t.seed_hi = c.ng_seed_hi;
+        t.sample_ctx = &c;
         t.fwd = ld_weak(&hdr->iter) + c.ng_rng_offset;
-        t.tok = c.tok; t.row_group = c.row_group; t.rows_total = T;
-        t.ng_prop = c.ng_prop; t.ng_gumbel = c.ng_gumbel; t.ng_ms = c.ng_ms; t.ms_stride = c.T_cap;
+        t.rows_total = T;
       }
       return t;
     };

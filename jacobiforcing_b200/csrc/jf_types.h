@@ -198,15 +198,24 @@ struct alignas(16) DevCtx {
 
 enum RunMode : int { RUN_PLAN = 0, RUN_JACOBI = 1 };
 
-// Attention units per kv head along its query heads for a forward whose units number `base_units` without any head split:
-// the stage is latency-bound, so small forwards spread the heads of a kv head over up to four units (more SMs, shorter
-// units) and large ones keep them together (the K / V chunk is loaded once per kv head).  Results do not depend on it.
-__host__ __device__ inline int pick_attn_hsplit(int base_units, int nctas, int n_rep, int fixed) {
+// Attention units per kv head along its query heads for a forward whose units number `base_units` without any head split
+// and whose longest group has `max_len` rows.  The stage is latency-bound: a CTA pays a fixed cost per unit (K / V fill,
+// query loads, partial stores: ~3 us) plus ~3 us per round of four 16-row tiles (one per worker warp), and the stage lasts
+// as long as its busiest CTA.  The split that minimises waves x (fixed + rounds) wins; measured (profiles/
+// r02_attention_hsplit.txt): one sequence of 32 rows at 9 key chunks -> 4 (144 single-round units), at 13 chunks -> 2,
+// eight sequences -> 1.  Results do not depend on the split (a row's partial results are computed identically).
+__host__ __device__ inline int pick_attn_hsplit(int base_units, int nctas, int n_rep, int max_len, int fixed) {
   if (fixed > 0) return fixed < n_rep ? fixed : (n_rep > 0 ? n_rep : 1);
-  const int cap = nctas + nctas / 2;
-  if (n_rep >= 4 && base_units * 4 <= cap) return 4;
-  if (n_rep >= 2 && base_units * 2 <= cap) return 2;
-  return 1;
+  const int row_tiles = ((max_len < kQTokPerUnit ? max_len : kQTokPerUnit) + 15) >> 4;
+  int best = 1, best_cost = 1 << 30;
+  for (int hs = 1; hs <= 4 && hs <= n_rep; hs <<= 1) {
+    const int hp = (n_rep + hs - 1) / hs;
+    const int waves = (base_units * hs + nctas - 1) / nctas;
+    const int rounds = (hp * row_tiles + 3) >> 2;
+    const int cost = waves * (3 + 3 * rounds);
+    if (cost < best_cost) { best_cost = cost; best = hs; }
+  }
+  return best;
 }
 
 __host__ __device__ inline size_t kv_cache_offset(const ModelDims& md, int num_pages, int layer, int kv, int page,
