@@ -41,6 +41,9 @@ class Config:
                                                            # every rank: one exchange per block, any tp in {2,4,8});
                                                            # None: shard when the heads divide, else replicate
 
+    tp_devices: Any = None                                 # CUDA device of every rank when the ranks are threads of this
+                                                           # process (default: rank r -> device r mod device count)
+
     def __post_init__(self):
         self.model = _resolve_checkpoint_dir(self.model)
         if self.kvcache_block_size % 256:

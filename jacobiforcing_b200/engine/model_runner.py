@@ -50,17 +50,22 @@ class ModelRunner:
         self.rank = rank
         self.world_size = config.tensor_parallel_size
         tp_group = None
+        threaded = False
         if config.tensor_parallel_size > 1:
-            # SPMD instead of the reference's spawned workers + SHM RPC (engine/llm_engine.py:31-44, model_runner.py:
-            # 423-458): every rank is started by the launcher (torchrun, one process per GPU), builds the same engine
-            # and makes the same calls; the ranks only meet inside the kernel, over NVLink peer memory.
+            # Two ways to run the ranks (reference: spawned workers + SHM RPC, engine/llm_engine.py:31-44,
+            # model_runner.py:423-458).  Under a launcher (torchrun, one process per GPU, torch.distributed initialised)
+            # every process builds the same engine and makes the same calls (SPMD).  From a plain script the ranks are
+            # host threads of THIS process, one per GPU (runtime.ThreadedTensorParallel).  Either way the ranks only meet
+            # inside the kernel, over NVLink peer memory.
             import torch.distributed as dist
-            if not dist.is_initialized() or dist.get_world_size() != config.tensor_parallel_size:
-                raise RuntimeError("tensor_parallel_size > 1 needs torch.distributed initialised with one process per "
-                                   "GPU (world_size == tensor_parallel_size); launch with torchrun")
-            self.rank = dist.get_rank()
-            config.device = self.rank
-            tp_group = dist.group.WORLD
+            if dist.is_available() and dist.is_initialized():
+                if dist.get_world_size() != config.tensor_parallel_size:
+                    raise RuntimeError("torch.distributed world size != tensor_parallel_size")
+                self.rank = dist.get_rank()
+                config.device = self.rank
+                tp_group = dist.group.WORLD
+            else:
+                threaded = True
         hf = config.hf_config
         self.block_size = config.kvcache_block_size
         assert self.block_size == PAGE, "the device KV cache uses 256-token pages"
@@ -70,12 +75,15 @@ class ModelRunner:
             config.num_kvcache_blocks = self._size_kv_cache(hf, config)
         max_seqs = min(config.max_num_seqs, 64)
         rows = max(min(config.max_num_batched_tokens, 2048), 64)
-        self.rt = JacobiRuntime(hf, device=config.device, max_rows=rows, max_seqs=max_seqs,
-                                num_kv_pages=config.num_kvcache_blocks, max_pages_per_seq=self.max_pages_per_seq,
-                                gen_capacity=config.max_model_len + 1024 + 64, max_calls=1024,
-                                trace_capacity=1 << 20, tp_rank=(self.rank if self.world_size > 1 else 0),
-                                tp_size=self.world_size, tp_group=tp_group,
-                                tp_shard_attention=config.tp_shard_attention)
+        kw = dict(max_rows=rows, max_seqs=max_seqs, num_kv_pages=config.num_kvcache_blocks,
+                  max_pages_per_seq=self.max_pages_per_seq, gen_capacity=config.max_model_len + 1024 + 64, max_calls=1024,
+                  trace_capacity=1 << 20, tp_shard_attention=config.tp_shard_attention)
+        if threaded:
+            from ..runtime import ThreadedTensorParallel
+            self.rt = ThreadedTensorParallel(hf, self.world_size, devices=config.tp_devices, **kw)
+        else:
+            self.rt = JacobiRuntime(hf, device=config.device, tp_rank=(self.rank if self.world_size > 1 else 0),
+                                    tp_size=self.world_size, tp_group=tp_group, **kw)
         self.rt.free_pages = []                            # pages are owned by the scheduler's BlockManager
         if config.state_dict is not None:
             self.rt.load_state_dict(config.state_dict)

@@ -418,3 +418,125 @@ def hf_generate(rt: JacobiRuntime, prompts: Sequence[Sequence[int]], *, n: int, 
     results, run = rt.jacobi_run(seqs, knobs, fcs, fcts, rng_states=chs, want_trace=want_trace)
     run["prefill_ms"] = prefill_ms
     return seqs, results, run
+
+
+class ThreadedTensorParallel:
+    """tensor_parallel_size ranks inside ONE process: one JacobiRuntime per rank, each driven by its own host thread (the
+    launches must overlap: the ranks meet inside the kernels), wired with tp.LocalTPGroup / jf_tp_attach_local.  What the
+    reference gets by spawning worker processes behind `LLM(..., tensor_parallel_size=N)` (engine/llm_engine.py:31-44,
+    model_runner.py:423-458) - a plain script, no torchrun.  `devices[r]` is rank r's CUDA device; ranks may share a device
+    (its SMs are then divided between them), which is how the single-GPU tests cover this class.
+
+    The object has the JacobiRuntime surface the engine uses; every call is collective (fanned out to all ranks) and
+    returns rank 0's result.  Host bookkeeping objects (SeqHandle) passed in are mutated by rank 0 only: the other ranks
+    work on copies."""
+
+    def __init__(self, hf_config, tp_size: int, devices: Optional[Sequence[int]] = None, **kw):
+        import copy
+        from concurrent.futures import ThreadPoolExecutor
+        import torch
+        self._copy = copy
+        self.tp_size = tp_size
+        _cabi.load()                                             # once, before the rank threads race for it
+        ndev = torch.cuda.device_count()
+        devices = list(devices) if devices is not None else [r % max(1, ndev) for r in range(tp_size)]
+        sharing = max(devices.count(d) for d in set(devices))
+        if sharing > 1 and not kw.get("num_ctas"):
+            sms = torch.cuda.get_device_properties(devices[0]).multi_processor_count
+            kw["num_ctas"] = (sms - 4) // sharing                 # co-resident persistent kernels
+        self.group = LocalTPGroup(tp_size)
+        self._pool = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"jf-tp{r}") for r in range(tp_size)]
+        futs = [self._pool[r].submit(JacobiRuntime, hf_config, device=devices[r], tp_rank=r, tp_size=tp_size,
+                                     tp_group=self.group, **kw) for r in range(tp_size)]
+        self.ranks: List[JacobiRuntime] = [f.result() for f in futs]
+        r0 = self.ranks[0]
+        self.vocab, self.hidden, self.max_rows, self.max_seqs = r0.vocab, r0.hidden, r0.max_rows, r0.max_seqs
+        self.max_pages_per_seq, self.max_calls, self.trace_capacity = r0.max_pages_per_seq, r0.max_calls, r0.trace_capacity
+        self.tp_shard_attention = r0.tp_shard_attention
+
+    def _all(self, method: str, *args, **kwargs):
+        def call(r):
+            a, k = (args, kwargs) if r == 0 else self._copy.deepcopy((args, kwargs))
+            return getattr(self.ranks[r], method)(*a, **k)
+        futs = [self._pool[r].submit(call, r) for r in range(self.tp_size)]
+        errs, out = [], None
+        for r, f in enumerate(futs):
+            try:
+                res = f.result()
+                if r == 0:
+                    out = res
+            except BaseException as e:       # noqa: BLE001 - collect, keep joining: a dead rank must not strand its peers
+                errs.append(e)
+                try:
+                    self.group._barrier.abort()
+                except Exception:
+                    pass
+        if errs:
+            raise errs[0]
+        return out
+
+    # ---- the JacobiRuntime surface -------------------------------------------------------------------------------
+    def load_tensor(self, name, t):
+        def call(r):
+            return self.ranks[r].load_tensor(name, t)            # every rank narrows the same tensor to its shard
+        for f in [self._pool[r].submit(call, r) for r in range(self.tp_size)]:
+            f.result()
+
+    def load_state_dict(self, sd):
+        for name, t in sd.items():
+            if not name.endswith("rotary_emb.inv_freq"):
+                self.load_tensor(name, t)
+        self.finalize()
+
+    def finalize(self):
+        return self._all("finalize")
+
+    def set_rope_tables(self, cos, sin):
+        return self._all("set_rope_tables", cos, sin)
+
+    def prefill(self, seq, prompt, draft):
+        return self._all("prefill", seq, prompt, draft)
+
+    def forward(self, *a, **k):
+        return self._all("forward", *a, **k)
+
+    def commit_rows(self, *a, **k):
+        return self._all("commit_rows", *a, **k)
+
+    def jacobi_run(self, *a, **k):
+        return self._all("jacobi_run", *a, **k)
+
+    def new_sequence(self):
+        return self.ranks[0].new_sequence()
+
+    def ensure_capacity(self, seq, n_tokens):
+        return self.ranks[0].ensure_capacity(seq, n_tokens)
+
+    def release(self, seq):
+        return self.ranks[0].release(seq)
+
+    @property
+    def free_pages(self):
+        return self.ranks[0].free_pages
+
+    @free_pages.setter
+    def free_pages(self, v):
+        for rt in self.ranks:
+            rt.free_pages = list(v)
+
+    @property
+    def stats(self):
+        return self.ranks[0].stats
+
+    @property
+    def launches(self) -> int:
+        return sum(rt.launches for rt in self.ranks)
+
+    def device_info(self):
+        return self.ranks[0].device_info()
+
+    def close(self):
+        for r, rt in enumerate(self.ranks):
+            self._pool[r].submit(rt.close).result()
+        for p in self._pool:
+            p.shutdown(wait=True)

@@ -135,3 +135,43 @@ def test_virtual_ranks_match_oracle_and_single_engine(model_name, tp, shard_attn
         lg = teacher_forced_logits(model, r0["prompt"] + one[:same])[-1]
         t2 = lg.topk(2).values
         assert float(t2[0] - t2[1]) < NEAR_TIE
+
+
+@pytest.mark.parametrize("tp", [2, 4])
+def test_llm_tensor_parallel_from_a_plain_process(tp):
+    """`LLM(..., tensor_parallel_size=N)` without a launcher: the ranks are threads of this process
+    (runtime.ThreadedTensorParallel; here they share one GPU).  Jacobi == autoregressive on the sharded engine, and both
+    equal the single-engine output up to near-ties of the oracle."""
+    from jacobiforcing_b200 import LLM, SamplingParams
+    from oracle.hf_model import build_model, state_dict_bf16, teacher_forced_logits
+    model = build_model("tiny", seed=0, dtype=torch.float32)
+    sd = state_dict_bf16(model)
+    with torch.no_grad():
+        for k, v in model.state_dict().items():
+            v.copy_(v.to(torch.bfloat16).to(torch.float32))
+    g = torch.Generator().manual_seed(0)
+    prompts = [torch.randint(0, 1000, (16 + 5 * i,), generator=g).tolist() for i in range(3)]
+    kw = dict(hf_config=model.config, state_dict=sd, max_model_len=2048, num_kvcache_blocks=64, max_num_seqs=8,
+              max_num_batched_tokens=2048, draft_seed=7)
+
+    def run(tp_size):
+        extra = dict(tensor_parallel_size=tp_size, tp_devices=[0] * tp_size) if tp_size > 1 else {}
+        llm = LLM(None, **kw, **extra)
+        llm.config.eos, llm.config.pad = -1, 0
+        llm.scheduler.eos = -1
+        try:
+            ar = llm.generate(prompts, SamplingParams(temperature=0.0, max_tokens=40, decode_strategy="autoregressive"),
+                              use_tqdm=False)
+            jc = llm.generate(prompts, SamplingParams(temperature=0.0, max_tokens=40, decode_strategy="jacobi",
+                                                      jacobi_block_len=8), use_tqdm=False)
+            return [a["token_ids"][:40] for a in ar], [j["token_ids"][:40] for j in jc]
+        finally:
+            llm.exit()
+    ar_tp, jc_tp = run(tp)
+    assert ar_tp == jc_tp
+    ar_1, _ = run(1)
+    for p, a, b in zip(prompts, ar_tp, ar_1):
+        same = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), 40)
+        if same < 40:
+            t2 = teacher_forced_logits(model, p + b[:same])[-1].topk(2).values
+            assert float(t2[0] - t2[1]) < NEAR_TIE
