@@ -431,7 +431,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="qwen2.5-coder-7b", choices=sorted(SHAPES))
     ap.add_argument("--mode", default="single", choices=["single", "multiblock"])
-    ap.add_argument("--n", type=int, default=32)
+    ap.add_argument("--n", "--block-size", dest="n", type=int, default=32,
+                    help="Jacobi block size (under torchrun spell it --block-size: the launcher's parser claims --n)")
     ap.add_argument("--K", type=int, default=2)
     ap.add_argument("--r", type=float, default=0.85)
     ap.add_argument("--pool", type=int, default=4)

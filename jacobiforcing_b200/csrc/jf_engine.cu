@@ -15,7 +15,7 @@
 using namespace jf;
 
 static_assert(sizeof(jf_policy_knobs) == sizeof(PolicyKnobs), "jf_policy_knobs must mirror jf::PolicyKnobs");
-static_assert(sizeof(DevCtx) % 16 == 0 && sizeof(DevCtx) <= 4992, "DevCtx is staged in shared memory");
+static_assert(sizeof(DevCtx) % 16 == 0 && sizeof(DevCtx) <= 5120, "DevCtx is staged in shared memory");
 
 static thread_local std::string g_create_error;
 
@@ -320,11 +320,12 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     const char* e5 = getenv("JF_FUSE_NORM");
     c.fuse_norm = e5 ? atoi(e5) : 1;
   }
-  ALLOC(c.ng_prop, c.T_cap, h->bytes_act);
-  ALLOC(c.ng_gumbel, c.T_cap, h->bytes_act);
+  ALLOC(c.ng_prop, (size_t)2 * c.T_cap, h->bytes_act);
+  ALLOC(c.ng_gumbel, (size_t)2 * c.T_cap, h->bytes_act);
   ALLOC(c.ng_px, c.T_cap, h->bytes_act);
   ALLOC(c.ng_bonus, c.T_cap, h->bytes_act);
-  ALLOC(c.ng_ms, (size_t)h->num_ctas * c.T_cap, h->bytes_act);
+  c.ng_parts = std::min(h->num_ctas, nt_v);
+  ALLOC(c.ng_ms, (size_t)2 * c.ng_parts * c.T_cap, h->bytes_act);
   ALLOC(c.seq_state, c.S_cap, h->bytes_act);
   ALLOC(c.seq_slot, c.S_cap, h->bytes_act);
   ALLOC(c.knobs, c.S_cap, h->bytes_act);
@@ -379,7 +380,9 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
   h->arena_mode = 2;
   if ((rc = layout()) != JF_OK) return fail(rc, h->err);
   h->arena_mode = 0;
+  c.arena_self = h->arena_base[2];
   for (int r2 = 0; r2 < kMaxTP; ++r2) {            // until jf_tp_import: every 'peer' is this rank itself
+    c.peer_arena[r2] = h->arena_base[2];
     for (int b = 0; b < 3; ++b) c.peer_part_rs[r2][b] = c.part_rs[b];
     c.push_buf[r2] = c.push_buf[tpr]; c.stage_buf[r2] = c.stage_buf[tpr];
     c.peer_keys[r2] = c.argmax_keys; c.peer_xflag[r2] = c.xflag;
@@ -437,6 +440,7 @@ static void map_peer(jf_engine* h, int r, uint8_t* base) {
   DevCtx& c = h->hctx;
   const uint8_t* mine = h->arena_base[2];
   auto at = [&](const void* own) { return base + (reinterpret_cast<const uint8_t*>(own) - mine); };
+  c.peer_arena[r] = base;
   for (int b = 0; b < 3; ++b) c.peer_part_rs[r][b] = reinterpret_cast<const float*>(at(c.part_rs[b]));
   c.push_buf[r] = reinterpret_cast<unsigned long long*>(at(c.push_buf[c.tp_rank]));
   c.stage_buf[r] = reinterpret_cast<unsigned long long*>(at(c.stage_buf[c.tp_rank]));
@@ -921,7 +925,6 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
   if (kn.mode == MODE_ENGINE_NG) {
     memcpy(&ng_temp, &kn.temp_bits, 4);
     if (!(ng_temp > 0.f) || !std::isfinite(ng_temp)) { h->err = "non-greedy Jacobi needs a finite temperature > 0"; return JF_ERR_INVALID; }
-    if (c.tp_size > 1) { h->err = "non-greedy Jacobi is not available under tensor parallelism on this build"; return JF_ERR_UNSUPPORTED; }
   }
   if (kn.mode == MODE_HF_MULTI && (kn.K < 1 || kn.K > 2)) { h->err = "device multiblock policy supports K in {1, 2}"; return JF_ERR_UNSUPPORTED; }
   if (kn.pool_size < 0 || kn.pool_size > kPoolMax) { h->err = "n_gram_pool_size outside [0, 16]"; return JF_ERR_INVALID; }
@@ -1005,9 +1008,9 @@ extern "C" int jf_jacobi_run(jf_handle h, int32_t n_seqs, const jf_policy_knobs*
       TRYC(cudaMemcpyAsync(h->dctx, &h->hctx, sizeof(DevCtx), cudaMemcpyHostToDevice, h->stream));
     }
     if (ng) {           // accumulators of the sampling epilogue start clean (the policy stage re-arms them after every forward)
-      std::vector<float> ninf(c.T_cap, -INFINITY);
-      TRYC(cudaMemcpyAsync(c.ng_prop, ninf.data(), (size_t)c.T_cap * 4, cudaMemcpyHostToDevice, h->stream));
-      TRYC(cudaMemsetAsync(c.ng_gumbel, 0, (size_t)c.T_cap * 8, h->stream));
+      std::vector<float> ninf((size_t)2 * c.T_cap, -INFINITY);
+      TRYC(cudaMemcpyAsync(c.ng_prop, ninf.data(), (size_t)2 * c.T_cap * 4, cudaMemcpyHostToDevice, h->stream));
+      TRYC(cudaMemsetAsync(c.ng_gumbel, 0, (size_t)2 * c.T_cap * 8, h->stream));
       TRYC(cudaStreamSynchronize(h->stream));
     }
   }

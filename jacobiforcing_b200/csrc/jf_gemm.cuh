@@ -70,6 +70,7 @@ struct GemmTask {
   // from the kernel context, so the task stays small (it is rebuilt by every role at every stage)
   const DevCtx* sample_ctx;
   int fwd;                   // forward index that enters the random counters
+  int fwd_parity;            // which half of the double-buffered accumulators this forward fills
   int rows_total;            // T of the forward
 };
 
@@ -401,7 +402,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
         const DevCtx& sc = *t.sample_ctx;
         const float inv_temp = sc.ng_inv_temp;
         const unsigned int seed_lo = sc.ng_seed_lo, seed_hi = sc.ng_seed_hi;
-        float* ng_prop = sc.ng_prop;
+        float* ng_prop = sc.ng_prop + (size_t)(t.fwd_parity) * sc.T_cap;
         for (int c0 = 0; c0 < mpad; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
@@ -495,7 +496,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
     for (int m = lane; m < t.M; m += 32) {
       const unsigned long long ka = ng_best[q * kNgRows + m], kg = ng_gbest[q * kNgRows + m];
       if (ka != 0ull) atomicMax(&keys[t.x_row0 + m], ka);
-      if (kg != 0ull) atomicMax(&t.sample_ctx->ng_gumbel[t.x_row0 + m], kg);
+      if (kg != 0ull) atomicMax(&t.sample_ctx->ng_gumbel[(size_t)t.fwd_parity * t.sample_ctx->T_cap + t.x_row0 + m], kg);
     }
     named_bar_sync(1, kWorkerThreads);           // every epilogue warp's (max, sum) pairs are final
     if (cta < units)
@@ -507,7 +508,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
           const float nm = fmaxf(acc.x, o.x);
           if (nm > -INFINITY) acc = make_float2(nm, acc.y * __expf(acc.x - nm) + o.y * __expf(o.x - nm));
         }
-        t.sample_ctx->ng_ms[(size_t)cta * t.sample_ctx->T_cap + t.x_row0 + m] = acc;
+        t.sample_ctx->ng_ms[((size_t)t.fwd_parity * t.sample_ctx->ng_parts + cta) * t.sample_ctx->T_cap + t.x_row0 + m] = acc;
       }
     named_bar_sync(1, kWorkerThreads);           // before a following task re-initialises the tables
   }

@@ -124,26 +124,36 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
     for (int t = w.wtid; t < c.T_cap; t += kWorkerThreads) c.argmax_keys[(size_t)(kbuf ^ 1) * c.T_cap + t] = 0ull;
   }
   if (!first && c.ng_mode) {
-    // non-greedy verify inputs: merge the CTAs' (max, sum exp) pairs of every row, turn the drafted token's scaled logit
-    // into its probability, decode the residual sample, and reset the accumulators for the next forward
-    const int parts = min((int)gridDim.x, (c.md.vocab + kTileN - 1) / kTileN);
+    // non-greedy verify inputs: merge the (max, sum exp) pairs of every CTA of every rank (rank order, then CTA order: the
+    // same on every rank), turn the drafted token's scaled logit into its probability, decode the residual sample (best
+    // Gumbel key over the ranks' vocabulary slices), and re-arm the OTHER half of the accumulators for the next forward
+    const int parts = c.ng_parts;
+    const size_t half = (size_t)kbuf * c.T_cap;
     for (int t = w.wtid; t < Tprev; t += kWorkerThreads) {
-      float M = -INFINITY, S = 0.f;
-      for (int p0 = 0; p0 < parts; p0 += 8) {
-        float2 v[8];
+      float M = -INFINITY, S = 0.f, lp = -INFINITY;
+      unsigned long long gk = 0ull;
+      for (int r = 0; r < c.tp_size; ++r) {
+        const float2* ms = peer_ptr(c, r, c.ng_ms) + (size_t)kbuf * parts * c.T_cap;
+        for (int p0 = 0; p0 < parts; p0 += 8) {
+          float2 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (p0 + i < parts) ? ld_weak(&c.ng_ms[(size_t)(p0 + i) * c.T_cap + t]) : make_float2(-INFINITY, 0.f);
+          for (int i = 0; i < 8; ++i) v[i] = (p0 + i < parts) ? ld_weak(&ms[(size_t)(p0 + i) * c.T_cap + t]) : make_float2(-INFINITY, 0.f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float nm = fmaxf(M, v[i].x);
-          if (nm > -INFINITY) { S = S * __expf(M - nm) + v[i].y * __expf(v[i].x - nm); M = nm; }
+          for (int i = 0; i < 8; ++i) {
+            const float nm = fmaxf(M, v[i].x);
+            if (nm > -INFINITY) { S = S * __expf(M - nm) + v[i].y * __expf(v[i].x - nm); M = nm; }
+          }
         }
+        lp = fmaxf(lp, ld_weak(peer_ptr(c, r, c.ng_prop) + half + t));          // exactly one rank holds the drafted token
+        const unsigned long long k = ld_weak(peer_ptr(c, r, c.ng_gumbel) + half + t);
+        gk = k > gk ? k : gk;
       }
-      const float lp = ld_weak(&c.ng_prop[t]);
       c.ng_px[t] = (S > 0.f && lp > -INFINITY) ? __expf(lp - M) / S : 0.f;
-      c.ng_bonus[t] = argmax_key_index(ld_weak(&c.ng_gumbel[t]));
-      c.ng_prop[t] = -INFINITY;
-      c.ng_gumbel[t] = 0ull;
+      c.ng_bonus[t] = argmax_key_index(gk);
+    }
+    for (int t = w.wtid; t < c.T_cap; t += kWorkerThreads) {
+      c.ng_prop[(size_t)(kbuf ^ 1) * c.T_cap + t] = -INFINITY;
+      c.ng_gumbel[(size_t)(kbuf ^ 1) * c.T_cap + t] = 0ull;
     }
   }
   __threadfence_block();
@@ -509,6 +519,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         t.epilogue = EPI_SAMPLE;
         t.sample_ctx = &c;
         t.fwd = ld_weak(&hdr->iter) + c.ng_rng_offset;
+        t.fwd_parity = ld_weak(&hdr->iter) & 1;
         t.rows_total = T;
       }
       return t;

@@ -148,9 +148,12 @@ struct alignas(16) DevCtx {
   float ng_inv_temp;                 // 1 / temperature
   unsigned int ng_seed_lo, ng_seed_hi;
   int ng_rng_offset;
-  float* ng_prop;                    // [T_cap] logit / T of the drafted token of every row (-inf: outside the vocabulary)
-  unsigned long long* ng_gumbel;     // [T_cap] best Gumbel-perturbed key among the other tokens
-  float2* ng_ms;                     // [nctas][T_cap] per-CTA (max, sum exp) of logit / T
+  // the three accumulators below are double-buffered by forward parity, like argmax_keys: under tensor parallelism the
+  // peers read them (vocabulary-parallel LM head) while this rank may already be clearing the other half
+  float* ng_prop;                    // [2][T_cap] logit / T of the drafted token of every row (-inf: not in this rank's slice)
+  unsigned long long* ng_gumbel;     // [2][T_cap] best Gumbel-perturbed key among the other tokens (of this rank's slice)
+  float2* ng_ms;                     // [2][nctas][T_cap] per-CTA (max, sum exp) of logit / T
+  int ng_parts;                      // CTAs that hold LM-head tiles (identical on every rank)
   float* ng_px;                      // [T_cap] merged by the policy stage: probability of the drafted token
   int* ng_bonus;                     // [T_cap] and the residual sample
   int* trace;                        // optional forward trace: {iter, seq, ctx, B, L, tokens...}*
@@ -171,6 +174,8 @@ struct alignas(16) DevCtx {
   unsigned long long* push_buf[kMaxTP];       // rank r's push buffer [push_rows_cap][tp_size][h] of tagged partial sums
   unsigned long long* stage_buf[kMaxTP];      // rank r's staging buffer [fuse_rows][h / 8][8] of tagged finished rows:
                                               // per 8-column group, words 0-3 = hidden, 4-7 = xn (two bf16 per word)
+  const uint8_t* arena_self;                  // this rank's activation arena and the peers' mappings of theirs: every rank
+  const uint8_t* peer_arena[kMaxTP];          // lays its arena out identically, so peer_ptr() reaches any peer buffer
   const float* peer_part_rs[kMaxTP][3];       // the peers' fp32 partial buffers (stand-alone reduce stage, prefill)
   const unsigned long long* peer_keys[kMaxTP];
   unsigned long long* peer_xflag[kMaxTP];     // rank r's flag array (this rank writes element [tp_rank])
@@ -197,6 +202,13 @@ struct alignas(16) DevCtx {
 };
 
 enum RunMode : int { RUN_PLAN = 0, RUN_JACOBI = 1 };
+
+// rank r's copy of one of this rank's activation-arena buffers
+template <typename T>
+__host__ __device__ inline const T* peer_ptr(const DevCtx& c, int r, const T* own) {
+  if (r == c.tp_rank) return own;
+  return reinterpret_cast<const T*>(c.peer_arena[r] + (reinterpret_cast<const uint8_t*>(own) - c.arena_self));
+}
 
 // Attention units per kv head along its query heads for a forward whose units number `base_units` without any head split
 // and whose longest group has `max_len` rows.  The stage is latency-bound: a CTA pays a fixed cost per unit (K / V fill,

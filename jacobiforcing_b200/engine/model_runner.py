@@ -300,8 +300,6 @@ class ModelRunner:
                 raise NotImplementedError("Mixed greedy / non-greedy temperatures in one batch are not supported")
             if nongreedy and mb:
                 raise NotImplementedError("the multiblock strategy is greedy only")
-            if nongreedy and self.world_size > 1:
-                raise NotImplementedError("non-greedy Jacobi decoding is not available under tensor parallelism")
             if is_prefill:
                 return self._jacobi_prefill_with_drafting(seqs)
             return self._run_jacobi(seqs, "engine_nongreedy" if nongreedy else ("engine" if jac else "multiblock"))

@@ -175,3 +175,106 @@ def test_llm_tensor_parallel_from_a_plain_process(tp):
         if same < 40:
             t2 = teacher_forced_logits(model, p + b[:same])[-1].topk(2).values
             assert float(t2[0] - t2[1]) < NEAR_TIE
+
+
+def _ng_rank_main(rank, tp, group, cfg, sd, shard_attn, num_ctas, shared, out, errors):
+    """Non-greedy generation on the sharded engine, then the restatement driven by the SHARDED device forward: every rank
+    runs the same replay (the forwards are collective) and assembles the full logits from the ranks' vocabulary slices."""
+    try:
+        from jacobiforcing_b200.policy import MODES, PolicyKnobs
+        from jacobiforcing_b200.runtime import JacobiRuntime
+        from oracle import jacobi_policy as jp
+        from oracle.hf_model import rope_tables
+        from tests.gpu_helpers import DeviceEngineForward
+        cos, sin = rope_tables(float(cfg.rope_theta), cfg.hidden_size // cfg.num_attention_heads,
+                               cfg.max_position_embeddings)
+        rt = JacobiRuntime(cfg, device=0, max_rows=256, max_seqs=2, num_kv_pages=8, max_pages_per_seq=4,
+                           trace_capacity=1 << 16, tp_rank=rank, tp_size=tp, tp_group=group,
+                           tp_shard_attention=shard_attn, num_ctas=num_ctas)
+        rt.load_state_dict(sd)
+        rt.set_rope_tables(cos.numpy(), sin.numpy())
+        V, L, T, kseed, off = cfg.vocab_size, 8, 0.7, 0x5eed5eed1234, 3
+        g = torch.Generator().manual_seed(21)
+        prompt = torch.randint(0, V, (24,), generator=g).tolist()
+        prng = random.Random(21)
+        pads = [prng.randrange(V) for _ in range(64 * L)]
+        seq = rt.new_sequence()
+        rt.prefill(seq, prompt, [])
+        seq.ctx = len(prompt) - 1
+        knobs = PolicyKnobs(mode=MODES["engine_nongreedy"], n=L, eos=None, pad=0, max_iteration_count=128, max_new_tokens=32,
+                            vocab=V, temperature=T, seed=kseed, rng_offset=off)
+        results, run = rt.jacobi_run([seq], knobs, [0], None, pad_stream=[pads], want_trace=True)
+        rt.release(seq)
+        dev = (results[0].tokens, results[0].total_iterations, [t["rows"][0] for t in run["trace"]])
+        # replay
+        seq = rt.new_sequence()
+        rt.prefill(seq, prompt, [])
+        fwd = DeviceEngineForward(rt, seq, want_logits=True)
+        cur = {"p": 0, "it": -1}
+        inv_t = np.float32(1.0) / np.float32(T)
+
+        def forward_step(token_ids, draft):
+            greedy = fwd(token_ids, draft)
+            cur["it"] += 1
+            shared[(cur["it"], rank)] = fwd.last_logits[:L - 1]
+            group.barrier()
+            full = np.concatenate([shared[(cur["it"], r)] for r in range(tp)], axis=1)
+            group.barrier()
+            sc = torch.from_numpy(np.ascontiguousarray(full)).to(torch.bfloat16).float().numpy() * inv_t
+            e = np.exp(sc - sc.max(axis=1, keepdims=True))
+            probs = e / e.sum(axis=1, keepdims=True)
+            px = [float(probs[t, draft[t + 1]]) for t in range(L - 1)]
+
+            def residual(t):
+                u = jp.device_gumbel_uniforms(kseed, off, t, cur["it"], V)
+                key = sc[t] + (-np.log(-np.log(u))).astype(np.float32)
+                key[draft[t + 1]] = -np.inf
+                return int(np.argmax(key))
+            return greedy, px, residual
+
+        def randint(k):
+            o = pads[cur["p"]:cur["p"] + k]
+            cur["p"] += k
+            return o
+        toks = list(prompt)
+        accepted, iters, per_iter, drafts = jp.engine_nongreedy(
+            forward_step, toks, L, 32, 128, randint, lambda it, t: jp.device_accept_uniform(kseed, off, t, it))
+        rt.release(seq)
+        out[rank] = (dev, (accepted, iters, drafts))
+        group.barrier()
+        rt.close()
+    except BaseException as e:       # noqa: BLE001
+        errors.append((rank, repr(e)))
+        try:
+            group._barrier.abort()
+        except Exception:
+            pass
+        raise
+
+
+@pytest.mark.parametrize("tp,shard_attn", [(2, False), (2, True), (4, False)])
+def test_nongreedy_on_the_sharded_engine(tp, shard_attn):
+    """Non-greedy Jacobi under tensor parallelism: the vocabulary-parallel sampling epilogue (each rank holds the softmax
+    normaliser, the drafted token's logit and a Gumbel-max sample of ITS slice; the policy stage of every rank merges all
+    of them) gives every rank the same run, equal to the restatement on the gathered device logits."""
+    from jacobiforcing_b200.tp import LocalTPGroup
+    from oracle.hf_model import state_dict_bf16
+    from tests.gpu_helpers import make_pair
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    model, rt1 = make_pair("tiny")
+    rt1.close()
+    sd = state_dict_bf16(model)
+    group = LocalTPGroup(tp)
+    shared, out, errors = {}, {}, []
+    threads = [threading.Thread(target=_ng_rank_main, args=(r, tp, group, model.config, sd, shard_attn, (sms - 4) // tp,
+                                                            shared, out, errors)) for r in range(tp)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(600)
+    assert not errors, errors
+    for r in range(1, tp):
+        assert out[r] == out[0], "ranks disagree"
+    dev, rep = out[0]
+    assert dev[0] == rep[0] and dev[1] == rep[1] and dev[2] == rep[2]
+    assert len(dev[0]) >= 32
