@@ -85,6 +85,8 @@ struct GemmSmem {
   long long t_acc_full;       // developer aid: clock of the first accumulator hand-over of the last GEMM stage
   unsigned long long* best;   // [4][kArgmaxRows] EPI_ARGMAX running best key per epilogue warp and row (aliases
                               // the attention tile buffer: the LM head never overlaps an attention stage)
+  int stage_rows;             // rows of a [2][rows][128 B] staging tile that fit the same buffer (EPI_SWIGLU_BF16 bulk
+                              // stores; 0 = disabled): the MLP never overlaps an attention stage either
 };
 
 struct PipeState {      // smem ring position.  Phase parity is tracked PER SLOT (bit i = parity of slot i) so the ring
@@ -277,6 +279,14 @@ __device__ __forceinline__ void gemm_issue_mma(const GemmTask& t, GemmSmem* gs, 
   }
 }
 
+// EPI_SWIGLU_BF16 through shared memory: the tile's silu(g) * u values are staged in the operand layout of the down
+// projection ([k-chunk][row][128 B], 128-byte swizzle) and leave as ONE bulk copy per k-chunk.  Against 32 scattered 2-byte
+// stores per thread this (a) needs no generic-proxy -> async-proxy fence and no drain of hundreds of small stores before the
+// hand-over to the down projection (the bulk group's completion IS the drain), (b) is a 4x smaller, rolled epilogue body.
+__device__ __forceinline__ bool swiglu_bulk_ok(const GemmTask& t, int stage_rows) {
+  return t.epilogue == EPI_SWIGLU_BF16 && t.M <= 128 && round_up16(t.M) <= stage_rows && ((t.x_row0 & 7) == 0);
+}
+
 // ---- warps 2..5: TMEM -> registers -> global ----------------------------------------------------------------------
 __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, int cta, int nctas, AccState& acc) {
   const int warp = threadIdx.x >> 5;
@@ -368,6 +378,46 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
             st_pred_u64(out + (size_t)m * t.out_row_stride + t.N + n, tg | (unsigned long long)up[j], live);
           }
         }
+      } else if (t.epilogue == EPI_SWIGLU_BF16 && swiglu_bulk_ok(t, gs->stage_rows)) {
+        // gate in columns [0,mpad), up in columns [128,128+mpad); rounding points as in the direct path below
+        uint8_t* stg = reinterpret_cast<uint8_t*>(gs->best);
+        const int kc2 = feat_in_tile >> 6, cc = feat_in_tile & 63;
+        const bool nvalid = n < t.N;
+        uint8_t* srow = stg + (size_t)kc2 * mpad * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < mpad; c0 += 8) {
+          uint32_t g[8], up[8];
+          tmem_ld8(taddr + c0, g);
+          tmem_ld8(taddr + up_off + c0, up);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gf = bf16_round(__uint_as_float(g[j]));
+            const float uf = bf16_round(__uint_as_float(up[j]));
+            const float s = bf16_round(gf / (1.f + __expf(-gf)));
+            const __nv_bfloat16 ob = __float2bfloat16_rn(s * uf);
+            if (nvalid && c0 + j < mlive)
+              *reinterpret_cast<unsigned short*>(srow + sw128_offset((uint32_t)(c0 + j), (uint32_t)cc)) = *reinterpret_cast<const unsigned short*>(&ob);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&gs->acc_empty[acc.buf]);              // the accumulator is free while the tile is still on its way out
+        fence_proxy_async_smem();
+        named_bar_sync(1, kWorkerThreads);
+        if (threadIdx.x == 64) {
+          uint8_t* dst = reinterpret_cast<uint8_t*>(t.out);
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const int nk = r.n_tile * kTileN + k2 * 64;
+            if (nk < t.N)
+              bulk_s2g(dst + ((size_t)(nk >> 6) * t.out_rows_cap + t.x_row0 + m0) * 128, stg + (size_t)k2 * mpad * 128, (uint32_t)mlive * 128u);
+          }
+          bulk_commit();
+          bulk_wait_all();
+        }
+        if (u + nctas < units || mt + 1 < m_tiles) named_bar_sync(1, kWorkerThreads);    // the staging tile is reused
+        acc.advance();
+        continue;
       } else if (t.epilogue == EPI_SWIGLU_BF16) {
         // gate in columns [0,mpad), up in columns [128,128+mpad).  HF Qwen2MLP rounding points
         // (transformers Qwen2MLP.forward: down(act(gate(x)) * up(x)), every op in bf16): g,u -> bf16; silu(g) -> bf16;

@@ -37,20 +37,20 @@ struct BarState {
   __device__ __forceinline__ unsigned int target(unsigned int nctas) const { return epoch * nctas + xcount; }
 };
 
-__device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w, BarState& bs,
-                                             int* prof_slot = nullptr, bool tma_consumer = true, bool xgpu = false,
-                                             int stage_id = 0) {
+__device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerView& w, BarState& bs, bool profiled = true,
+                                             bool tma_consumer = true, bool xgpu = false, int stage_id = 0) {
+  const bool prof_act = profiled && w.prof_on() != 0;
   if (tma_consumer) fence_proxy_async_all();   // only stages whose output a bulk copy (async proxy) will read need it
   workers_sync();
-  const unsigned int local_target = (bs.epoch + 1) * (unsigned int)w.nctas + bs.xcount;
+  const unsigned int local_target = (bs.epoch + 1) * (unsigned int)w.nctas() + bs.xcount;
   bs.epoch += 1;
   if (xgpu) bs.xcount += 1;
-  if (w.wtid == 0) {
+  if (w.wtid() == 0) {
     long long t_arrive = 0;
-    if (prof_slot) t_arrive = clock64();
+    if (prof_act) t_arrive = clock64();
     prof_mark(c, w, 900);
     red_release_gpu_add_u32(c.bar_counter, 1u);
-    if (xgpu && w.cta == 0) {
+    if (xgpu && w.cta() == 0) {
       wait_epoch<false>(c.bar_counter, local_target);          // every CTA of this GPU has arrived
       fence_acq_rel_sys();
       const unsigned long long val = c.xflag_base + bs.xcount;
@@ -65,12 +65,15 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerCtx& w
       fence_acq_rel_sys();
       red_release_gpu_add_u32(c.bar_counter, 1u);              // the extra arrival releases this GPU's CTAs
     }
-    wait_epoch<false>(c.bar_counter, bs.target(w.nctas), xgpu);      // critical path: spin, do not sleep
-    if (prof_slot && *prof_slot + 3 <= c.prof_cap) {      // (stage id, arrival of CTA 0, release of the barrier)
-      c.prof[*prof_slot] = stage_id;
-      c.prof[*prof_slot + 1] = t_arrive;
-      c.prof[*prof_slot + 2] = clock64();
-      *prof_slot += 3;
+    wait_epoch<false>(c.bar_counter, bs.target(w.nctas()), xgpu);      // critical path: spin, do not sleep
+    if (prof_act) {                                       // (stage id, arrival of CTA 0, release of the barrier)
+      const int prof_n = w.shared()->prof_n;
+      if (prof_n + 3 <= c.prof_cap) {
+        c.prof[prof_n] = stage_id;
+        c.prof[prof_n + 1] = t_arrive;
+        c.prof[prof_n + 2] = clock64();
+        w.shared()->prof_n = prof_n + 3;
+      }
     }
     prof_mark(c, w, 901);
   }
@@ -100,11 +103,11 @@ __device__ __noinline__ void policy_stage_plan(const DevCtx& c, const WorkerShar
   const int n_lm = ld_weak(&hdr->n_lm_tasks);
   for (int i = 0; i < n_lm; ++i) {
     const int r0 = ld_weak(&hdr->lm_row0[i]), rn = ld_weak(&hdr->lm_rows[i]);
-    for (int t = r0 + w.wtid; t < r0 + rn; t += kWorkerThreads) {
+    for (int t = r0 + w.wtid(); t < r0 + rn; t += kWorkerThreads) {
       c.greedy[t] = argmax_key_index(merged_key(c, kbuf, t));
     }
   }
-  if (w.wtid == 0) {
+  if (w.wtid() == 0) {
     hdr->n_commit = ld_weak(&hdr->n_commit_after);
     hdr->iter = ld_weak(&hdr->iter) + 1;
     hdr->rows_total = ld_weak(&hdr->rows_total) + ld_weak(&hdr->T);
@@ -118,10 +121,10 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
   const int Tprev = first ? 0 : ld_weak(&hdr->T);
   const int kbuf = first ? 0 : (ld_weak(&hdr->iter) & 1);
   if (!first) {
-    for (int t = w.wtid; t < Tprev; t += kWorkerThreads) c.greedy[t] = argmax_key_index(merged_key(c, kbuf, t));
+    for (int t = w.wtid(); t < Tprev; t += kWorkerThreads) c.greedy[t] = argmax_key_index(merged_key(c, kbuf, t));
     // the OTHER buffer is cleared for the next forward; its last readers (the previous policy stage of every rank)
     // are separated from this point by that forward's cross-GPU barriers
-    for (int t = w.wtid; t < c.T_cap; t += kWorkerThreads) c.argmax_keys[(size_t)(kbuf ^ 1) * c.T_cap + t] = 0ull;
+    for (int t = w.wtid(); t < c.T_cap; t += kWorkerThreads) c.argmax_keys[(size_t)(kbuf ^ 1) * c.T_cap + t] = 0ull;
   }
   if (!first && c.ng_mode) {
     // non-greedy verify inputs: merge the (max, sum exp) pairs of every CTA of every rank (rank order, then CTA order: the
@@ -129,7 +132,7 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
     // Gumbel key over the ranks' vocabulary slices), and re-arm the OTHER half of the accumulators for the next forward
     const int parts = c.ng_parts;
     const size_t half = (size_t)kbuf * c.T_cap;
-    for (int t = w.wtid; t < Tprev; t += kWorkerThreads) {
+    for (int t = w.wtid(); t < Tprev; t += kWorkerThreads) {
       float M = -INFINITY, S = 0.f, lp = -INFINITY;
       unsigned long long gk = 0ull;
       for (int r = 0; r < c.tp_size; ++r) {
@@ -151,15 +154,15 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
       c.ng_px[t] = (S > 0.f && lp > -INFINITY) ? __expf(lp - M) / S : 0.f;
       c.ng_bonus[t] = argmax_key_index(gk);
     }
-    for (int t = w.wtid; t < c.T_cap; t += kWorkerThreads) {
+    for (int t = w.wtid(); t < c.T_cap; t += kWorkerThreads) {
       c.ng_prop[(size_t)(kbuf ^ 1) * c.T_cap + t] = -INFINITY;
       c.ng_gumbel[(size_t)(kbuf ^ 1) * c.T_cap + t] = 0ull;
     }
   }
   __threadfence_block();
   workers_sync();
-  if (w.lane == 0) {
-    for (int s = w.wwarp; s < c.n_seqs; s += 4) {
+  if (w.lane() == 0) {
+    for (int s = w.wwarp(); s < c.n_seqs; s += 4) {
       SeqState& st = c.seq_state[s];
       SeqSlot& sl = c.seq_slot[s];
       sl.had_forward = (sl.active && !first) ? 1 : 0;
@@ -187,7 +190,7 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
   }
   __threadfence_block();
   workers_sync();
-  if (w.wtid == 0) {
+  if (w.wtid() == 0) {
     const int iter_done = first ? 0 : ld_weak(&hdr->iter) + 1;
     int T = 0, G = 0, nc = 0, units = 0, slots = 0, err = 0;
     const int CH = c.attn_chunk;
@@ -263,7 +266,7 @@ __device__ __noinline__ void policy_stage_jacobi(const DevCtx& c, const WorkerSh
     if (!sl.active) continue;
     const SeqState& st = c.seq_state[s];
     const int n = sl.B * sl.L;
-    for (int idx = w.wtid; idx < n; idx += kWorkerThreads) {
+    for (int idx = w.wtid(); idx < n; idx += kWorkerThreads) {
       const int i = idx / sl.L, j = idx - i * sl.L;
       c.tok[sl.row0 + idx] = st.out_rows[i][j];
       c.row_group[sl.row0 + idx] = sl.g0 + i;
@@ -288,9 +291,12 @@ struct IterPlan {
 };
 
 template <int ROLE>
-__device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring_bytes, WorkerShared* ws,
-                         int run_mode, int max_forwards) {
-  WorkerCtx w = load_wctx(ws);
+__device__ void run_role(uint8_t* tiles, int ring_bytes, int run_mode, int max_forwards) {
+  // the fixed shared-memory blocks are addressed by constant offsets: no pointer register (or stack slot) is spent on them
+  const DevCtx& c = *reinterpret_cast<const DevCtx*>(jf_smem_base + kSmemCtxOff);
+  GemmSmem* const gs = reinterpret_cast<GemmSmem*>(jf_smem_base);
+  WorkerShared* const ws = reinterpret_cast<WorkerShared*>(jf_smem_base + kSmemWsOff);
+  const WorkerView w{};
   const int cta = blockIdx.x, nctas = gridDim.x;
   BarState bs;
   PipeState pipe;
@@ -301,8 +307,6 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
   const int nt_v = (md.vocab + 127) >> 7;
   const bool tp = c.tp_size > 1;
   int nstages = 1, slot_bytes = 0;
-  int prof_n = 0;
-  int* prof_slot = nullptr;
   const uint64_t w_policy = (ROLE == ROLE_W) ? l2_policy_evict_first() : 0ull;
   unsigned int df_uses = 0u;                   // gate/up -> down dataflow hand-overs so far in this launch
 
@@ -332,23 +336,36 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     } else if (ROLE == ROLE_MMA) {
       gemm_issue_mma(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, acc);
     } else {
-      w.tag = c.tag_base + bs.epoch + 1u;
-      ws->tag = w.tag;
+      ws->tag = c.tag_base + bs.epoch + 1u;
       prof_mark(c, w, 600);
       gemm_epilogue(t, gs, cta, nctas, acc);
-      if (w.prof_on && w.wtid == 0 && c.prof_marks != nullptr) {
-        int* cnt = reinterpret_cast<int*>(w.red) + 4;
+      if (w.prof_on() && w.wtid() == 0 && c.prof_marks != nullptr) {
+        int* cnt = reinterpret_cast<int*>(w.red()) + 4;
         const int n = *cnt;
         // developer aid: 600 = epilogue entered, 601 = first accumulator handed over, 602 = epilogue done
         if (n + 4 <= 8192) { c.prof_marks[n] = 601; c.prof_marks[n + 1] = gs->t_acc_full; c.prof_marks[n + 2] = 602; c.prof_marks[n + 3] = clock64(); *cnt = n + 4; }
       }
       if (fuse_kind == 5) {
         // gate/up -> down without a grid barrier: publish this tile to the k-splits of the down projection that read it
-        fence_proxy_async_all();                        // the tile is read by bulk copies (async proxy) of other CTAs
-        workers_sync();
-        if (w.wtid == 0 && cta < t.n_tiles) {
-          for (int s2 = 0; s2 < c.splits_down; ++s2)
-            if (df_tile_feeds_split(cta, s2, c.splits_down, kc_i)) red_release_gpu_add_u32(c.tile_ctr + s2, 1u);
+        const bool bulk = swiglu_bulk_ok(t, gs->stage_rows);
+        if (!bulk) {
+          fence_proxy_async_all();                      // the tile is read by bulk copies (async proxy) of other CTAs
+          workers_sync();
+        }
+        // bulk: the tile left through the async proxy and thread 0 has waited for the copy to complete (gemm_epilogue)
+        if (w.wtid() == 0 && cta < t.n_tiles) {
+          const unsigned int df_mask = ws->df_mask;
+          if (bulk) {
+            prof_mark(c, w, 605);
+            if (!(c.debug_skip & 32768)) fence_acq_rel_gpu();
+            prof_mark(c, w, 607);
+            for (int s2 = 0; s2 < c.splits_down; ++s2)
+              if ((df_mask >> s2) & 1u) red_relaxed_gpu_add_u32(c.tile_ctr + s2, 1u);
+          } else {
+            for (int s2 = 0; s2 < c.splits_down; ++s2)
+              if ((df_mask >> s2) & 1u) red_release_gpu_add_u32(c.tile_ctr + s2, 1u);
+          }
+          prof_mark(c, w, 606);
         }
       } else if (fuse_kind != 0 && cta < t.n_tiles * t.splits) {
         // no flag, fence or barrier: the tails poll the tagged partial sums themselves
@@ -361,24 +378,30 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     }
     if (barrier_after) {
       if (ROLE == ROLE_WORKER)
-        grid_barrier(c, w, bs, prof_slot, t.epilogue == EPI_SWIGLU_BF16 || fuse_kind == 1 || fuse_kind == 2 || fuse_kind == 4, xgpu, stage_id);
+        grid_barrier(c, w, bs, true, t.epilogue == EPI_SWIGLU_BF16 || fuse_kind == 1 || fuse_kind == 2 || fuse_kind == 4, xgpu, stage_id);
       else skip_barrier(xgpu);
     }
   };
 #define JF_SIMT_STAGE_X(tma_out, sid, body)                    \
   do {                                                        \
-    if (ROLE == ROLE_WORKER) { w.tag = c.tag_base + bs.epoch + 1u; ws->tag = w.tag; body; grid_barrier(c, w, bs, prof_slot, tma_out, false, sid); } else { skip_barrier(false); } \
+    if (ROLE == ROLE_WORKER) { ws->tag = c.tag_base + bs.epoch + 1u; body; grid_barrier(c, w, bs, true, tma_out, false, sid); } else { skip_barrier(false); } \
   } while (0)
 
 #define JF_SIMT_STAGE(sid, body) JF_SIMT_STAGE_X(true, sid, body)
   auto launch_mark = [&](int id) {     // developer aid (JF_DEBUG_SKIP & 2048): coarse marks of the launch itself
-    if (ROLE == ROLE_WORKER && (c.debug_skip & 2048) && cta == 0 && w.wtid == 0 && c.prof_marks != nullptr) {
-      int* cnt = reinterpret_cast<int*>(w.red) + 5;
+    if (ROLE == ROLE_WORKER && (c.debug_skip & 2048) && cta == 0 && w.wtid() == 0 && c.prof_marks != nullptr) {
+      int* cnt = reinterpret_cast<int*>(w.red()) + 5;
       if (id == 990) *cnt = 0;
       const int n = *cnt;
       if (n + 2 <= 8192) { c.prof_marks[n] = id; c.prof_marks[n + 1] = clock64(); *cnt = n + 2; *c.prof_marks_n = n + 2; }
     }
   };
+  if (ROLE == ROLE_WORKER && w.wtid() == 0) {
+    unsigned int m = 0u;
+    for (int s2 = 0; s2 < c.splits_down && s2 < 32; ++s2)
+      if (df_tile_feeds_split(cta, s2, c.splits_down, kc_i)) m |= 1u << s2;
+    ws->df_mask = m;                     // read by this thread only (gate/up -> down hand-over)
+  }
   launch_mark(990);
   if (run_mode == RUN_JACOBI) {
     JF_SIMT_STAGE(SID_POLICY, if (cta == 0) policy_stage_jacobi(c, ws, true, max_forwards));
@@ -395,48 +418,49 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     ip.hsplit = max(1, ld_weak(&hdr->attn_hsplit));
     if (ip.done) {
       if (ROLE == ROLE_WORKER) {
-        if (prof_slot != nullptr && w.wtid == 0) {
+        if (w.prof_on() && w.wtid() == 0) {
+          int prof_n = ws->prof_n;
           if (prof_n + 3 <= c.prof_cap) {
             c.prof[prof_n] = -(long long)globaltimer_ns(); c.prof[prof_n + 1] = clock64(); c.prof[prof_n + 2] = c.prof[prof_n + 1];
             prof_n += 3;
           }
           *c.prof_count = prof_n;
-          if (c.prof_marks_n) *c.prof_marks_n = reinterpret_cast<int*>(w.red)[4];
+          if (c.prof_marks_n) *c.prof_marks_n = reinterpret_cast<int*>(w.red())[4];
         }
-        if (tp) grid_barrier(c, w, bs, nullptr, false, true);      // every rank has read every rank's keys
+        if (tp) grid_barrier(c, w, bs, false, false, true);      // every rank has read every rank's keys
         if (cta == 0)
-          for (int t = w.wtid; t < 2 * c.T_cap; t += kWorkerThreads) c.argmax_keys[t] = 0ull;   // clean for the next launch
+          for (int t = w.wtid(); t < 2 * c.T_cap; t += kWorkerThreads) c.argmax_keys[t] = 0ull;   // clean for the next launch
         stage_commit(c, ws, ip.n_commit);
       }
       launch_mark(992);
       break;
     }
     const int T = ip.T;
-    if (ROLE == ROLE_WORKER && (c.debug_skip & 2048) && cta == 0 && w.wtid == 0 && c.prof_marks != nullptr) {
+    if (ROLE == ROLE_WORKER && (c.debug_skip & 2048) && cta == 0 && w.wtid() == 0 && c.prof_marks != nullptr) {
       // developer aid: one (1000 + rows, clock) mark per forward of the launch (per-forward durations)
-      int* cnt = reinterpret_cast<int*>(w.red) + 5;
+      int* cnt = reinterpret_cast<int*>(w.red()) + 5;
       const int n = *cnt;
       if (n + 2 <= 8192) { c.prof_marks[n] = 1000 + T; c.prof_marks[n + 1] = clock64(); *cnt = n + 2; *c.prof_marks_n = n + 2; }
     }
     if (ROLE == ROLE_WORKER) {
-      if (prof_slot != nullptr && w.wtid == 0) {                           // forward profiled: publish and stop
+      if (w.prof_on() && w.wtid() == 0) {                                    // forward profiled: publish and stop
+        int prof_n = ws->prof_n;
         if (prof_n + 3 <= c.prof_cap) {        // closing record: (-wall clock ns, SM clock) calibrates cycles -> time
           c.prof[prof_n] = -(long long)globaltimer_ns(); c.prof[prof_n + 1] = clock64(); c.prof[prof_n + 2] = c.prof[prof_n + 1];
           prof_n += 3;
         }
         *c.prof_count = prof_n;
-        if (c.prof_marks_n) *c.prof_marks_n = reinterpret_cast<int*>(w.red)[4];
+        if (c.prof_marks_n) *c.prof_marks_n = reinterpret_cast<int*>(w.red())[4];
       }
-      prof_slot = nullptr;
-      w.prof_on = 0;
+      workers_sync();                          // thread 0 has read the flag the others are about to rewrite
       ws->prof_on = 0;
       if (cta == 0 && c.prof != nullptr && ld_weak(&hdr->iter) == c.prof_forward) {
-        prof_n = 0;
-        prof_slot = &prof_n;
-        w.prof_on = 1;
         ws->prof_on = 1;
-        if (w.wtid == 0) reinterpret_cast<int*>(w.red)[4] = 0;
-        if (w.wtid == 0 && c.prof_cap >= 3) { c.prof[0] = -(long long)globaltimer_ns(); c.prof[1] = clock64(); c.prof[2] = c.prof[1]; prof_n = 3; }
+        if (w.wtid() == 0) {
+          reinterpret_cast<int*>(w.red())[4] = 0;
+          ws->prof_n = 0;
+          if (c.prof_cap >= 3) { c.prof[0] = -(long long)globaltimer_ns(); c.prof[1] = clock64(); c.prof[2] = c.prof[1]; ws->prof_n = 3; }
+        }
       }
     }
     if (ROLE == ROLE_WORKER) {
@@ -444,11 +468,10 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
       const int ok = (T <= kPlanRows && ip.G <= kPlanGroups) ? 1 : 0;
       if (ok) {
         PlanCache* pc = ws->plan;
-        for (int t = w.wtid; t < T; t += kWorkerThreads) { pc->row_pos[t] = ld_weak(&c.row_pos[t]); pc->row_attn[t] = ld_weak(&c.row_attn[t]); }
-        for (int g = w.wtid; g < ip.G; g += kWorkerThreads) pc->groups[g] = load_group(c, g);
+        for (int t = w.wtid(); t < T; t += kWorkerThreads) { pc->row_pos[t] = ld_weak(&c.row_pos[t]); pc->row_attn[t] = ld_weak(&c.row_attn[t]); }
+        for (int g = w.wtid(); g < ip.G; g += kWorkerThreads) pc->groups[g] = load_group(c, g);
       }
-      if (w.wtid == 0) ws->plan_ok = ok;
-      w.plan = ok ? ws->plan : nullptr;
+      if (w.wtid() == 0) ws->plan_ok = ok;
     }
     slot_bytes = gemm_slot_bytes(min(kMaxRowsMMA, round_up16(T)));
     nstages = min(kMaxStages, ring_bytes / slot_bytes);
@@ -462,7 +485,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
     // split-K gate/up is a property of the engine (set when it is created), never of the forward: every forward must
     // add the same partial sums in the same order (Jacobi == AR == chunked prefill, bit for bit)
     const bool fuse_g = c.splits_gu > 1;
-    const bool dflow = c.dataflow_gd != 0 && fuse_d && !fuse_g && !tp && 2 * nt_i >= kc_i && c.splits_down <= kMaxTilesPerKind;
+    const bool dflow = c.dataflow_gd != 0 && fuse_d && !fuse_g && !tp && 2 * nt_i >= kc_i && c.splits_down <= 32;
     const bool fuse_q = c.fuse_rope != 0 && T <= kFuseRopeRows && nt_qkv * c.splits_qkv <= nctas && nt_qkv <= kMaxTilesPerKind;
 
     auto base_task = [&]() {
@@ -571,7 +594,7 @@ __device__ void run_role(const DevCtx& c, GemmSmem* gs, uint8_t* tiles, int ring
         gemm_stage(t, false, SID_LM);
       }
     }
-    if (ROLE == ROLE_WORKER) grid_barrier(c, w, bs, prof_slot, true, tp, SID_LM); else skip_barrier(tp);
+    if (ROLE == ROLE_WORKER) grid_barrier(c, w, bs, true, true, tp, SID_LM); else skip_barrier(tp);
 
     JF_SIMT_STAGE(SID_POLICY, if (cta == 0) {
       if (run_mode == RUN_JACOBI) policy_stage_jacobi(c, ws, false, max_forwards); else policy_stage_plan(c, ws);
@@ -602,7 +625,10 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
   const int attn_need = 2 * kAttnSub * (c.md.d + 8) * 2;
   const int best_need = 4 * kArgmaxRows * 8;
   const int attn_bytes = attn_need > best_need ? attn_need : best_need;
-  if (threadIdx.x == 0) gs->best = reinterpret_cast<unsigned long long*>(attn);
+  if (threadIdx.x == 0) {
+    gs->best = reinterpret_cast<unsigned long long*>(attn);
+    gs->stage_rows = c.swiglu_bulk ? ((attn_bytes / 256) & ~15) : 0;
+  }
   const uint32_t base_addr = smem_u32(smem);     // the ring must be 1024-byte aligned in the shared window (sw128)
   const size_t tiles_off = (((size_t)base_addr + (size_t)(attn - smem) + attn_bytes + 1023) & ~(size_t)1023) - base_addr;
   uint8_t* tiles = smem + tiles_off;
@@ -614,19 +640,19 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
   static_assert(sizeof(WorkerShared) <= 24 * sizeof(float), "WorkerShared must fit red[8..31]");
   WorkerShared* ws = reinterpret_cast<WorkerShared*>(red + 8);      // red[8..31]
   if (threadIdx.x == 0) {
-    ws->red = red; ws->attn_smem = attn; ws->prof_on = 0; ws->tag = 0u; ws->plan = plan; ws->plan_ok = 0;
+    ws->red = red; ws->attn_smem = attn; ws->prof_on = 0; ws->tag = 0u; ws->plan = plan; ws->plan_ok = 0; ws->prof_n = 0;
     ws->tmem_base = gs->tmem_base; ws->attn_phase = 0u; ws->attn_bar = &gs->attn_bar;
   }
   __syncthreads();
 
   if (warp == kWarpW) {
-    if (lane == 0) run_role<ROLE_W>(c, gs, tiles, ring_bytes, ws, run_mode, max_forwards);
+    if (lane == 0) run_role<ROLE_W>(tiles, ring_bytes, run_mode, max_forwards);
   } else if (warp == kWarpMMA) {
-    if (lane == 0) run_role<ROLE_MMA>(c, gs, tiles, ring_bytes, ws, run_mode, max_forwards);
+    if (lane == 0) run_role<ROLE_MMA>(tiles, ring_bytes, run_mode, max_forwards);
   } else if (warp == kWarpX) {
-    if (lane == 0) run_role<ROLE_X>(c, gs, tiles, ring_bytes, ws, run_mode, max_forwards);
+    if (lane == 0) run_role<ROLE_X>(tiles, ring_bytes, run_mode, max_forwards);
   } else {
-    run_role<ROLE_WORKER>(c, gs, tiles, ring_bytes, ws, run_mode, max_forwards);
+    run_role<ROLE_WORKER>(tiles, ring_bytes, run_mode, max_forwards);
   }
   __syncwarp();
   gemm_teardown(gs);

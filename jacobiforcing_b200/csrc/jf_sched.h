@@ -14,8 +14,10 @@
 namespace jf {
 
 // k-chunks [k0, k1) of k-split `split` out of `splits` over `k_chunks` chunks (balanced, contiguous)
-JF_HD inline int split_k0(int split, int splits, int k_chunks) { return (int)(((long long)split * k_chunks) / splits); }
-JF_HD inline int split_k1(int split, int splits, int k_chunks) { return (int)(((long long)(split + 1) * k_chunks) / splits); }
+// (32-bit unsigned arithmetic: split <= splits <= 64 and k_chunks < 2^20, so the product cannot overflow - and a 64-bit
+// division is a ~100-instruction library call on the device, paid by every role at the start of every GEMM stage)
+JF_HD inline int split_k0(int split, int splits, int k_chunks) { return (int)(((unsigned)split * (unsigned)k_chunks) / (unsigned)splits); }
+JF_HD inline int split_k1(int split, int splits, int k_chunks) { return (int)(((unsigned)(split + 1) * (unsigned)k_chunks) / (unsigned)splits); }
 
 // gate/up tile `tile` (128 features) holds k-chunks 2*tile and 2*tile+1 (the last tile may hold one) of the down
 // projection's K dimension (k_chunks = intermediate / 64).  Does the k-range of down k-split `split` read it?

@@ -16,21 +16,29 @@
 namespace jf {
 
 struct PlanCache;
+// Worker context of the non-inlined stage functions: a register copy of the shared-memory block below, taken once per call.
+// What derives from special registers (CTA, thread, lane) is never stored - it is re-read where it is used.
 struct WorkerCtx {
-  int cta, nctas;
-  int wtid;        // 0..127 among the worker warps
-  int wwarp;       // 0..3
-  int lane;
-  float* red;      // [16] scratch words
-  uint8_t* attn_smem;
-  int prof_on;     // CTA 0, forward being profiled
-  unsigned int tag; // unique id of the stage instance being executed (launch id, barrier count)
-  const PlanCache* plan;   // non-null: plan arrays of the forward in flight, in shared memory
+  float* red_;      // [16] scratch words
+  uint8_t* attn_smem_;
+  int prof_on_;     // CTA 0, forward being profiled
+  unsigned int tag_; // unique id of the stage instance being executed (launch id, barrier count)
+  const PlanCache* plan_;   // non-null: plan arrays of the forward in flight, in shared memory
+  __device__ __forceinline__ int cta() const { return (int)blockIdx.x; }
+  __device__ __forceinline__ int nctas() const { return (int)gridDim.x; }
+  __device__ __forceinline__ int wtid() const { return (int)threadIdx.x - 2 * 32; }       // 0..127 among the worker warps
+  __device__ __forceinline__ int wwarp() const { return (int)(threadIdx.x >> 5) - 2; }    // 0..3 (kWarpWorker0 = 2)
+  __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+  __device__ __forceinline__ float* red() const { return red_; }
+  __device__ __forceinline__ uint8_t* attn_smem() const { return attn_smem_; }
+  __device__ __forceinline__ int prof_on() const { return prof_on_; }
+  __device__ __forceinline__ unsigned int tag() const { return tag_; }
+  __device__ __forceinline__ const PlanCache* plan() const { return plan_; }
 };
 // The part of the worker context that is not derivable from special registers lives in shared memory.  Non-inlined
 // stage functions receive a pointer to it and rebuild their WorkerCtx in registers: a struct passed by reference to a
 // non-inlined function lives on the caller's stack, and every field access becomes a local-memory load that misses L1
-// after each grid barrier (ncu: long-scoreboard stalls on w.lane / grp.slot0 inside the attention stage).
+// after each grid barrier (ncu: long-scoreboard stalls on w.lane() / grp.slot0 inside the attention stage).
 // Per-forward copy of the small plan arrays every layer's stages index (row positions, attention slots, groups): read
 // from global memory they cost an L2 round trip per stage and layer; filled once per forward by the worker warps.
 constexpr int kPlanRows = 64, kPlanGroups = 8;
@@ -49,23 +57,43 @@ struct WorkerShared {
   uint32_t tmem_base;  // tensor memory of the CTA (free between the GEMM stages: the attention stage borrows it)
   uint32_t attn_phase; // parity of the attention MMA barrier
   uint64_t* attn_bar;
+  int prof_n;          // stage-profile words written so far (CTA 0, worker thread 0)
+  unsigned int df_mask; // bit s: this CTA's gate/up tile feeds k-split s of the down projection (fixed per launch)
 };
+// Shared-memory map of the kernel's fixed blocks (jf_kernel.cuh lays them out): GemmSmem, 8 scratch words, WorkerShared, the
+// kernel context.  Fixed offsets from the dynamic shared-memory base, so code that needs them holds no pointer register.
+extern __shared__ __align__(1024) uint8_t jf_smem_base[];
+constexpr size_t kSmemRedOff = (sizeof(GemmSmem) + 15) & ~(size_t)15;
+constexpr size_t kSmemWsOff = kSmemRedOff + 8 * sizeof(float);
+constexpr size_t kSmemCtxOff = kSmemRedOff + 32 * sizeof(float);
 __device__ __forceinline__ WorkerCtx load_wctx(const WorkerShared* ws) {
   WorkerCtx w;
-  w.cta = blockIdx.x; w.nctas = gridDim.x;
-  w.lane = threadIdx.x & 31;
-  w.wwarp = (int)(threadIdx.x >> 5) - 2;          // kWarpWorker0
-  w.wtid = (int)threadIdx.x - 2 * 32;
-  w.red = ws->red; w.attn_smem = ws->attn_smem; w.prof_on = ws->prof_on; w.tag = ws->tag;
-  w.plan = ws->plan_ok ? ws->plan : nullptr;
+  w.red_ = ws->red; w.attn_smem_ = ws->attn_smem; w.prof_on_ = ws->prof_on; w.tag_ = ws->tag;
+  w.plan_ = ws->plan_ok ? ws->plan : nullptr;
   return w;
 }
+// The persistent kernel's own loop keeps NO copy: every field is read from the shared-memory block where it is used (a
+// register copy held across the whole forward ends up in local memory - 255 registers are not enough for that loop - and
+// local memory misses L1 after every grid barrier's acquire fence; shared memory does not).
+struct WorkerView {
+  __device__ __forceinline__ WorkerShared* shared() const { return reinterpret_cast<WorkerShared*>(jf_smem_base + kSmemWsOff); }
+  __device__ __forceinline__ int cta() const { return (int)blockIdx.x; }
+  __device__ __forceinline__ int nctas() const { return (int)gridDim.x; }
+  __device__ __forceinline__ int wtid() const { return (int)threadIdx.x - 2 * 32; }
+  __device__ __forceinline__ int wwarp() const { return (int)(threadIdx.x >> 5) - 2; }
+  __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+  __device__ __forceinline__ float* red() const { return reinterpret_cast<float*>(jf_smem_base + kSmemRedOff); }
+  __device__ __forceinline__ uint8_t* attn_smem() const { return shared()->attn_smem; }
+  __device__ __forceinline__ int prof_on() const { return shared()->prof_on; }
+  __device__ __forceinline__ unsigned int tag() const { return shared()->tag; }
+};
 
-__device__ __forceinline__ void prof_mark(const DevCtx& c, const WorkerCtx& w, int id) {
-  if (w.prof_on && w.wtid == 0 && c.prof_marks != nullptr) {
+template <class W>
+__device__ __forceinline__ void prof_mark(const DevCtx& c, const W& w, int id) {
+  if (w.prof_on() && w.wtid() == 0 && c.prof_marks != nullptr) {
     // the running count lives in shared memory (a global counter costs an L2 round trip per mark: ~0.45 us measured);
     // it is published with the stage stamps when the profiled forward ends
-    int* cnt = reinterpret_cast<int*>(w.red) + 4;
+    int* cnt = reinterpret_cast<int*>(w.red()) + 4;
     const int n = *cnt;
     if (n + 2 <= 8192) { c.prof_marks[n] = id; c.prof_marks[n + 1] = clock64(); *cnt = n + 2; }
   }
@@ -154,11 +182,11 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
   const int nt_h = (h + 127) >> 7;
   const int NS = (nvec + kWorkerThreads - 1) / kWorkerThreads;     // slices per row (<= 8), one CTA each
   const int items = T * NS;
-  const int l16 = w.lane & 15;
+  const int l16 = w.lane() & 15;
   prof_mark(c, w, 200);
-  for (int item = w.cta; item < items; item += w.nctas) {
+  for (int item = w.cta(); item < items; item += w.nctas()) {
     const int t = item / NS, sl = item - t * NS;
-    const int v = sl * kWorkerThreads + w.wtid;
+    const int v = sl * kWorkerThreads + w.wtid();
     __nv_bfloat16* hrow = c.hidden + (size_t)t * h;
     float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, wt[8];
     if (v < nvec) {
@@ -201,9 +229,9 @@ __device__ __forceinline__ void rows_norm_impl(const DevCtx& c, const WorkerCtx&
     }
     prof_mark(c, w, 201);
     const float tile_ss = halfwarp_tree(sumsq8(x));                 // lanes past the row end contribute zeros
-    if (l16 == 0 && (v >> 4) < nt_h) publish_tile_ss(c, t, v >> 4, w.tag, tile_ss);
+    if (l16 == 0 && (v >> 4) < nt_h) publish_tile_ss(c, t, v >> 4, w.tag(), tile_ss);
     prof_mark(c, w, 202);
-    const float total = row_total_canonical(c, t, nt_h, w.tag, l16, true);
+    const float total = row_total_canonical(c, t, nt_h, w.tag(), l16, true);
     prof_mark(c, w, 203);
     if (v < nvec) {
       const float rstd = 1.0f / sqrtf(total / (float)h + c.md.eps);
@@ -269,7 +297,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
   constexpr int MW = kMaxHTiles / 16;                      // statistic words one lane may poll per row
   const int h = c.md.h;
   const int nt_h = (h + 127) >> 7;
-  const int l16 = w.lane & 15, hw = w.lane >> 4;
+  const int l16 = w.lane() & 15, hw = w.lane() >> 4;
   const int v = n_tile * 16 + l16;                       // 16-byte chunk of the row
   const bool cvalid = v < (h >> 3);
   const int nit = (T + 7) >> 3;
@@ -280,8 +308,8 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
   const int njt = (cnt + 7) >> 3;
   const size_t sstride = (size_t)h;                        // words between the k-split slices of a row
   const unsigned long long* tsrc = c.tpart_rs[which];
-  const int trow = w.wwarp * 2 + hw;                       // this half-warp's row inside a step
-  const unsigned long long tg = (unsigned long long)w.tag << 32;
+  const int trow = w.wwarp() * 2 + hw;                       // this half-warp's row inside a step
+  const unsigned long long tg = (unsigned long long)w.tag() << 32;
   uint4 wraw = make_uint4(0u, 0u, 0u, 0u);
   if (cvalid) wraw = __ldg(reinterpret_cast<const uint4*>(normw) + v);
   if (PUSH) {
@@ -290,7 +318,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
       const int t = it * 8 + trow;
       if (t < T && cvalid) {
         float sr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        poll_slices_add<SPLITS, false>(tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8, sstride, w.tag, sr);
+        poll_slices_add<SPLITS, false>(tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8, sstride, w.tag(), sr);
         const int owner = t % R, j = t / R;
         unsigned long long* dst = c.push_buf[owner] + ((size_t)j * R + me) * h + (size_t)v * 8;
 #pragma unroll
@@ -310,13 +338,13 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     if (live) {
       rr = ld_weak(reinterpret_cast<const uint4*>(c.hidden + (size_t)t * h) + v);
       if (!PUSH) {
-        poll_slices_add<SPLITS, false>(tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8, sstride, w.tag, acc);
+        poll_slices_add<SPLITS, false>(tsrc + ((size_t)t * c.part_splits) * h + (size_t)v * 8, sstride, w.tag(), acc);
       } else {                                              // rank order: deterministic, identical to rows_norm_impl
         const unsigned long long* p = c.push_buf[me] + ((size_t)j * R) * h + (size_t)v * 8;
-        if (R == 2) poll_slices_add<2, true>(p, sstride, w.tag, acc);
+        if (R == 2) poll_slices_add<2, true>(p, sstride, w.tag(), acc);
         else {
-          poll_slices_add<4, true>(p, sstride, w.tag, acc);
-          if (R == 8) poll_slices_add<4, true>(p + 4 * sstride, sstride, w.tag, acc);
+          poll_slices_add<4, true>(p, sstride, w.tag(), acc);
+          if (R == 8) poll_slices_add<4, true>(p + 4 * sstride, sstride, w.tag(), acc);
         }
       }
     }
@@ -327,7 +355,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     for (int e = 0; e < 8; ++e) x[e] = bf16_round(r[e] + bf16_round(acc[e]));
     if (live) reinterpret_cast<uint4*>(c.hidden + (size_t)t * h)[v] = pack8(x);
     const float tile_ss = halfwarp_tree(sumsq8(x));
-    if (l16 == 0 && j < cnt) publish_tile_ss(c, t, n_tile, w.tag, tile_ss);
+    if (l16 == 0 && j < cnt) publish_tile_ss(c, t, n_tile, w.tag(), tile_ss);
     prof_mark(c, w, 502);
   }
   // phase 2, four row steps at a time: the statistic words of all four rows are polled together (one round trip when
@@ -364,7 +392,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
         if (j < cnt) {
 #pragma unroll
           for (int m = 0; m < MW; ++m)
-            if (l16 + 16 * m < nt_h) ok = ok && tagged_ok(sw[q][m], w.tag);
+            if (l16 + 16 * m < nt_h) ok = ok && tagged_ok(sw[q][m], w.tag());
         }
       }
       if (ok) break;
@@ -423,7 +451,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
 #pragma unroll
           for (int k = 0; k < 4; ++k) wd[k] = ld_sys_poll_u64x2(sp + 2 * k);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[k].x, w.tag) && tagged_ok(wd[k].y, w.tag);
+          for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[k].x, w.tag()) && tagged_ok(wd[k].y, w.tag());
           if (ok) break;
           if (clock64() - t0 > JF_XSPIN_LIMIT_CYCLES) jf_trap_timeout();
         }
@@ -461,10 +489,10 @@ template <int SPLITS>
 __device__ __noinline__ void gu_swiglu_tail_impl(const DevCtx& c, const WorkerShared* ws, int T, int n_tile, int split) {
   const WorkerCtx w = load_wctx(ws);
   const int N = c.md.inter;
-  const int l16 = w.lane & 15, hw = w.lane >> 4;
+  const int l16 = w.lane() & 15, hw = w.lane() >> 4;
   const int n0 = n_tile * kTileN + l16 * 8;
   const int nit = (T + 7) >> 3;
-  const int trow = w.wwarp * 2 + hw;
+  const int trow = w.wwarp() * 2 + hw;
   if (n0 >= N) return;
   for (int it = split; it < nit; it += SPLITS) {
     const int t = it * 8 + trow;
@@ -484,7 +512,7 @@ __device__ __noinline__ void gu_swiglu_tail_impl(const DevCtx& c, const WorkerSh
 #pragma unroll
         for (int s2 = 0; s2 < SPLITS; ++s2)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag) && tagged_ok(wd[s2][k].y, w.tag);
+          for (int k = 0; k < 4; ++k) ok = ok && tagged_ok(wd[s2][k].x, w.tag()) && tagged_ok(wd[s2][k].y, w.tag());
         if (ok) break;
         if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
       }
@@ -562,15 +590,15 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
       const int t = item / nslots;
       if (tt[q] > 0) tt[q] = t;
       slot[q] = slot_base + item - t * nslots;
-      pos[q] = w.plan ? w.plan->row_pos[t] : ld_weak(&c.row_pos[t]);
-      p0[q] = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane * PPL;
+      pos[q] = w.plan() ? w.plan()->row_pos[t] : ld_weak(&c.row_pos[t]);
+      p0[q] = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane() * PPL;
     }
     if (TAGGED) {
       // fused tail: poll the tagged partial sums (2 * PPL words per item and split) until all of them are this stage's
       const unsigned long long* tp[2];
 #pragma unroll
       for (int q = 0; q < 2; ++q)
-        tp[q] = c.tpart + (size_t)(tt[q] < 0 ? 0 : tt[q]) * c.part_splits * c.part_n + slot[q] * d + w.lane * PPL;
+        tp[q] = c.tpart + (size_t)(tt[q] < 0 ? 0 : tt[q]) * c.part_splits * c.part_n + slot[q] * d + w.lane() * PPL;
       unsigned long long wl[2][SPLITS][PPL], wh[2][SPLITS][PPL];
       const long long t0 = clock64();
       for (;;) {
@@ -594,7 +622,7 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
           for (int s2 = 0; s2 < SPLITS; ++s2)
 #pragma unroll
             for (int j = 0; j < PPL; ++j)
-              ok = ok && (tt[q] < 0 || (tagged_ok(wl[q][s2][j], w.tag) && tagged_ok(wh[q][s2][j], w.tag)));
+              ok = ok && (tt[q] < 0 || (tagged_ok(wl[q][s2][j], w.tag()) && tagged_ok(wh[q][s2][j], w.tag())));
         if (ok) break;
         if (clock64() - t0 > JF_SPIN_LIMIT_CYCLES) jf_trap_timeout();
       }
@@ -652,7 +680,7 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
       else dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, t, slot[q] - md.n_q - md.n_kv);
 #pragma unroll
       for (int j = 0; j < PPL; ++j) {
-        const int e = w.lane * PPL + j;
+        const int e = w.lane() * PPL + j;
         float l = bf16_round(lo[q][j] + __ldg(bias + col0 + e));
         float hv = bf16_round(hi[q][j] + __ldg(bias + col0 + half + e));
         if (slot[q] < md.n_q + md.n_kv) {
@@ -673,7 +701,7 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
 __device__ __noinline__ void stage_qkv_rope(const DevCtx& c, const WorkerShared* ws, int T, int layer) {
   const WorkerCtx w = load_wctx(ws);
   const int splits = c.splits_qkv;
-  const int first = w.cta * 4 + w.wwarp, stride = w.nctas * 4, nslots = c.md.n_q + 2 * c.md.n_kv;
+  const int first = w.cta() * 4 + w.wwarp(), stride = w.nctas() * 4, nslots = c.md.n_q + 2 * c.md.n_kv;
 #define JF_ROPE_CASE(S)                                                                   \
   case S:                                                                                 \
     if (c.md.d == 128) qkv_rope_impl<S, 2, false>(c, w, T, layer, first, stride, 0, nslots); \
@@ -695,7 +723,7 @@ __device__ __noinline__ void qkv_rope_tail(const DevCtx& c, const WorkerShared* 
   const int slot_base = n_tile * hpt;
   const int nslots = min(hpt, c.md.n_q + 2 * c.md.n_kv - slot_base);
   if (nslots <= 0) return;
-  const int first = split * 4 + w.wwarp, stride = splits * 4;
+  const int first = split * 4 + w.wwarp(), stride = splits * 4;
 #define JF_ROPE_CASE(S)                                                                   \
   case S:                                                                                 \
     if (c.md.d == 128) qkv_rope_impl<S, 2, true>(c, w, T, layer, first, stride, slot_base, nslots); \
@@ -718,7 +746,7 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
                                int qs, int hs, bool prefetched, int hsplit) {
   constexpr int LDS = D + 8;                  // padded smem row (bf16 elements) -> conflict-free fragment loads
   constexpr int VPR = D / 8;                  // 16-byte chunks per row
-  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem);
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem());
   __nv_bfloat16* Vs = Ks + kAttnSub * LDS;
   const uint32_t ks_addr = smem_u32(Ks), vs_addr = smem_u32(Vs);
   const ModelDims& md = c.md;
@@ -735,7 +763,7 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
   const int nsub = (key_hi - key_lo + kAttnSub - 1) / kAttnSub;
   const int* bt = c.block_tables + (size_t)grp.seq * c.max_pages_per_seq;
   const float scale = rsqrtf((float)D);
-  const int r0 = w.lane >> 2, c2 = (w.lane & 3) * 2;
+  const int r0 = w.lane() >> 2, c2 = (w.lane() & 3) * 2;
 
   // K/V sub-tile fill: asynchronous 16-byte copies, one page-table lookup per 64-key sub-tile (kPage % kAttnSub == 0)
   // skip_committed: the committed keys of this sub-tile are already in flight / in place (attention_prefetch)
@@ -751,7 +779,7 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
                                      c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, row0, g_kvh)};
     const size_t srow = (size_t)md.n_kv * D;             // scratch stride between consecutive tokens
 #pragma unroll 4
-    for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
+    for (int idx = w.wtid(); idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
       const int kv = idx / (kAttnSub * VPR);
       const int rem = idx - kv * (kAttnSub * VPR);
       const int jr = rem / VPR, v = rem - jr * VPR;
@@ -792,7 +820,7 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
   };
   uint32_t qnx[D / 16][4];
   for (int tb = 0; tb * 4 < tiles; ++tb) {
-    const int tile = tb * 4 + w.wwarp;
+    const int tile = tb * 4 + w.wwarp();
     const bool tvalid = tile < tiles;
     const int j = j_lo + (tvalid ? tile / ntt : 0);
     const int tt = tvalid ? tile % ntt : 0;
@@ -832,7 +860,7 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
       float s[8][4];
       // K fragments with ldmatrix: matrix m of one x4 = keys nt*8..+7 (rows) x dims (ks2*32 + m*8)..+7, i.e. (b0, b1) of
       // k-steps 2*ks2 and 2*ks2+1 for n-tile nt
-      const uint32_t k_lane = ks_addr + (uint32_t)(((w.lane & 7) * LDS + (w.lane >> 3) * 8) * 2);
+      const uint32_t k_lane = ks_addr + (uint32_t)(((w.lane() & 7) * LDS + (w.lane() >> 3) * 8) * 2);
       // k-step outer, key tile inner: eight independent accumulator chains in flight (the mma latency, not its
       // issue rate, bounds a lone warp per scheduler)
 #pragma unroll
@@ -894,8 +922,8 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
         pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
         // V fragments with ldmatrix.trans: matrix m = keys kk*16 + (m&1)*8..+7 (rows) x dims (nd2*16 + (m>>1)*8)..+7,
         // transposed on load -> (b0, b1) of dim tiles 2*nd2 and 2*nd2+1 for key step kk
-        const uint32_t v_lane = vs_addr + (uint32_t)((((kk * 16 + (w.lane & 7) + ((w.lane >> 3) & 1) * 8) * LDS) +
-                                                     (w.lane >> 4) * 8) * 2);
+        const uint32_t v_lane = vs_addr + (uint32_t)((((kk * 16 + (w.lane() & 7) + ((w.lane() >> 3) & 1) * 8) * LDS) +
+                                                     (w.lane() >> 4) * 8) * 2);
         uint32_t vb[D / 16][4];
 #pragma unroll
         for (int nd2 = 0; nd2 < D / 16; ++nd2)
@@ -919,14 +947,14 @@ __device__ __forceinline__ void attention_unit(const DevCtx& c, const WorkerCtx&
         float* op = c.attn_o + sh * D + c2;
 #pragma unroll
         for (int nd = 0; nd < D / 8; ++nd) *reinterpret_cast<float2*>(op + nd * 8) = make_float2(o[nd][0], o[nd][1]);
-        if ((w.lane & 3) == 0) *reinterpret_cast<float2*>(c.attn_ml + sh * 2) = make_float2(m_a, l_a);
+        if ((w.lane() & 3) == 0) *reinterpret_cast<float2*>(c.attn_ml + sh * 2) = make_float2(m_a, l_a);
       }
       if (ib < len) {
         const size_t sh = ((size_t)(grp.slot0 + ib * grp.nchunks + chunk) * md.n_q + head);
         float* op = c.attn_o + sh * D + c2;
 #pragma unroll
         for (int nd = 0; nd < D / 8; ++nd) *reinterpret_cast<float2*>(op + nd * 8) = make_float2(o[nd][2], o[nd][3]);
-        if ((w.lane & 3) == 0) *reinterpret_cast<float2*>(c.attn_ml + sh * 2) = make_float2(m_b, l_b);
+        if ((w.lane() & 3) == 0) *reinterpret_cast<float2*>(c.attn_ml + sh * 2) = make_float2(m_b, l_b);
       }
     }
   }
@@ -945,12 +973,12 @@ struct AttnUnitId { Group grp; int kvh, hs, chunk, qs; };
 __device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, const WorkerCtx& w, int u, int G, int hsplit) {
   AttnUnitId id;
   int g = 0;
-  id.grp = w.plan ? w.plan->groups[0] : load_group(c, 0);
+  id.grp = w.plan() ? w.plan()->groups[0] : load_group(c, 0);
   while (g + 1 < G) {                                   // groups are few; linear scan over unit ranges
     const int per = c.md.n_kv * id.grp.nchunks * id.grp.qsplit * hsplit;
     if (u < id.grp.unit0 + per) break;
     ++g;
-    id.grp = w.plan ? w.plan->groups[g] : load_group(c, g);
+    id.grp = w.plan() ? w.plan()->groups[g] : load_group(c, g);
   }
   int local = u - id.grp.unit0;
   id.kvh = local % c.md.n_kv; local /= c.md.n_kv;
@@ -978,7 +1006,7 @@ constexpr uint32_t kTcQ = 0, kTcS = 64, kTcP = 128, kTcO = 256;     // tensor-me
 
 template <int D>
 __device__ __forceinline__ uint32_t tc_kv_base(const WorkerCtx& w) {
-  return (smem_u32(w.attn_smem) + 1023u) & ~1023u;
+  return (smem_u32(w.attn_smem()) + 1023u) & ~1023u;
 }
 // K (kv = 0) / V (kv = 1) tile address of 16-byte chunk `v` (8 dims) of key row `jr`
 template <int D>
@@ -1026,7 +1054,7 @@ __device__ __forceinline__ void attention_unit_tc(const DevCtx& c, const WorkerC
   const uint32_t base = tc_kv_base<D>(w);
   const uint32_t tm = ws->tmem_base;
   const int q = (int)(threadIdx.x >> 5) & 3;                 // TMEM lane quarter of this warp
-  const int lane_tm = q * 32 + w.lane;                       // TMEM lane = pair index inside a tile
+  const int lane_tm = q * 32 + w.lane();                       // TMEM lane = pair index inside a tile
   const uint32_t tq = tm + ((uint32_t)(q * 32) << 16);
   const float scale = rsqrtf((float)D);
   const int* bt = c.block_tables + (size_t)grp.seq * c.max_pages_per_seq;
@@ -1044,7 +1072,7 @@ __device__ __forceinline__ void attention_unit_tc(const DevCtx& c, const WorkerC
                                      c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 1, row0, g_kvh)};
     const size_t srow = (size_t)md.n_kv * D;
 #pragma unroll 4
-    for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
+    for (int idx = w.wtid(); idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
       const int kv = idx / (kAttnSub * VPR);
       const int rem = idx - kv * (kAttnSub * VPR);
       const int jr = rem / VPR, v = rem - jr * VPR;
@@ -1086,7 +1114,7 @@ __device__ __forceinline__ void attention_unit_tc(const DevCtx& c, const WorkerC
     fence_proxy_async_smem();                                // K / V written by this thread's copies -> async proxy (MMA)
     tc_fence_before();
     workers_sync();
-    if (w.wtid == 0) {                                       // S = Q K^T : M = 128 pairs, N = 64 keys, K = D dims
+    if (w.wtid() == 0) {                                       // S = Q K^T : M = 128 pairs, N = 64 keys, K = D dims
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, kAttnSub);
 #pragma unroll
@@ -1127,7 +1155,7 @@ __device__ __forceinline__ void attention_unit_tc(const DevCtx& c, const WorkerC
     }
     tc_fence_before();
     workers_sync();
-    if (w.wtid == 0) {                                       // O = P V : M = 128 pairs, N = D dims, K = 64 keys
+    if (w.wtid() == 0) {                                       // O = P V : M = 128 pairs, N = D dims, K = 64 keys
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16_bmn(128, D);
       constexpr uint32_t kTile = 64u * D * 2u;
@@ -1172,22 +1200,22 @@ __device__ __forceinline__ void attention_unit_tc(const DevCtx& c, const WorkerC
 // in-flight rows.  (The tile buffer is free: the previous attention stage and LM head ended grid barriers ago.)
 __device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerShared* ws, int layer, int G, int units, int hsplit) {
   const WorkerCtx w = load_wctx(ws);
-  if (w.cta >= units || !c.attn_prefetch) return;
-  const AttnUnitId id = decode_attn_unit(c, w, w.cta, G, hsplit);
+  if (w.cta() >= units || !c.attn_prefetch) return;
+  const AttnUnitId id = decode_attn_unit(c, w, w.cta(), G, hsplit);
   const ModelDims& md = c.md;
   const int D = md.d, LDS = D + 8, VPR = D >> 3;
   const int ctx = id.grp.ctx;
   const int k0 = id.chunk * c.attn_chunk;
   if (k0 >= ctx) return;
-  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem);
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(w.attn_smem());
   __nv_bfloat16* Vs = Ks + kAttnSub * LDS;
   const int page = ld_weak(c.block_tables + (size_t)id.grp.seq * c.max_pages_per_seq + (k0 / kPage));
   const __nv_bfloat16* cbase[2] = {c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 0, page, id.kvh, k0 % kPage),
                                    c.kv_cache + kv_cache_offset(md, c.num_pages, layer, 1, page, id.kvh, k0 % kPage)};
   const int nrow = min(kAttnSub, ctx - k0);
   const bool tc = c.attn_tc != 0 && c.attn_chunk == kAttnSub;
-  const uint32_t tbase = (smem_u32(w.attn_smem) + 1023u) & ~1023u;
-  for (int idx = w.wtid; idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
+  const uint32_t tbase = (smem_u32(w.attn_smem()) + 1023u) & ~1023u;
+  for (int idx = w.wtid(); idx < kAttnSub * VPR * 2; idx += kWorkerThreads) {
     const int kv = idx / (kAttnSub * VPR);
     const int rem = idx - kv * (kAttnSub * VPR);
     const int jr = rem / VPR, v = rem - jr * VPR;
@@ -1205,26 +1233,26 @@ __device__ __noinline__ void attention_prefetch(const DevCtx& c, const WorkerSha
 __device__ __noinline__ void stage_attention_tc(const DevCtx& c, WorkerShared* ws, int layer, int G, int units, int hsplit) {
   const WorkerCtx w = load_wctx(ws);
   uint32_t phase = ws->attn_phase;
-  for (int u = w.cta; u < units; u += w.nctas) {
+  for (int u = w.cta(); u < units; u += w.nctas()) {
     prof_mark(c, w, 398);
     const AttnUnitId id = decode_attn_unit(c, w, u, G, hsplit);
-    const bool pf = c.attn_prefetch && u == w.cta;
+    const bool pf = c.attn_prefetch && u == w.cta();
     prof_mark(c, w, 399);
     if (c.md.d == 128) attention_unit_tc<128>(c, w, ws, phase, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf, hsplit);
     else attention_unit_tc<64>(c, w, ws, phase, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf, hsplit);
     prof_mark(c, w, 403);
   }
   workers_sync();
-  if (w.wtid == 0) ws->attn_phase = phase;
+  if (w.wtid() == 0) ws->attn_phase = phase;
 }
 
 __device__ __noinline__ void stage_attention(const DevCtx& c, WorkerShared* ws, int layer, int G, int units, int hsplit) {
   if (c.attn_tc != 0 && c.attn_chunk == kAttnSub) { stage_attention_tc(c, ws, layer, G, units, hsplit); return; }
   const WorkerCtx w = load_wctx(ws);
-  for (int u = w.cta; u < units; u += w.nctas) {
+  for (int u = w.cta(); u < units; u += w.nctas()) {
     prof_mark(c, w, 398);
     const AttnUnitId id = decode_attn_unit(c, w, u, G, hsplit);
-    const bool pf = c.attn_prefetch && u == w.cta;
+    const bool pf = c.attn_prefetch && u == w.cta();
     prof_mark(c, w, 399);
     if (c.md.d == 128) attention_unit<128>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf, hsplit);
     else attention_unit<64>(c, w, layer, id.grp, id.kvh, id.chunk, id.qs, id.hs, pf, hsplit);
@@ -1256,9 +1284,9 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
   const int vpl = D >> 5;                                  // floats per lane: 4 (d=128) or 2 (d=64)
   const int items = T * md.n_q;
   const size_t cstride = md.n_q;                            // slots of consecutive chunks are adjacent
-  const int stride = w.nctas * 4;
+  const int stride = w.nctas() * 4;
   prof_mark(c, w, 300);
-  for (int item0 = w.cta * 4 + w.wwarp; item0 < items; item0 += 2 * stride) {
+  for (int item0 = w.cta() * 4 + w.wwarp(); item0 < items; item0 += 2 * stride) {
     int tt[2], hh[2], cmax[2];
     size_t base[2];
     float wl[2], ll[2];
@@ -1268,7 +1296,7 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
       tt[q] = -1; cmax[q] = -1; base[q] = 0; hh[q] = 0;
       if (item < items) {
         tt[q] = item / md.n_q; hh[q] = item - tt[q] * md.n_q;
-        const int2 ra = w.plan ? w.plan->row_attn[tt[q]] : ld_weak(&c.row_attn[tt[q]]);
+        const int2 ra = w.plan() ? w.plan()->row_attn[tt[q]] : ld_weak(&c.row_attn[tt[q]]);
         cmax[q] = ra.y;
         base[q] = (size_t)ra.x * md.n_q + hh[q];
       }
@@ -1277,7 +1305,7 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
 #pragma unroll
     for (int q = 0; q < 2; ++q) {                            // statistics of the first 32 chunks of both items
       float2 ml = make_float2(-INFINITY, 0.f);
-      if (tt[q] >= 0 && w.lane <= cmax[q]) ml = ld_weak(reinterpret_cast<const float2*>(c.attn_ml + (base[q] + w.lane * cstride) * 2));
+      if (tt[q] >= 0 && w.lane() <= cmax[q]) ml = ld_weak(reinterpret_cast<const float2*>(c.attn_ml + (base[q] + w.lane() * cstride) * 2));
       float mx = ml.x;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -1289,7 +1317,7 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
     const int cm0 = (tt[0] >= 0 && cmax[0] < 32) ? cmax[0] : -1;     // -1: nothing to do on the fast path
     const int cm1 = (tt[1] >= 0 && cmax[1] < 32) ? cmax[1] : -1;
     const int nmax = max(cm0, cm1) + 1;
-    const float* ob[2] = {c.attn_o + base[0] * D + w.lane * vpl, c.attn_o + base[1] * D + w.lane * vpl};
+    const float* ob[2] = {c.attn_o + base[0] * D + w.lane() * vpl, c.attn_o + base[1] * D + w.lane() * vpl};
     const size_t ostride = cstride * D;
     for (int cc = 0; cc < nmax; cc += 8) {
       // Loads are unconditional (chunk index clamped, weight zeroed) so the batch stays in registers and in flight.
@@ -1326,7 +1354,7 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
       if (cmax[q] >= 32) {                                   // long contexts: generic two-pass merge over all chunks
         float mg = -INFINITY;
         for (int c0 = 0; c0 <= cmax[q]; c0 += 32) {
-          const int ch = c0 + w.lane;
+          const int ch = c0 + w.lane();
           const float mc = (ch <= cmax[q]) ? ld_weak(c.attn_ml + (base[q] + ch * cstride) * 2) : -INFINITY;
           mg = fmaxf(mg, mc);
         }
@@ -1335,7 +1363,7 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
         float lg = 0.f;
         float ag[4] = {0.f, 0.f, 0.f, 0.f};
         for (int c0 = 0; c0 <= cmax[q]; c0 += 32) {
-          const int chl = c0 + w.lane;
+          const int chl = c0 + w.lane();
           float2 ml = make_float2(-INFINITY, 0.f);
           if (chl <= cmax[q]) ml = ld_weak(reinterpret_cast<const float2*>(c.attn_ml + (base[q] + chl * cstride) * 2));
           const float wq = (ml.x == -INFINITY) ? 0.f : __expf(ml.x - mg);
@@ -1344,7 +1372,7 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
           for (int u = 0; u < nch; ++u) {
             const float wgt = __shfl_sync(0xffffffffu, wq, u);
             lg += __shfl_sync(0xffffffffu, lq, u);
-            const float* op = c.attn_o + (base[q] + (size_t)(c0 + u) * cstride) * D + w.lane * vpl;
+            const float* op = c.attn_o + (base[q] + (size_t)(c0 + u) * cstride) * D + w.lane() * vpl;
             if (vpl == 4) {
               const float4 v = ld_weak(reinterpret_cast<const float4*>(op));
               ag[0] += wgt * v.x; ag[1] += wgt * v.y; ag[2] += wgt * v.z; ag[3] += wgt * v.w;
@@ -1354,9 +1382,9 @@ __device__ __noinline__ void stage_attn_combine(const DevCtx& c, const WorkerSha
             }
           }
         }
-        combine_store(c, tt[q], hh[q], w.lane, vpl, D, ag, lg);
+        combine_store(c, tt[q], hh[q], w.lane(), vpl, D, ag, lg);
       } else {
-        combine_store(c, tt[q], hh[q], w.lane, vpl, D, acc[q], l[q]);
+        combine_store(c, tt[q], hh[q], w.lane(), vpl, D, acc[q], l[q]);
       }
     }
   }
@@ -1369,7 +1397,7 @@ __device__ __noinline__ void stage_commit(const DevCtx& c, const WorkerShared* w
   const int per = md.layers * 2;
   const int items = n_commit * per;
   const int vpr = md.d >> 3;
-  for (int item = w.cta * 4 + w.wwarp; item < items; item += w.nctas * 4) {
+  for (int item = w.cta() * 4 + w.wwarp(); item < items; item += w.nctas() * 4) {
     const int e = item / per, lk = item - e * per;
     const int layer = lk >> 1, kv = lk & 1;
     const int src_row = ld_weak(&c.commits[e].src_row);
@@ -1379,7 +1407,7 @@ __device__ __noinline__ void stage_commit(const DevCtx& c, const WorkerShared* w
     for (int kvh = 0; kvh < md.n_kv; ++kvh) {
       const uint4* src = reinterpret_cast<const uint4*>(c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, kv, src_row, kvh));
       uint4* dst = reinterpret_cast<uint4*>(c.kv_cache + kv_cache_offset(md, c.num_pages, layer, kv, page, kvh, pos % kPage));
-      for (int v = w.lane; v < vpr; v += 32) dst[v] = ld_weak(src + v);
+      for (int v = w.lane(); v < vpr; v += 32) dst[v] = ld_weak(src + v);
     }
   }
 }
