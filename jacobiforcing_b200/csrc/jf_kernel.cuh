@@ -11,8 +11,11 @@
 
 namespace jf {
 
+// fence = false: the caller reads what the counter publishes ONLY through the async proxy (bulk copies served by L2, never
+// by this SM's L1) and issues those copies after the successful probe, so it needs neither the L1 invalidation nor the
+// ordering of the acquire fence
 template <bool kSleep = true>
-__device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned int target, bool sys = false) {
+__device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned int target, bool sys = false, bool fence = true) {
   if (ld_relaxed_gpu_u32(counter) < target) {
     const long long t0 = clock64();
     while (ld_relaxed_gpu_u32(counter) < target) {
@@ -23,6 +26,7 @@ __device__ __forceinline__ void wait_epoch(const unsigned int* counter, unsigned
   // one acquire (one L1 invalidation) per barrier, not one per probe; system scope when the data published before the
   // barrier may have been written by a tensor-parallel peer (finished rows copied out of the staging buffer are local
   // writes, but the flag barriers of the prefill path order peer reads)
+  if (!fence) return;
   if (sys) fence_acq_rel_sys(); else fence_acq_rel_gpu();
 }
 
@@ -323,15 +327,18 @@ __device__ void run_role(uint8_t* tiles, int ring_bytes, int run_mode, int max_f
       if (c.debug_skip & 16) wait_epoch(c.bar_counter, bs.target(nctas));   // experiment: no run-ahead
       gemm_produce_w(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, c.w_evict_first != 0, w_policy);
     } else if (ROLE == ROLE_X) {
+      // the X producer reads its operand only with bulk copies: no acquire fence, no proxy fence on this side (the writers
+      // fenced generic -> async before they released the counter); JF_X_FENCE=1 restores both
+      const bool xf = c.x_fence != 0;
       if (!df_wait) {
-        wait_epoch(c.bar_counter, bs.target(nctas));
+        wait_epoch(c.bar_counter, bs.target(nctas), false, xf);
       } else if (cta < t.n_tiles * t.splits) {
         // dataflow: the gate/up tiles whose features are this unit's k-range (tile j holds k-chunks 2j, 2j+1)
         const UnitRange r = unit_range(t, cta);
         const unsigned int need = (unsigned int)df_tiles_needed(r.k0, r.k1);
-        wait_epoch(c.tile_ctr + r.split, df_uses * need);
+        wait_epoch(c.tile_ctr + r.split, df_uses * need, false, xf);
       }
-      fence_proxy_async_all();
+      if (xf) fence_proxy_async_all();
       gemm_produce_x(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe);
     } else if (ROLE == ROLE_MMA) {
       gemm_issue_mma(t, gs, tiles, nstages, slot_bytes, cta, nctas, pipe, acc);

@@ -593,6 +593,25 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
       pos[q] = w.plan() ? w.plan()->row_pos[t] : ld_weak(&c.row_pos[t]);
       p0[q] = c.part + (size_t)t * c.part_splits * c.part_n + slot[q] * d + w.lane() * PPL;
     }
+    // bias and rotary factors do not depend on the projection: fetched BEFORE the partial sums are polled (one L2 round trip less)
+    float bl[2][PPL], bh[2][PPL], rc[2][PPL], rs[2][PPL];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int col0 = slot[q] * d;
+      int p = pos[q];
+      p = p < 0 ? 0 : (p >= md.max_pos ? md.max_pos - 1 : p);
+#pragma unroll
+      for (int j = 0; j < PPL; ++j) {
+        const int e = w.lane() * PPL + j;
+        bl[q][j] = __ldg(bias + col0 + e);
+        bh[q][j] = __ldg(bias + col0 + half + e);
+        rc[q][j] = 1.f; rs[q][j] = 0.f;
+        if (slot[q] < md.n_q + md.n_kv) {
+          rc[q][j] = __bfloat162float(__ldg(c.rope_cos + (size_t)p * half + e));
+          rs[q][j] = __bfloat162float(__ldg(c.rope_sin + (size_t)p * half + e));
+        }
+      }
+    }
     if (TAGGED) {
       // fused tail: poll the tagged partial sums (2 * PPL words per item and split) until all of them are this stage's
       const unsigned long long* tp[2];
@@ -672,8 +691,6 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
     for (int q = 0; q < 2; ++q) {
       if (tt[q] < 0) continue;
       const int t = tt[q], col0 = slot[q] * d;
-      int p = pos[q];
-      p = p < 0 ? 0 : (p >= md.max_pos ? md.max_pos - 1 : p);
       __nv_bfloat16* dst;
       if (slot[q] < md.n_q) dst = c.qbuf + (size_t)t * md.q_dim + col0;
       else if (slot[q] < md.n_q + md.n_kv) dst = c.kv_scratch + kv_scratch_offset(md, c.T_cap, layer, 0, t, slot[q] - md.n_q);
@@ -681,11 +698,10 @@ __device__ __forceinline__ void qkv_rope_impl(const DevCtx& c, const WorkerCtx& 
 #pragma unroll
       for (int j = 0; j < PPL; ++j) {
         const int e = w.lane() * PPL + j;
-        float l = bf16_round(lo[q][j] + __ldg(bias + col0 + e));
-        float hv = bf16_round(hi[q][j] + __ldg(bias + col0 + half + e));
+        float l = bf16_round(lo[q][j] + bl[q][j]);
+        float hv = bf16_round(hi[q][j] + bh[q][j]);
         if (slot[q] < md.n_q + md.n_kv) {
-          const float cs = __bfloat162float(__ldg(c.rope_cos + (size_t)p * half + e));
-          const float sn = __bfloat162float(__ldg(c.rope_sin + (size_t)p * half + e));
+          const float cs = rc[q][j], sn = rs[q][j];
           const float nlo = bf16_round(bf16_round(l * cs) - bf16_round(hv * sn));
           const float nhi = bf16_round(bf16_round(hv * cs) + bf16_round(l * sn));
           l = nlo; hv = nhi;
