@@ -478,7 +478,17 @@ __device__ void run_role(uint8_t* tiles, int ring_bytes, int run_mode, int max_f
         for (int t = w.wtid(); t < T; t += kWorkerThreads) { pc->row_pos[t] = ld_weak(&c.row_pos[t]); pc->row_attn[t] = ld_weak(&c.row_attn[t]); }
         for (int g = w.wtid(); g < ip.G; g += kWorkerThreads) pc->groups[g] = load_group(c, g);
       }
-      if (w.wtid() == 0) ws->plan_ok = ok;
+      if (w.wtid() == 0) {
+        ws->plan_ok = ok;
+        PlanCache* pc = ws->plan;
+        pc->first_unit_ok = 0;
+        if (ok && cta < ip.attn_units) {       // decoded from the global plan: the shared copy is still being filled
+          WorkerCtx wc = load_wctx(ws);
+          wc.plan_ = nullptr;
+          pc->first_unit = decode_attn_unit(c, wc, cta, ip.G, ip.hsplit);
+          pc->first_unit_ok = 1;
+        }
+      }
     }
     slot_bytes = gemm_slot_bytes(min(kMaxRowsMMA, round_up16(T)));
     nstages = min(kMaxStages, ring_bytes / slot_bytes);

@@ -42,10 +42,13 @@ struct WorkerCtx {
 // Per-forward copy of the small plan arrays every layer's stages index (row positions, attention slots, groups): read
 // from global memory they cost an L2 round trip per stage and layer; filled once per forward by the worker warps.
 constexpr int kPlanRows = 64, kPlanGroups = 8;
+struct AttnUnitId { Group grp; int kvh, hs, chunk, qs; };
 struct PlanCache {
   int row_pos[kPlanRows];
   int2 row_attn[kPlanRows];
   Group groups[kPlanGroups];
+  AttnUnitId first_unit;     // this CTA's first attention unit, decoded once per forward (every layer runs the same units)
+  int first_unit_ok;
 };
 struct WorkerShared {
   float* red;
@@ -985,8 +988,8 @@ __device__ __forceinline__ Group load_group(const DevCtx& c, int g) {
   return grp;
 }
 
-struct AttnUnitId { Group grp; int kvh, hs, chunk, qs; };
 __device__ __forceinline__ AttnUnitId decode_attn_unit(const DevCtx& c, const WorkerCtx& w, int u, int G, int hsplit) {
+  if (u == w.cta() && w.plan() && w.plan()->first_unit_ok) return w.plan()->first_unit;
   AttnUnitId id;
   int g = 0;
   id.grp = w.plan() ? w.plan()->groups[0] : load_group(c, 0);

@@ -1,0 +1,8 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_engine_api.py -x -q 2>&1 | tail -3 > gpurun_out/s3_tests11.txt; tail -3 gpurun_out/s3_tests11.txt
+for i in 1 2; do
+python bench.py --no-cpu-baseline --steps 3 --warmup 3 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('new', d['value'], d['roofline']['ms_per_forward'])"
+done
+python bench.py --no-cpu-baseline --mode multiblock --batch 8 --steps 2 --warmup 3 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('b8', d['value'], d['roofline']['ms_per_forward'])"
+JF_PROF_MARKS=gpurun_out/s3_marks11_n1.txt python tools/stage_profile.py --gen 64 > gpurun_out/s3_stage11_n1.txt 2>&1; tail -12 gpurun_out/s3_stage11_n1.txt | head -9
+python tools/prof_marks2.py gpurun_out/s3_marks11_n1.txt 1860 | head -4
