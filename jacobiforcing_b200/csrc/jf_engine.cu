@@ -319,6 +319,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     c.attn_tc = e10 ? atoi(e10) : 0;
     const char* e5 = getenv("JF_FUSE_NORM");
     c.fuse_norm = e5 ? atoi(e5) : 1;
+    const char* e15 = getenv("JF_EARLY_FENCE");
+    c.early_fence = e15 ? atoi(e15) : 1;
     const char* e13 = getenv("JF_X_FENCE");
     c.x_fence = e13 ? atoi(e13) : 0;
     const char* e12 = getenv("JF_SWIGLU_BULK");

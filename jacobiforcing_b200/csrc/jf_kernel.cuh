@@ -69,7 +69,16 @@ __device__ __forceinline__ void grid_barrier(const DevCtx& c, const WorkerView& 
       fence_acq_rel_sys();
       red_release_gpu_add_u32(c.bar_counter, 1u);              // the extra arrival releases this GPU's CTAs
     }
-    wait_epoch<false>(c.bar_counter, bs.target(w.nctas()), xgpu);      // critical path: spin, do not sleep
+    if (c.early_fence && !xgpu) {
+      // The acquire fence's job here is to drop this SM's L1 copies of what other CTAs wrote during the stage.  Issued right
+      // behind the arrival it costs its L2 round trip while the other CTAs are still arriving, instead of after the last
+      // of them: no worker thread of this CTA loads anything between here and the release (they are parked at the named
+      // barrier below, the probes bypass L1), so L1 cannot pick the stale lines up again before the counter completes
+      fence_acq_rel_gpu();
+      wait_epoch<false>(c.bar_counter, bs.target(w.nctas()), false, false);
+    } else {
+      wait_epoch<false>(c.bar_counter, bs.target(w.nctas()), xgpu);    // critical path: spin, do not sleep
+    }
     if (prof_act) {                                       // (stage id, arrival of CTA 0, release of the barrier)
       const int prof_n = w.shared()->prof_n;
       if (prof_n + 3 <= c.prof_cap) {

@@ -198,6 +198,7 @@ struct alignas(16) DevCtx {
   int w_evict_first;                 // 1: weight tiles are streamed with the L2 evict_first hint (see jf_ptx.cuh)
   int attn_prefetch;                 // 1: committed K/V of each CTA's first attention unit is fetched during the QKV GEMM
   volatile int* dbg;                 // developer aid: host-mapped progress words (survive a trapped launch)
+  int early_fence;                   // 1: the grid barrier's acquire fence is issued behind the arrival, not behind the release
   int x_fence;                       // 1: the activation producer fences (acquire + proxy) after every barrier it waits on
   int swiglu_bulk;                   // 1: the SwiGLU epilogue stages its tile in shared memory and stores it with bulk copies
   int attn_tc;                       // 1: attention on the tcgen05 tensor cores (TMEM-staged Q / P, MN-major V); 0: mma.sync
