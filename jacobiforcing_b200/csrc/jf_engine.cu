@@ -323,6 +323,8 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     c.early_fence = e15 ? atoi(e15) : 1;
     const char* e13 = getenv("JF_X_FENCE");
     c.x_fence = e13 ? atoi(e13) : 0;
+    const char* e16 = getenv("JF_EPI_BULK");
+    c.epi_bulk = e16 ? atoi(e16) : 1;
     const char* e12 = getenv("JF_SWIGLU_BULK");
     c.swiglu_bulk = e12 ? atoi(e12) : 1;
   }

@@ -66,6 +66,7 @@ struct GemmTask {
   int out_rows_cap;          // SWIGLU: xrows_cap of the destination packed buffer
   int index_offset;          // ARGMAX: added to the local feature index (vocabulary slice of this rank)
   unsigned int tag;          // PARTIAL_TAGGED: stage tag stored with every partial sum
+  int bulk_rows;             // PARTIAL_TAGGED: 1 = the tile's rows leave through shared memory, one 1 KiB bulk store per row
   // ---- SAMPLE: everything else the sampling epilogue needs (temperature, generator key, row tables, accumulators) is read
   // from the kernel context, so the task stays small (it is rebuilt by every role at every stage)
   const DevCtx* sample_ctx;
@@ -85,6 +86,7 @@ struct GemmSmem {
   long long t_acc_full;       // developer aid: clock of the first accumulator hand-over of the last GEMM stage
   unsigned long long* best;   // [4][kArgmaxRows] EPI_ARGMAX running best key per epilogue warp and row (aliases
                               // the attention tile buffer: the LM head never overlaps an attention stage)
+  int tag_stage_rows;         // rows of a [rows][128] tile of tagged 64-bit words that fit the same buffer (0 = disabled)
   int stage_rows;             // rows of a [2][rows][128 B] staging tile that fit the same buffer (EPI_SWIGLU_BF16 bulk
                               // stores; 0 = disabled): the MLP never overlaps an attention stage either
 };
@@ -346,6 +348,37 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
             st_pred_f32(out + (size_t)m * t.out_row_stride + n, __uint_as_float(v[j]), nvalid && c0 + j < mlive);
           }
         }
+      } else if (t.epilogue == EPI_PARTIAL_TAGGED && t.bulk_rows && mpad <= gs->tag_stage_rows && (t.N & 127) == 0) {
+        // The tagged partial sums of the tile go through shared memory ([row][128 features] 64-bit words) and leave as one
+        // 1 KiB bulk store per row, issued by 32 different threads: the epilogue's issue time shrinks from 32 scattered
+        // 8-byte stores per thread to 8 shared-memory stores per 8 rows, and the words land together.  The consumers poll
+        // the tags as before, so nobody waits for the copies here (the caller waits for their READ side before the buffer
+        // is reused).
+        unsigned long long* stg = gs->best;
+        const unsigned long long tg = (unsigned long long)t.tag << 32;
+        named_bar_sync(1, kWorkerThreads);                 // earlier users of the buffer (this CTA) are done with it
+#pragma unroll 1
+        for (int c0 = 0; c0 < mpad; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) stg[(size_t)(c0 + j) * kTileN + feat_in_tile] = tg | (unsigned long long)v[j];
+        }
+        tc_fence_before();
+        mbar_arrive(&gs->acc_empty[acc.buf]);
+        fence_proxy_async_smem();
+        named_bar_sync(1, kWorkerThreads);
+        const int i = (int)threadIdx.x - 2 * 32;
+        if (i < mlive) {
+          unsigned long long* out = reinterpret_cast<unsigned long long*>(t.out) + (size_t)r.split * t.out_split_stride +
+                                    (size_t)(t.x_row0 + m0 + i) * t.out_row_stride + (size_t)r.n_tile * kTileN;
+          bulk_s2g(out, stg + (size_t)i * kTileN, kTileN * 8);
+          bulk_commit();
+        }
+        if (u + nctas < units || mt + 1 < m_tiles) { bulk_wait_read_all(); }   // (the sync at the top of the next pass follows)
+        acc.advance();
+        continue;
       } else if (t.epilogue == EPI_PARTIAL_TAGGED) {
         unsigned long long* out = reinterpret_cast<unsigned long long*>(t.out) + (size_t)r.split * t.out_split_stride;
         const unsigned long long tg = (unsigned long long)t.tag << 32;

@@ -392,6 +392,7 @@ __device__ void run_role(uint8_t* tiles, int ring_bytes, int run_mode, int max_f
                             fuse_kind == 1 ? c.tp_attn > 1 : c.tp_size > 1);
       }
     }
+    if (ROLE == ROLE_WORKER && t.bulk_rows) bulk_wait_read_all();   // the staging tile (attention buffer) may be rewritten
     if (barrier_after) {
       if (ROLE == ROLE_WORKER)
         grid_barrier(c, w, bs, true, t.epilogue == EPI_SWIGLU_BF16 || fuse_kind == 1 || fuse_kind == 2 || fuse_kind == 4, xgpu, stage_id);
@@ -516,7 +517,7 @@ __device__ void run_role(uint8_t* tiles, int ring_bytes, int run_mode, int max_f
 
     auto base_task = [&]() {
       GemmTask t;
-      t.tag = 0u;
+      t.tag = 0u; t.bulk_rows = 0;
       t.M = T; t.x_row0 = 0; t.xrows_cap = c.xrows_cap; t.out_rows_cap = c.xrows_cap; t.index_offset = 0;
       t.out_row_stride = c.part_splits * c.part_n; t.out_split_stride = c.part_n;
       return t;
@@ -538,7 +539,7 @@ __device__ void run_role(uint8_t* tiles, int ring_bytes, int run_mode, int max_f
       GemmTask t = base_task();
       t.W = c.layer[l].wo; t.X = c.xa; t.out = c.part_rs[which_o()]; t.n_tiles = nt_h; t.k_chunks = kc_q; t.splits = c.splits_o;
       t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
-      if (fused) { t.out = c.tpart_rs[0]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; }
+      if (fused) { t.out = c.tpart_rs[0]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; t.bulk_rows = c.epi_bulk; }
       return t;
     };
     auto task_gu = [&](int l, bool fused = false) {       // gate/up projection with the SwiGLU epilogue
@@ -555,7 +556,7 @@ __device__ void run_role(uint8_t* tiles, int ring_bytes, int run_mode, int max_f
       GemmTask t = base_task();
       t.W = c.layer[l].wd; t.X = c.xact; t.out = c.part_rs[which_d(l)]; t.n_tiles = nt_h; t.k_chunks = kc_i; t.splits = c.splits_down;
       t.N = md.h; t.epilogue = EPI_PARTIAL_F32; t.out_row_stride = c.part_splits * md.h; t.out_split_stride = md.h;
-      if (fused) { t.out = c.tpart_rs[1]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; }
+      if (fused) { t.out = c.tpart_rs[1]; t.epilogue = EPI_PARTIAL_TAGGED; t.tag = c.tag_base + bs.epoch + 1u; t.bulk_rows = c.epi_bulk; }
       return t;
     };
     auto task_lm = [&](int i) {
@@ -654,6 +655,7 @@ jf_persistent_kernel(const DevCtx* __restrict__ ctxp, int smem_total, int run_mo
   if (threadIdx.x == 0) {
     gs->best = reinterpret_cast<unsigned long long*>(attn);
     gs->stage_rows = c.swiglu_bulk ? ((attn_bytes / 256) & ~15) : 0;
+    gs->tag_stage_rows = c.epi_bulk ? ((attn_bytes / (kTileN * 8)) & ~15) : 0;
   }
   const uint32_t base_addr = smem_u32(smem);     // the ring must be 1024-byte aligned in the shared window (sw128)
   const size_t tiles_off = (((size_t)base_addr + (size_t)(attn - smem) + attn_bytes + 1023) & ~(size_t)1023) - base_addr;

@@ -117,6 +117,8 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // every bulk group of this thread has COMPLETED (its writes are performed), not merely read its source
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// every bulk group of this thread has finished READING its shared-memory source (the source may be rewritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // Ampere-style 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");

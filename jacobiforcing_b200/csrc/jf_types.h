@@ -200,6 +200,7 @@ struct alignas(16) DevCtx {
   volatile int* dbg;                 // developer aid: host-mapped progress words (survive a trapped launch)
   int early_fence;                   // 1: the grid barrier's acquire fence is issued behind the arrival, not behind the release
   int x_fence;                       // 1: the activation producer fences (acquire + proxy) after every barrier it waits on
+  int epi_bulk;                      // 1: the O / down epilogues store their tagged partial sums row by row with bulk copies
   int swiglu_bulk;                   // 1: the SwiGLU epilogue stages its tile in shared memory and stores it with bulk copies
   int attn_tc;                       // 1: attention on the tcgen05 tensor cores (TMEM-staged Q / P, MN-major V); 0: mma.sync
 };
