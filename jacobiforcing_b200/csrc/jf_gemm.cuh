@@ -383,12 +383,13 @@ __device__ __forceinline__ void gemm_epilogue(const GemmTask& t, GemmSmem* gs, i
         unsigned long long* out = reinterpret_cast<unsigned long long*>(t.out) + (size_t)r.split * t.out_split_stride;
         const unsigned long long tg = (unsigned long long)t.tag << 32;
         const bool nvalid = n < t.N;
-        for (int c0 = 0; c0 < mpad; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
+#pragma unroll 1
+        for (int c0 = 0; c0 < mpad; c0 += 8) {             // a short rolled body: this code runs once per stage, cold
+          uint32_t v[8];
+          tmem_ld8(taddr + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const int m = t.x_row0 + m0 + c0 + j;
             st_pred_u64(out + (size_t)m * t.out_row_stride + n, tg | (unsigned long long)v[j], nvalid && c0 + j < mlive);
           }
