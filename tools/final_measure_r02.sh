@@ -1,4 +1,4 @@
-# round-2 end-of-round measurement batch (GPU box, 1 GPU): tests, smoke, bench (ours + reference arm), stage profile,
+# round-2 end-of-round measurement batch (GPU box, 1 GPU): tests, smoke, bench (ours + reference arm), stage profile + marks,
 # ncu launch list + full capture, batch-8 and 0.5B configurations; outputs under gpurun_out/
 set -x
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/r02_gputests_final.txt; cat gpurun_out/r02_gputests_final.txt
