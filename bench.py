@@ -307,6 +307,35 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "iters_per_seq": [r.total_iterations for r in results],
                 "stop": [r.stop_reason for r in results]}
 
+    # Tensor-parallel self-check on the engine about to be timed (untimed): a short greedy generation decoded
+    # autoregressively (n = 1) and by Jacobi iteration (n = 8, n = args.n) must give the SAME ids (exact on this engine:
+    # attention chunks are aligned to absolute key positions), and every rank of the group must return the same ids,
+    # iteration counts and forward counts - the ranks run the policy independently on keys merged over NVLink peer memory.
+    tp_check = None
+    if tp > 1:
+        from jacobiforcing_b200.runtime import hf_generate
+        runs = {}
+        m_chk = max(4, min(16, rt.max_calls - 2))        # n = 1 needs one call per token
+        for nn in (1, 8, n):
+            seqs_c, res_c, run_c = hf_generate(rt, [prompts[0][:64]], n=nn, max_new_tokens=m_chk, mode="single", pad=0,
+                                               rngs=[random.Random(7)])
+            runs[nn] = (res_c[0].tokens[:m_chk], list(res_c[0].iters), int(run_c["forwards"]))
+            for s_c in seqs_c:
+                rt.release(s_c)
+        gathered = [None] * tp
+        dist.all_gather_object(gathered, runs, group=tp_group)
+        ok_ar = runs[1][0] == runs[8][0] == runs[n][0]
+        ok_ranks = all(g2 == gathered[0] for g2 in gathered)
+        flags = torch.tensor([1.0 if ok_ar else 0.0, 1.0 if ok_ranks else 0.0], device=device)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        tp_check = {"jacobi_equals_ar": bool(flags[0] > 0), "ranks_identical": bool(flags[1] > 0), "tokens": m_chk,
+                    "block_sizes": [1, 8, n], "forwards": [runs[1][2], runs[8][2], runs[n][2]],
+                    "what": f"{m_chk} greedy tokens from a 64-token prompt on the timed tensor-parallel engine: AR == Jacobi(8) == "
+                            f"Jacobi({n}) ids, and ids / per-call iterations / forward counts identical on all {tp} ranks of "
+                            "every group (min over all ranks)"}
+        if not (tp_check["jacobi_equals_ar"] and tp_check["ranks_identical"]):
+            raise SystemExit(f"tensor-parallel self-check failed: {tp_check}")
+
     for i in range(args.warmup):
         one_step(i)
     if world > 1:
@@ -418,6 +447,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "timed_region_wall_s": t_total,
     }
+    if tp_check is not None:
+        line["tp_check"] = tp_check
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
