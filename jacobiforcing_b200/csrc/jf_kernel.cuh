@@ -373,7 +373,7 @@ __device__ void run_role(uint8_t* tiles, int ring_bytes, int run_mode, int max_f
           const unsigned int df_mask = ws->df_mask;
           if (bulk) {
             prof_mark(c, w, 605);
-            if (!(c.debug_skip & 32768)) fence_acq_rel_gpu();
+            fence_acq_rel_gpu();
             prof_mark(c, w, 607);
             for (int s2 = 0; s2 < c.splits_down; ++s2)
               if ((df_mask >> s2) & 1u) red_relaxed_gpu_add_u32(c.tile_ctr + s2, 1u);

@@ -326,3 +326,48 @@ def test_fused_tails_equal_standalone_stages_bitwise(monkeypatch, gen_kw):
     # hidden 1024: logits reach |6|, one bf16 ulp there is 0.03; tolerance relative to what the HF bf16 forward achieves
     assert err.mean() <= 1.5 * err16.mean() + 1e-4
     assert err.max() <= max(LOGIT_MAX_TOL, 1.5 * err16.max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# epilogues through shared memory + bulk stores, fence placement: the same bits as the direct-store / textbook variants
+# ---------------------------------------------------------------------------------------------------------------
+def _run_switches(monkeypatch, shape, env, rows_list, gen_kw):
+    import random
+    from tests.gpu_helpers import make_pair
+    from jacobiforcing_b200.runtime import hf_generate
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)                              # read once, when the engine is created
+    model, rt = make_pair(shape)
+    out = {"logits": []}
+    for rows in rows_list:
+        ids = _prompt(model, rows, seed=11)
+        seq = rt.new_sequence()
+        rt.ensure_capacity(seq, len(ids))
+        res = rt.forward(ids, [(0, len(ids), 0, 0)], [seq], 0, len(ids), want_logits=True)
+        out["logits"].append(res["logits"].copy())
+        rt.release(seq)
+    prompt = _prompt(model, 40, seed=5)
+    seqs, results, run = hf_generate(rt, [prompt], rngs=[random.Random(7)], pad=0, **gen_kw)
+    out["tokens"], out["iters"], out["forwards"] = list(results[0].tokens), list(results[0].iters), run["forwards"]
+    for s_ in seqs:
+        rt.release(s_)
+    rt.close()
+    return out
+
+
+@pytest.mark.parametrize("shape,common", [("tiny128", {}), ("mid128", {}), ("mid128", {"JF_GU_SPLITS": "1"})])
+def test_bulk_epilogues_and_fence_placement_do_not_change_a_bit(monkeypatch, shape, common):
+    """Defaults (SwiGLU tile and O / down partial sums leave through shared memory + bulk copies, acquire fence behind the
+    barrier arrival, fence-less activation producer) against JF_SWIGLU_BULK=0 JF_EPI_BULK=0 JF_EARLY_FENCE=0 JF_X_FENCE=1:
+    logits of 1 .. 100-row forwards (<= 32 rows: bulk row stores; <= 128: bulk SwiGLU tile) and a generation, bit for bit.
+    JF_GU_SPLITS=1 forces the single-accumulator-pair gate/up projection (the 7B layout: SwiGLU in the epilogue, gate/up -> down
+    hand-over by arrival counters) on the small shape, whose default is the split-K gate/up + SwiGLU tail."""
+    rows_list = [1, 7, 16, 24, 32, 40, 64, 100]
+    gen_kw = dict(n=16, max_new_tokens=48, mode="multiblock", K=2, r=0.85, n_gram_pool_size=4)
+    a = _run_switches(monkeypatch, shape, dict(common, JF_SWIGLU_BULK="1", JF_EPI_BULK="1", JF_EARLY_FENCE="1", JF_X_FENCE="0"),
+                      rows_list, gen_kw)
+    b = _run_switches(monkeypatch, shape, dict(common, JF_SWIGLU_BULK="0", JF_EPI_BULK="0", JF_EARLY_FENCE="0", JF_X_FENCE="1"),
+                      rows_list, gen_kw)
+    for rows, la, lb in zip(rows_list, a["logits"], b["logits"]):
+        assert np.array_equal(la.view(np.uint32), lb.view(np.uint32)), f"logits differ at {rows} rows"
+    assert a["tokens"] == b["tokens"] and a["iters"] == b["iters"] and a["forwards"] == b["forwards"]
