@@ -10,6 +10,7 @@
 // Rounding points follow the HF bf16 modules: linear outputs, RMSNorm (fp32 statistics, bf16
 // normalised value times bf16 weight), rotary products and sums, residual adds are each rounded to bf16.
 #pragma once
+#include <type_traits>
 #include "jf_types.h"
 #include "jf_gemm.cuh"
 
@@ -361,16 +362,20 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     if (l16 == 0 && j < cnt) publish_tile_ss(c, t, n_tile, w.tag(), tile_ss);
     prof_mark(c, w, 502);
   }
-  // phase 2, four row steps at a time: the statistic words of all four rows are polled together (one round trip when
+  // phase 2, NB row steps at a time: the statistic words of all NB rows are polled together (one round trip when
   // they are there) and added per row in the canonical order (lane l: tiles l, l+16, ...; 16-lane xor tree); the row
-  // itself is read back from `hidden` (this thread's own store) in the same round trip
+  // itself is read back from `hidden` (this thread's own store) in the same round trip.  NB = 4 for forwards whose CTAs
+  // own several row steps; Jacobi-sized forwards (at most one row step per CTA) run the NB = 1 body - a quarter of the code,
+  // and this code runs cold every time
   float wt[8];
   unpack8(wraw, wt);
-  for (int it0 = split; it0 < njt; it0 += 4 * SPLITS) {
-    uint4 xr[4];
-    unsigned long long sw[4][MW];
+  auto phase2 = [&](auto nbtag) {
+  constexpr int NB = decltype(nbtag)::value;
+  for (int it0 = split; it0 < njt; it0 += NB * SPLITS) {
+    uint4 xr[NB];
+    unsigned long long sw[NB][MW];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NB; ++q) {
       const int j = (it0 + q * SPLITS) * 8 + trow;
       const int t = me + j * R;
       xr[q] = make_uint4(0u, 0u, 0u, 0u);
@@ -380,7 +385,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     for (;;) {
       bool ok = true;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < NB; ++q) {
         const int j = (it0 + q * SPLITS) * 8 + trow;
         if (j < cnt) {
           const unsigned long long* slots = c.row_ss + (size_t)(me + j * R) * kMaxHTiles;
@@ -390,7 +395,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < NB; ++q) {
         const int j = (it0 + q * SPLITS) * 8 + trow;
         if (j < cnt) {
 #pragma unroll
@@ -403,7 +408,7 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
     }
     prof_mark(c, w, 503);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NB; ++q) {
       const int it = it0 + q * SPLITS;
       const int j = it * 8 + trow;
       const int t = me + j * R;
@@ -440,6 +445,8 @@ __device__ __noinline__ void gemm_norm_tail_impl(const DevCtx& c, const WorkerSh
       }
     }
   }
+  };
+  if (njt <= SPLITS) phase2(std::integral_constant<int, 1>{}); else phase2(std::integral_constant<int, 4>{});
   prof_mark(c, w, 504);
   if (PUSH) {
     // phase 3: the rows the peers own arrive, finished, in this rank's staging buffer
