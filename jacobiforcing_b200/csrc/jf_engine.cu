@@ -306,6 +306,9 @@ extern "C" int jf_create(const jf_model_cfg* m, const jf_runtime_cfg* r, jf_hand
     c.fuse_rope = e6 ? atoi(e6) : 1;
     const char* e8 = getenv("JF_DATAFLOW_GD");
     c.dataflow_gd = e8 ? atoi(e8) : 1;
+    // the hand-over announces ONE gate/up tile per CTA (tile index == CTA index): models whose intermediate size needs more
+    // tiles than there are CTAs (> 148 x 128 features on one GPU) keep the grid barrier between gate/up and down
+    if (nt_i > h->num_ctas) c.dataflow_gd = 0;
     if (getenv("JF_DEBUG_HOSTBUF") && h->arena_mode == 2) {
       int* hb = nullptr;
       cudaHostAlloc(&hb, 4096 * sizeof(int), cudaHostAllocMapped);
